@@ -1,0 +1,148 @@
+/*
+ * sba_b200 -- C ABI of the B200-native bundle-adjustment hot path (libsba_b200.so).
+ *
+ * The reference (centreborelli/sat-bundleadjust) has no plugin API: its hot path is ordinary Python
+ * (bundle_adjust/ba_core.py) on top of scipy, plus ONE native boundary, the ctypes call into
+ * lib/disp_to_h.so (bundle_adjust/s2p/triangulation.py:107-118 -> c/disp_to_h.c:40-42).
+ * Each entry point below names the reference interface it replaces.  All functions return 0 on
+ * success or a negative SBA_E_* code; none of them calls exit().  Unless a parameter is documented
+ * as a device pointer, pointers are HOST pointers owned by the caller and host<->device copies
+ * happen inside the call.  A handle is bound to the CUDA device that was current at creation and to
+ * one CUDA stream; calls on the same handle must not overlap.
+ */
+#ifndef SBA_B200_H
+#define SBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBA_OK 0
+#define SBA_E_INVALID (-1)      /* bad argument / unsupported combination */
+#define SBA_E_CUDA (-2)         /* CUDA runtime error (sba_last_error() has the text) */
+#define SBA_E_NUMERIC (-3)      /* non-finite residuals at the initial point (scipy raises ValueError there) */
+#define SBA_E_NOMEM (-4)
+
+enum { SBA_MODEL_AFFINE = 0, SBA_MODEL_PERSPECTIVE = 1, SBA_MODEL_RPC = 2 };
+enum { SBA_LOSS_LINEAR = 0, SBA_LOSS_HUBER = 1, SBA_LOSS_SOFT_L1 = 2, SBA_LOSS_CAUCHY = 3, SBA_LOSS_ARCTAN = 4 };
+
+typedef struct sba_problem sba_problem;
+
+/* Problem description = the fields of the reference's BundleAdjustmentParameters that ba_core.fun
+ * reads (bundle_adjust/ba_params.py:78-181). */
+typedef struct sba_problem_desc {
+    int32_t cam_model;        /* SBA_MODEL_*                                   p.cam_model */
+    int32_t n_cam;            /* M                                             p.n_cam */
+    int32_t n_pts;            /* N (tracks held by this rank)                  p.n_pts */
+    int64_t n_obs;            /* K                                             p.n_obs */
+    int32_t n_params;         /* variables per camera: 3 | 5 | 6 | 8 | 11       p.n_params */
+    int32_t n_cam_params;     /* columns of cam_params: 8 | 11 | 9             p.cam_params.shape[1] */
+    int32_t n_cam_fix;        /* first n_cam_fix cameras are frozen            p.n_cam_fix */
+    int32_t n_pts_fix;        /* first n_pts_fix points are frozen             p.n_pts_fix */
+    const int64_t *cam_ind;   /* (K) camera of each observation                p.cam_ind */
+    const int64_t *pts_ind;   /* (K) track of each observation, non-decreasing p.pts_ind */
+    const double *pts2d;      /* (K,2) observed (col,row)                      p.pts2d */
+    const double *pts2d_w;    /* (K) observation weights                       p.pts2d_w */
+    const double *cam_params; /* (M, n_cam_params) initial camera parameters   p.cam_params */
+    const double *rpc_coefs;  /* (M, 90) RPC tables, NULL unless cam_model == RPC:
+                                 row_off col_off lat_off lon_off alt_off row_scl col_scl lat_scl lon_scl alt_scl,
+                                 row_num[20] row_den[20] col_num[20] col_den[20]   p.cameras[i] (rpcm.RPCModel) */
+    int32_t rpc_float32;      /* 1: round the RPC projection to float32 like ba_core.py:150 (fun parity) */
+    /* multi-GPU: this rank's position among the ranks that share the cameras; the tracks are sharded */
+    int32_t rank, world_size;
+} sba_problem_desc;
+
+/* Solver options = the reference's ls_params (bundle_adjust/ba_core.py:222-241) + scipy's gtol default */
+typedef struct sba_solve_opts {
+    int32_t loss;             /* SBA_LOSS_* */
+    double f_scale;
+    double ftol, xtol, gtol;  /* scipy.optimize.least_squares meanings */
+    int32_t max_nfev;         /* "max_iter" of the reference = max residual evaluations */
+    int32_t verbose;
+} sba_solve_opts;
+
+typedef struct sba_solve_info {
+    int32_t status;           /* scipy status: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 ftol+xtol */
+    int32_t nfev, njev;       /* residual evaluations / Jacobian (assembly) evaluations */
+    int32_t iterations;       /* outer trust-region iterations */
+    double cost_init, cost;   /* 0.5 * sum(rho) at x0 and at the solution */
+    double optimality;        /* ||J^T f||_inf at the solution */
+    double solve_ms;          /* device time of the iteration loop (CUDA events) */
+    int32_t chol_retries;     /* times the reduced camera system had to be re-damped */
+    int32_t gpu_launches;     /* kernels launched by this call */
+} sba_solve_info;
+
+/* Optional hook for the multi-GPU exchange step: must SUM `count` doubles at device pointer `buf`
+ * across all ranks, in place, enqueued on the handle's stream (e.g. torch.distributed.all_reduce). */
+typedef int (*sba_allreduce_fn)(void *user, double *device_buf, int64_t count);
+
+const char *sba_last_error(void);
+int sba_version(void);
+
+/* Replaces: the implicit set-up done on every ba_core.fun call (gathers cam_params[cam_ind], pts3d[pts_ind])
+ * and ba_core.build_jacobian_sparsity (ba_core.py:186-219).  `stream` is a cudaStream_t (0 = default). */
+int sba_problem_create(sba_problem **out, const sba_problem_desc *desc, void *stream);
+int sba_problem_destroy(sba_problem *p);
+int sba_problem_set_allreduce(sba_problem *p, sba_allreduce_fn fn, void *user);
+/* number of variables n = n_cam * n_params + 3 * n_pts */
+int64_t sba_problem_num_vars(const sba_problem *p);
+
+/* Replaces ba_core.fun(v, p) (ba_core.py:157-183): x (n) -> weighted residuals r (2K), interleaved.
+ * Also returns 0.5*sum(rho(r)) for the given loss in *cost (may be NULL). */
+int sba_residuals(sba_problem *p, const double *x, double *r, int32_t loss, double f_scale, double *cost);
+
+/* Jacobian pieces at x for tests: per-observation camera block (K,2,n_params), point block (K,2,3),
+ * both including observation weights but NOT the robust rescale.  Any output may be NULL. */
+int sba_jacobian_blocks(sba_problem *p, const double *x, double *Jc, double *Jp);
+
+/* Normal-equation blocks at x (robust rescale applied): U (M,c,c), V (N,6: xx xy xz yy yz zz), g (n). */
+int sba_normal_blocks(sba_problem *p, const double *x, int32_t loss, double f_scale, double *U, double *V, double *g);
+
+/* Replaces scipy.optimize.least_squares(fun, x0, jac_sparsity=A, x_scale='jac', method='trf', ...)
+ * as called by ba_core.run_ba_optimization (ba_core.py:284-297).
+ * x0 (n) in, x (n) out, r (2K) = un-scaled residuals at the solution (res.fun), may be NULL. */
+int sba_solve(sba_problem *p, const double *x0, const sba_solve_opts *opts, double *x, double *r, sba_solve_info *info);
+
+/* Same solve with x0 / x / r as DEVICE pointers (inputs already resident in HBM; nothing is copied
+ * to the host except the few scalars that steer the iteration). */
+int sba_solve_device(sba_problem *p, const double *x0_dev, const sba_solve_opts *opts, double *x_dev, double *r_dev,
+                     sba_solve_info *info);
+
+/* One fused residual + analytic Jacobian + robust weighting + J^T J / J^T r block assembly pass at the
+ * DEVICE vector x_dev, timed alone (bench: "Jacobian observations per second").  ms = device time. */
+int sba_assemble_device(sba_problem *p, const double *x_dev, int32_t loss, double f_scale, float *ms);
+
+/* Exact 2-D trust-region subproblem (host); replaces scipy/optimize/_lsq/common.py:171-219. */
+int sba_tr2d(const double B[4], const double g[2], double Delta, double p_out[2]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched RPC kernels (replace rpcm.RPCModel.projection / .localization and c/rpc.c).
+ * rpc: 90 doubles, layout as sba_problem_desc.rpc_coefs.  n points, arrays are (n) each.
+ * ---------------------------------------------------------------------------------------------- */
+/* c/rpc.c:442-452 eval_rpci / rpcm projection: (lon,lat,alt) -> (col,row) */
+int sba_rpc_projection(const double *rpc, const double *lon, const double *lat, const double *alt, int64_t n,
+                       double *col, double *row);
+/* cam_utils.apply_rpc_projection (cam_utils.py:217-231): ECEF (n,3) -> (n,2) incl. geo_utils.py:236-255 */
+int sba_rpc_projection_ecef(const double *rpc, const double *xyz, int64_t n, double *colrow);
+/* c/rpc.c:378-439 eval_rpc (iterative) / rpcm localization: (col,row,alt) -> (lon,lat); delta = first probe */
+int sba_rpc_localization(const double *rpc, const double *col, const double *row, const double *alt, int64_t n,
+                         double delta, double *lon, double *lat);
+
+/* The reference's one native entry point, same signature and struct layout (c/disp_to_h.c:40-42,
+ * c/rpc.h:14-32): two-view RPC triangulation of n_kp matches.  rpc_a / rpc_b point to `struct rpc`
+ * (181 doubles).  Runs batched on the GPU; buffers are host pointers like in the reference. */
+void stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, float *kp_a, float *kp_b, int n_kp,
+                                 void *rpc_a, void *rpc_b);
+int sba_stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, const float *kp_a, const float *kp_b, int64_t n_kp,
+                                    const void *rpc_a, const void *rpc_b);
+
+/* FP64 dense Cholesky solve of an n x n SPD system on the device (host buffers in/out), exposed for
+ * tests of the reduced-camera-system factorisation.  A is column-major, overwritten by L. */
+int sba_cholesky_solve(double *A, double *b, int32_t n, int32_t *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBA_B200_H */

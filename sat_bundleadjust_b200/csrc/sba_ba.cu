@@ -1,0 +1,705 @@
+// Host side of the bundle-adjustment hot path: problem set-up, kernel launches and the
+// trust-region (Levenberg-Marquardt type) iteration.
+//
+// The iteration reproduces scipy's `trf_no_bounds` (scipy/optimize/_lsq/trf.py:415-587), which is what
+// the reference runs through scipy.optimize.least_squares (bundle_adjust/ba_core.py:284-297), with two
+// changes: the Jacobian is analytic instead of 2-point finite differences, and the regularised
+// Gauss-Newton step  (J_h^T J_h + reg I) p = -g_h  is solved exactly through the Schur complement onto the
+// cameras + dense Cholesky instead of LSMR.  Everything else keeps scipy's definitions:
+//   * variables scaled by D = diag(max-so-far column norm of J)  (x_scale='jac', common.py:598-610)
+//   * damping  reg = -min_t q(-t g_h) / Delta^2  from the Cauchy step            (trf.py:485-490)
+//   * step from the exact 2-D trust-region problem in span{g_h, gn_h}           (trf.py:496-509)
+//   * Delta <- 0.25 |step| if ratio < 0.25 ; Delta <- 2 Delta if ratio > 0.75 and the step hit the
+//     boundary (common.py:222-245); initial Delta = |x0 * scale_inv|             (trf.py:443)
+//   * termination: dF < ftol F with ratio > 0.25 | |dx| < xtol (xtol + |x|) | |g|_inf < gtol |
+//     nfev == max_nfev                                                           (common.py:705-717)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sba_kernels.cuh"
+#include "sba_tr2d.h"
+
+namespace sba {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, cudaStream_t stream);
+
+static inline int grid_for(long long work, int threads, int max_blocks)
+{
+    long long b = (work + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+template <typename T>
+static int dev_alloc(T** ptr, size_t count)
+{
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    SBA_CUDA(cudaMalloc((void**)ptr, count * sizeof(T)));
+    return SBA_OK;
+}
+
+template <typename T>
+static int dev_upload(T** ptr, const std::vector<T>& h, cudaStream_t s)
+{
+    SBA_TRY(dev_alloc(ptr, h.size()));
+    if (!h.empty()) SBA_CUDA(cudaMemcpyAsync(*ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SBA_OK;
+}
+
+static bool valid_nc(int model, int nc)
+{
+    if (model == MODEL_PERSPECTIVE) return nc == 3 || nc == 6 || nc == 11;
+    if (model == MODEL_AFFINE) return nc == 3 || nc == 5 || nc == 8;
+    if (model == MODEL_RPC) return nc == 3 || nc == 6;
+    return false;
+}
+
+#define SBA_DISPATCH(p, MACRO)                                                          \
+    switch ((p)->model * 16 + (p)->nc) {                                                \
+    case MODEL_PERSPECTIVE * 16 + 3: MACRO(MODEL_PERSPECTIVE, 3); break;                \
+    case MODEL_PERSPECTIVE * 16 + 6: MACRO(MODEL_PERSPECTIVE, 6); break;                \
+    case MODEL_PERSPECTIVE * 16 + 11: MACRO(MODEL_PERSPECTIVE, 11); break;              \
+    case MODEL_AFFINE * 16 + 3: MACRO(MODEL_AFFINE, 3); break;                          \
+    case MODEL_AFFINE * 16 + 5: MACRO(MODEL_AFFINE, 5); break;                          \
+    case MODEL_AFFINE * 16 + 8: MACRO(MODEL_AFFINE, 8); break;                          \
+    case MODEL_RPC * 16 + 3: MACRO(MODEL_RPC, 3); break;                                \
+    case MODEL_RPC * 16 + 6: MACRO(MODEL_RPC, 6); break;                                \
+    default: set_error("unsupported (cam_model, n_params) combination"); return SBA_E_INVALID; \
+    }
+
+#define SBA_DISPATCH_MODEL(p, MACRO)                            \
+    switch ((p)->model) {                                       \
+    case MODEL_PERSPECTIVE: MACRO(MODEL_PERSPECTIVE); break;    \
+    case MODEL_AFFINE: MACRO(MODEL_AFFINE); break;              \
+    default: MACRO(MODEL_RPC); break;                           \
+    }
+
+static ObsArrays obs_arrays(const sba_problem* p)
+{
+    ObsArrays o;
+    o.cam_ind = p->cam_ind; o.pts_ind = p->pts_ind; o.pts2d = (const double2*)p->pts2d; o.w = p->w;
+    o.track_ptr = p->track_ptr;
+    return o;
+}
+
+static int check_launch(sba_problem* p)
+{
+    p->launches++;
+    SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int run_prepare(sba_problem* p, const double* x, double* camrec)
+{
+    k_prepare_cameras<<<grid_for(p->M, 128, 1 << 20), 128, 0, p->stream>>>(x, p->cam_static, camrec, p->M, p->P, p->nc,
+                                                                             p->n_cam_fix, p->model);
+    return check_launch(p);
+}
+
+static int run_residual(sba_problem* p, const double* x, const double* camrec, int loss, double f_scale, double* r_out,
+                        int slot, int rpc_f32)
+{
+    const int grid = grid_for(p->K, 256, NUM_SMS * 8);
+#define L(MODEL)                                                                                                  \
+    k_residual<MODEL><<<grid, 256, 0, p->stream>>>(obs_arrays(p), x + (size_t)p->M * p->nc, camrec, p->rpc_tab, p->K, \
+                                                   loss, f_scale, rpc_f32, (double2*)r_out, p->red_partials,       \
+                                                   p->counters + 0, p->scal, slot)
+    SBA_DISPATCH_MODEL(p, L);
+#undef L
+    return check_launch(p);
+}
+
+// fused residual + analytic Jacobian + robust weighting + block assembly at x (camrec must be prepared)
+static int run_assemble(sba_problem* p, const double* x, const double* camrec, int loss, double f_scale)
+{
+    const double* xp = x + (size_t)p->M * p->nc;
+    {
+        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+#define L(MODEL)                                                                                                      \
+    k_assemble_points<MODEL><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, camrec, p->rpc_tab, p->N, p->n_pts_fix, loss, \
+                                                          f_scale, p->V, p->g + (size_t)p->M * p->nc, p->red_partials,   \
+                                                          p->counters + 1, p->scal)
+        SBA_DISPATCH_MODEL(p, L);
+#undef L
+        SBA_TRY(check_launch(p));
+    }
+    {
+#define L(MODEL, NC)                                                                                                   \
+    k_assemble_cameras<MODEL, NC><<<p->chunks.n, TPB, 0, p->stream>>>(                                                \
+        p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_pts, (const double2*)p->cm_pts2d, p->cm_w, xp, camrec,      \
+        p->rpc_tab, p->n_cam_fix, loss, f_scale, p->cam_partials);                                                     \
+    SBA_TRY(check_launch(p));                                                                                          \
+    k_reduce_cameras<NC><<<p->M, 128, 0, p->stream>>>(p->cam_partials, p->cam_ptr /* first chunk table */, p->M,       \
+                                                      p->camsys_local)
+        SBA_DISPATCH(p, L);
+#undef L
+        SBA_TRY(check_launch(p));
+    }
+    if (p->world > 1) {
+        const size_t cnt = (size_t)p->M * p->nc * p->nc + (size_t)p->M * p->nc;
+        SBA_CUDA(cudaMemcpyAsync(p->camsys, p->camsys_local, cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        if (p->allreduce(p->allreduce_user, p->camsys, (int64_t)cnt) != 0) {
+            set_error("allreduce callback failed");
+            return SBA_E_INVALID;
+        }
+    }
+    return SBA_OK;
+}
+
+static int allreduce_scal(sba_problem* p, int first, int count)
+{
+    if (p->world <= 1) return SBA_OK;
+    if (p->allreduce(p->allreduce_user, p->scal + first, count) != 0) {
+        set_error("allreduce callback failed");
+        return SBA_E_INVALID;
+    }
+    return SBA_OK;
+}
+
+static int fetch_scal(sba_problem* p)
+{
+    SBA_CUDA(cudaMemcpyAsync(p->h_scal, p->scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
+static int run_scale_dots(sba_problem* p, int first)
+{
+    SBA_CUDA(cudaMemsetAsync(p->scal + SC_GMAX_SLOTS, 0, 16 * sizeof(double), p->stream));
+    const int grid = grid_for(p->n, 256, NUM_SMS * 8);
+    k_scale_dots<<<grid, 256, 0, p->stream>>>(p->camsys, p->V, p->x, p->g, p->sinv, p->t1, p->n, p->M * p->nc, p->nc, p->M,
+                                              first, p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal);
+    return check_launch(p);
+}
+
+static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out)
+{
+    const int grid = grid_for(p->K, TPB, NUM_SMS * 16);
+#define L(MODEL, NC)                                                                                                  \
+    if (nvec == 1)                                                                                                    \
+        k_jvp<MODEL, NC, 1><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->x + (size_t)p->M * p->nc, p->camrec,        \
+                                                         p->rpc_tab, p->K, p->M * p->nc, p->n_cam_fix, p->n_pts_fix,   \
+                                                         loss, f_scale, p->t1, p->t2, p->red_partials,                 \
+                                                         p->counters + 3, p->scal, out);                               \
+    else                                                                                                              \
+        k_jvp<MODEL, NC, 2><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->x + (size_t)p->M * p->nc, p->camrec,        \
+                                                         p->rpc_tab, p->K, p->M * p->nc, p->n_cam_fix, p->n_pts_fix,   \
+                                                         loss, f_scale, p->t1, p->t2, p->red_partials,                 \
+                                                         p->counters + 3, p->scal, out)
+    SBA_DISPATCH(p, L);
+#undef L
+    return check_launch(p);
+}
+
+// Schur complement + Cholesky solve + back-substitution for a given damping `reg`
+static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, double reg)
+{
+    const int ns = p->M * p->nc;
+    const double* xp = p->x + (size_t)ns;
+    SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
+    {
+        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+#define L(MODEL, NC)                                                                                                    \
+    k_point_prep<MODEL, NC><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, p->camrec, p->rpc_tab, p->N, ns, p->n_cam_fix, \
+                                                         p->n_pts_fix, loss, f_scale, reg, p->V, p->g, p->sinv, p->F,    \
+                                                         p->q, p->Z, p->scal)
+        SBA_DISPATCH(p, L);
+#undef L
+        SBA_TRY(check_launch(p));
+    }
+    {
+#define SCHUR_ARGS                                                                                                     \
+    p->si_j, p->si_jp, p->si_chunk, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->Z, p->q,   \
+        p->schur_partials
+        switch (p->nc) {
+        case 3: k_schur<3, 0, 3><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 5: k_schur<5, 0, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 6: k_schur<6, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 8: k_schur<8, 0, 8><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 11:
+            k_schur<11, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            SBA_TRY(check_launch(p));
+            k_schur<11, 6, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            break;
+        default: set_error("bad nc"); return SBA_E_INVALID;
+        }
+        SBA_TRY(check_launch(p));
+#undef SCHUR_ARGS
+#define FIN_ARGS                                                                                                  \
+    p->schur_partials, p->sb_first, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, reg, p->rank == 0, p->S
+        switch (p->nc) {
+        case 3: k_schur_finalize<3><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
+        case 5: k_schur_finalize<5><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
+        case 6: k_schur_finalize<6><<<p->n_schur_blocks, 64, 0, p->stream>>>(FIN_ARGS); break;
+        case 8: k_schur_finalize<8><<<p->n_schur_blocks, 96, 0, p->stream>>>(FIN_ARGS); break;
+        default: k_schur_finalize<11><<<p->n_schur_blocks, 160, 0, p->stream>>>(FIN_ARGS); break;
+        }
+        SBA_TRY(check_launch(p));
+#undef FIN_ARGS
+    }
+    if (p->world > 1) {
+        if (p->allreduce(p->allreduce_user, p->S, (int64_t)ns * ns + ns) != 0) {
+            set_error("allreduce callback failed");
+            return SBA_E_INVALID;
+        }
+    }
+    SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->stream));
+    p->launches++;
+    {
+        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+        switch (p->nc) {
+        case 3: k_backsub<3><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        case 5: k_backsub<5><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        case 6: k_backsub<6><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        case 8: k_backsub<8><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        default: k_backsub<11><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        }
+        SBA_TRY(check_launch(p));
+    }
+    return SBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the iteration
+// ------------------------------------------------------------------------------------------------
+static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_info* info)
+{
+    const int loss = o->loss;
+    const double fs = o->f_scale;
+    const int ns = p->M * p->nc;
+    const int elem_grid = grid_for(p->n, 256, NUM_SMS * 8);
+    std::memset(info, 0, sizeof(*info));
+    if (o->max_nfev < 1) { set_error("max_nfev must be >= 1"); return SBA_E_INVALID; }
+    p->launches = 0;
+    SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), p->stream));
+    SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
+
+    SBA_TRY(run_prepare(p, p->x, p->camrec));
+    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
+    int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0;
+    double cost = 0.0, Delta = 0.0, g_norm = 0.0;
+    bool first = true;
+
+    while (true) {
+        SBA_TRY(run_scale_dots(p, first ? 1 : 0));
+        Slots sa; sa.s[0] = SC_A; sa.s[1] = SC_SCRATCH; sa.s[2] = SC_SCRATCH;
+        SBA_TRY(run_jvp(p, loss, fs, 1, sa));
+        SBA_TRY(allreduce_scal(p, SC_COST, SC_GGN - SC_COST));
+        SBA_TRY(fetch_scal(p));
+        const double* h = p->h_scal;
+        if (first) {
+            cost = h[SC_COST];
+            if (!std::isfinite(cost)) { set_error("Residuals are not finite in the initial point."); return SBA_E_NUMERIC; }
+            info->cost_init = cost;
+            Delta = std::sqrt(h[SC_XS]);
+            if (Delta == 0.0) Delta = 1.0;
+            first = false;
+        }
+        const double gg = h[SC_GG], x_norm = std::sqrt(h[SC_XX]);
+        g_norm = 0.0;
+        for (int r = 0; r < 16; ++r) g_norm = std::max(g_norm, h[SC_GMAX_SLOTS + r]);
+        if (g_norm < o->gtol) status = 1;
+        if (o->verbose >= 2)
+            printf("[sba] it %3d nfev %3d cost %.10e |g|inf %.3e Delta %.3e\n", iteration, nfev, cost, g_norm, Delta);
+        if (status >= 0 || nfev >= o->max_nfev) break;
+
+        // damping from the Cauchy step (trf.py:485-490; build_quadratic_1d / minimize_quadratic_1d)
+        const double qa = 0.5 * h[SC_A], qb = -gg;
+        const double to_tr = Delta / std::sqrt(gg);
+        double ag_value = 0.0;   // t = 0
+        ag_value = std::min(ag_value, to_tr * (qa * to_tr + qb));
+        if (qa != 0.0) {
+            const double ext = -0.5 * qb / qa;
+            if (ext > 0.0 && ext < to_tr) ag_value = std::min(ag_value, ext * (qa * ext + qb));
+        }
+        double reg = -ag_value / (Delta * Delta);
+
+        // Gauss-Newton step of the damped system, second basis vector, and B_S (one host sync)
+        double ggn = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
+        for (int attempt = 0;; ++attempt) {
+            SBA_TRY(run_gauss_newton_step(p, loss, fs, reg));
+            k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->delta, p->n, ns, p->rank == 0, p->red_partials,
+                                                            p->counters + 4, p->scal);
+            SBA_TRY(check_launch(p));
+            SBA_TRY(allreduce_scal(p, SC_GGN, 1));
+            k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
+                                                         p->red_partials, p->counters + 5, p->scal);
+            SBA_TRY(check_launch(p));
+            Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
+            SBA_TRY(run_jvp(p, loss, fs, 2, sb));
+            SBA_TRY(allreduce_scal(p, SC_WW, SC_COST_NEW - SC_WW));
+            SBA_TRY(fetch_scal(p));
+            h = p->h_scal;
+            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_B22]);
+            if (!failed) break;
+            if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
+            // re-damp: J_h has unit column norms, so reg is relative to 1
+            reg = std::max(reg * 10.0, 1e-12);
+            ++chol_retries;
+        }
+        ggn = h[SC_GGN]; ww = h[SC_WW]; wg = h[SC_WG]; t11 = h[SC_T11]; t12 = h[SC_T12]; t22 = h[SC_T22];
+        b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
+        (void)ggn;
+        // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|
+        const double n1 = std::sqrt(gg);
+        const bool rank2 = ww > 1e-30 * std::max(t22, 1e-300) && ww > 0.0;
+        const double n2 = rank2 ? std::sqrt(ww) : 1.0;
+        double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
+        double gS0 = n1, gS1 = rank2 ? wg / n2 : 0.0;
+
+        double actual_reduction = -1.0, cost_new = cost, step_norm = 0.0;
+        int term = -1;
+        while (actual_reduction <= 0.0 && nfev < o->max_nfev) {
+            double pS[2];
+            solve_trust_region_2d(B00, B01, B11, gS0, gS1, Delta, pS);
+            const double predicted = -(0.5 * (B00 * pS[0] * pS[0] + 2.0 * B01 * pS[0] * pS[1] + B11 * pS[1] * pS[1]) +
+                                       gS0 * pS[0] + gS1 * pS[1]);
+            const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
+            const double step_h_norm = std::sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
+            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, c1, c2, p->x_new, p->n);
+            SBA_TRY(check_launch(p));
+            SBA_TRY(run_prepare(p, p->x_new, p->camrec_new));
+            SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
+            SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
+            SBA_TRY(fetch_scal(p));
+            ++nfev;
+            cost_new = p->h_scal[SC_COST_NEW];
+            if (!std::isfinite(cost_new)) { Delta = 0.25 * step_h_norm; continue; }
+            actual_reduction = cost - cost_new;
+            // update_tr_radius (common.py:222-245)
+            double ratio;
+            if (predicted > 0.0) ratio = actual_reduction / predicted;
+            else if (predicted == 0.0 && actual_reduction == 0.0) ratio = 1.0;
+            else ratio = 0.0;
+            double Delta_new = Delta;
+            if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
+            else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
+            step_norm = std::sqrt(std::max(0.0, c1 * c1 * t11 + 2.0 * c1 * c2 * t12 + c2 * c2 * t22));
+            // check_termination (common.py:705-717)
+            const bool ftol_ok = actual_reduction < o->ftol * cost && ratio > 0.25;
+            const bool xtol_ok = step_norm < o->xtol * (o->xtol + x_norm);
+            if (ftol_ok && xtol_ok) term = 4; else if (ftol_ok) term = 2; else if (xtol_ok) term = 3;
+            if (term >= 0) break;
+            Delta = Delta_new;
+        }
+        if (actual_reduction > 0.0) {
+            std::swap(p->x, p->x_new);
+            std::swap(p->camrec, p->camrec_new);
+            cost = cost_new;
+            if (term < 0) {
+                SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
+                ++njev;
+            }
+        }
+        ++iteration;
+        if (term >= 0) { status = term; break; }
+    }
+    if (status < 0) status = 0;
+    SBA_CUDA(cudaEventRecord(p->ev1, p->stream));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0.f;
+    SBA_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    info->status = status; info->nfev = nfev; info->njev = njev; info->iterations = iteration;
+    info->cost = cost; info->optimality = g_norm; info->solve_ms = ms; info->chol_retries = chol_retries;
+    info->gpu_launches = p->launches;
+    return SBA_OK;
+}
+
+}  // namespace sba
+
+using namespace sba;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: problem life cycle
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* sba_last_error(void) { return g_error.c_str(); }
+extern "C" int sba_version(void) { return 100; }
+
+extern "C" int sba_problem_destroy(sba_problem* p)
+{
+    if (!p) return SBA_OK;
+    cudaSetDevice(p->device);
+    void* ptrs[] = {p->cam_ind, p->pts_ind, p->track_ptr, p->pts2d, p->w, p->cam_static, p->rpc_tab, p->cm_obs, p->cm_pts,
+                    p->cam_ptr, p->obs_of, p->cm_pts2d, p->cm_w, p->chunks.cam, p->chunks.beg, p->chunks.end, p->si_j,
+                    p->si_jp, p->si_chunk, p->sb_first, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
+                    p->t2, p->camrec, p->camrec_new, p->V, p->F, p->q, p->Z, p->camsys_local, p->S, p->cam_partials,
+                    p->schur_partials, p->red_partials, p->counters, p->scal, p->r_out, p->io_x};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (p->camsys && p->camsys != p->camsys_local) cudaFree(p->camsys);
+    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+    return SBA_OK;
+}
+
+static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
+{
+    const int M = p->M, N = p->N, nc = p->nc;
+    const int64_t K = p->K;
+    cudaStream_t s = p->stream;
+    // --- indices: int64 -> int32, track offsets, camera-major order (host, O(K)) ---
+    std::vector<int> cam(K), pts(K), track_ptr(N + 1, 0), cam_cnt(M + 1, 0);
+    for (int64_t a = 0; a < K; ++a) {
+        const int64_t c = d->cam_ind[a], t = d->pts_ind[a];
+        if (c < 0 || c >= M || t < 0 || t >= N) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
+        if (a > 0 && t < d->pts_ind[a - 1]) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
+        cam[a] = (int)c; pts[a] = (int)t;
+        track_ptr[t + 1]++;
+        cam_cnt[c + 1]++;
+    }
+    for (int i = 0; i < N; ++i) track_ptr[i + 1] += track_ptr[i];
+    for (int j = 0; j < M; ++j) cam_cnt[j + 1] += cam_cnt[j];
+    std::vector<int> cm_obs(K), cm_pts(K), fill(cam_cnt.begin(), cam_cnt.end() - 1);
+    std::vector<double> cm_pts2d(2 * K), cm_w(K);
+    for (int64_t a = 0; a < K; ++a) {
+        const int t = fill[cam[a]]++;
+        cm_obs[t] = (int)a; cm_pts[t] = pts[a];
+        cm_pts2d[2 * (size_t)t] = d->pts2d[2 * a]; cm_pts2d[2 * (size_t)t + 1] = d->pts2d[2 * a + 1];
+        cm_w[t] = d->pts2d_w[a];
+    }
+    // chunk table (camera-major work items)
+    std::vector<int> ch_cam, ch_beg, ch_end, first_chunk(M + 1, 0);
+    for (int j = 0; j < M; ++j) {
+        first_chunk[j] = (int)ch_cam.size();
+        for (int b = cam_cnt[j]; b < cam_cnt[j + 1]; b += CHUNK) {
+            ch_cam.push_back(j); ch_beg.push_back(b); ch_end.push_back(std::min(b + CHUNK, cam_cnt[j + 1]));
+        }
+    }
+    first_chunk[M] = (int)ch_cam.size();
+    p->chunks.n = (int)ch_cam.size();
+    p->chunks.h_cam = ch_cam;
+    p->chunks.h_first_of_cam = first_chunk;
+    // Schur work items: blocks (j <= j') x chunks of camera j
+    std::vector<int> si_j, si_jp, si_chunk, sb_first, sb_j, sb_jp;
+    for (int j = 0; j < M; ++j)
+        for (int jp = j; jp < M; ++jp) {
+            sb_first.push_back((int)si_j.size()); sb_j.push_back(j); sb_jp.push_back(jp);
+            for (int c = first_chunk[j]; c < first_chunk[j + 1]; ++c) { si_j.push_back(j); si_jp.push_back(jp); si_chunk.push_back(c); }
+        }
+    sb_first.push_back((int)si_j.size());
+    p->n_schur_items = (int)si_j.size();
+    p->n_schur_blocks = (int)sb_j.size();
+
+    SBA_TRY(dev_upload(&p->cam_ind, cam, s));
+    SBA_TRY(dev_upload(&p->pts_ind, pts, s));
+    SBA_TRY(dev_upload(&p->track_ptr, track_ptr, s));
+    SBA_TRY(dev_upload(&p->cm_obs, cm_obs, s));
+    SBA_TRY(dev_upload(&p->cm_pts, cm_pts, s));
+    SBA_TRY(dev_upload(&p->cm_pts2d, cm_pts2d, s));
+    SBA_TRY(dev_upload(&p->cm_w, cm_w, s));
+    SBA_TRY(dev_upload(&p->cam_ptr, first_chunk, s));   // camera -> first chunk (used by k_reduce_cameras)
+    SBA_TRY(dev_upload(&p->chunks.cam, ch_cam, s));
+    SBA_TRY(dev_upload(&p->chunks.beg, ch_beg, s));
+    SBA_TRY(dev_upload(&p->chunks.end, ch_end, s));
+    SBA_TRY(dev_upload(&p->si_j, si_j, s));
+    SBA_TRY(dev_upload(&p->si_jp, si_jp, s));
+    SBA_TRY(dev_upload(&p->si_chunk, si_chunk, s));
+    SBA_TRY(dev_upload(&p->sb_first, sb_first, s));
+    SBA_TRY(dev_upload(&p->sb_j, sb_j, s));
+    SBA_TRY(dev_upload(&p->sb_jp, sb_jp, s));
+
+    SBA_TRY(dev_alloc(&p->pts2d, 2 * (size_t)K));
+    SBA_CUDA(cudaMemcpyAsync(p->pts2d, d->pts2d, 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+    SBA_TRY(dev_alloc(&p->w, (size_t)K));
+    SBA_CUDA(cudaMemcpyAsync(p->w, d->pts2d_w, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+    SBA_TRY(dev_alloc(&p->cam_static, (size_t)M * p->P));
+    SBA_CUDA(cudaMemcpyAsync(p->cam_static, d->cam_params, (size_t)M * p->P * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (p->model == MODEL_RPC) {
+        SBA_TRY(dev_alloc(&p->rpc_tab, (size_t)M * RPC_TAB_STRIDE));
+        SBA_CUDA(cudaMemcpyAsync(p->rpc_tab, d->rpc_coefs, (size_t)M * RPC_TAB_STRIDE * sizeof(double),
+                                 cudaMemcpyHostToDevice, s));
+    }
+    SBA_TRY(dev_alloc(&p->obs_of, (size_t)M * N));
+    SBA_CUDA(cudaMemsetAsync(p->obs_of, 0xFF, (size_t)M * N * sizeof(int), s));
+    k_fill_obs_of<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cam_ind, p->pts_ind, K, N, p->obs_of);
+    SBA_CUDA(cudaGetLastError());
+
+    // --- iteration state ---
+    const size_t n = (size_t)p->n, ns = (size_t)M * nc;
+    SBA_TRY(dev_alloc(&p->x, n)); SBA_TRY(dev_alloc(&p->x_new, n)); SBA_TRY(dev_alloc(&p->g, n));
+    SBA_TRY(dev_alloc(&p->sinv, n)); SBA_TRY(dev_alloc(&p->delta, n)); SBA_TRY(dev_alloc(&p->t1, n));
+    SBA_TRY(dev_alloc(&p->t2, n)); SBA_TRY(dev_alloc(&p->io_x, n));
+    SBA_TRY(dev_alloc(&p->camrec, (size_t)M * CAMREC_STRIDE)); SBA_TRY(dev_alloc(&p->camrec_new, (size_t)M * CAMREC_STRIDE));
+    SBA_TRY(dev_alloc(&p->V, 6 * (size_t)N)); SBA_TRY(dev_alloc(&p->F, 6 * (size_t)N)); SBA_TRY(dev_alloc(&p->q, 3 * (size_t)N));
+    SBA_TRY(dev_alloc(&p->Z, (size_t)K * nc * 3));
+    SBA_TRY(dev_alloc(&p->camsys_local, ns * nc + ns));
+    if (p->world > 1) SBA_TRY(dev_alloc(&p->camsys, ns * nc + ns));
+    else p->camsys = p->camsys_local;
+    SBA_TRY(dev_alloc(&p->S, ns * ns + ns));
+    const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
+    SBA_TRY(dev_alloc(&p->cam_partials, (size_t)p->chunks.n * nv_cam));
+    SBA_TRY(dev_alloc(&p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));
+    SBA_CUDA(cudaMemsetAsync(p->schur_partials, 0, (size_t)p->n_schur_items * (nc * nc + nc) * sizeof(double), s));
+    SBA_TRY(dev_alloc(&p->red_partials, (size_t)NUM_SMS * 16 * 8));
+    SBA_TRY(dev_alloc(&p->counters, 16));
+    SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));
+    SBA_TRY(dev_alloc(&p->scal, SC_COUNT));
+    SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), s));
+    SBA_CUDA(cudaMallocHost((void**)&p->h_scal, SC_COUNT * sizeof(double)));
+    SBA_TRY(dev_alloc(&p->r_out, 2 * (size_t)K));
+    SBA_CUDA(cudaEventCreate(&p->ev0));
+    SBA_CUDA(cudaEventCreate(&p->ev1));
+    SBA_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope
+    return SBA_OK;
+}
+
+extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, void* stream)
+{
+    if (!out || !d) { set_error("null argument"); return SBA_E_INVALID; }
+    *out = nullptr;
+    if (d->n_cam < 1 || d->n_pts < 1 || d->n_obs < 1 || d->n_obs > 2000000000LL) { set_error("empty or oversized problem"); return SBA_E_INVALID; }
+    if (!valid_nc(d->cam_model, d->n_params)) { set_error("unsupported (cam_model, n_params) combination"); return SBA_E_INVALID; }
+    const int P = d->cam_model == MODEL_AFFINE ? 8 : (d->cam_model == MODEL_PERSPECTIVE ? 11 : 9);
+    if (d->n_cam_params != P) { set_error("cam_params has the wrong number of columns for this camera model"); return SBA_E_INVALID; }
+    if (d->cam_model == MODEL_RPC && !d->rpc_coefs) { set_error("rpc_coefs required for cam_model rpc"); return SBA_E_INVALID; }
+    if (!d->cam_ind || !d->pts_ind || !d->pts2d || !d->pts2d_w || !d->cam_params) { set_error("null array"); return SBA_E_INVALID; }
+    if (d->n_cam_fix < 0 || d->n_cam_fix > d->n_cam || d->n_pts_fix < 0 || d->n_pts_fix > d->n_pts) { set_error("bad n_cam_fix / n_pts_fix"); return SBA_E_INVALID; }
+    if (d->world_size < 1 || d->world_size > 16 || d->rank < 0 || d->rank >= d->world_size) { set_error("bad rank / world_size"); return SBA_E_INVALID; }
+    if ((double)d->n_cam * d->n_pts > 1.5e9) { set_error("n_cam * n_pts too large for the dense (camera, track) table; use the matrix-free path"); return SBA_E_INVALID; }
+    if ((int64_t)d->n_cam * d->n_params > 4096) { set_error("reduced camera system larger than 4096: use the matrix-free path"); return SBA_E_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: sat_bundleadjust_b200 has no CPU fallback");
+        return SBA_E_CUDA;
+    }
+    sba_problem* p = new sba_problem();
+    p->model = d->cam_model; p->M = d->n_cam; p->N = d->n_pts; p->K = d->n_obs; p->nc = d->n_params; p->P = P;
+    p->n_cam_fix = d->n_cam_fix; p->n_pts_fix = d->n_pts_fix; p->rpc_f32 = d->rpc_float32;
+    p->rank = d->rank; p->world = d->world_size;
+    p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
+    p->stream = (cudaStream_t)stream;
+    cudaGetDevice(&p->device);
+    const int rc = problem_create_impl(p, d);
+    if (rc != SBA_OK) { sba_problem_destroy(p); return rc; }
+    *out = p;
+    return SBA_OK;
+}
+
+extern "C" int sba_problem_set_allreduce(sba_problem* p, sba_allreduce_fn fn, void* user)
+{
+    if (!p) return SBA_E_INVALID;
+    p->allreduce = fn; p->allreduce_user = user;
+    return SBA_OK;
+}
+
+extern "C" int64_t sba_problem_num_vars(const sba_problem* p) { return p ? p->n : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: evaluation entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int sba_residuals(sba_problem* p, const double* x, double* r, int32_t loss, double f_scale, double* cost)
+{
+    if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
+    SBA_TRY(run_residual(p, p->io_x, p->camrec_new, loss, f_scale, p->r_out, SC_COST_NEW, p->rpc_f32));
+    if (r) SBA_CUDA(cudaMemcpyAsync(r, p->r_out, 2 * (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_TRY(fetch_scal(p));
+    if (cost) *cost = p->h_scal[SC_COST_NEW];
+    return SBA_OK;
+}
+
+extern "C" int sba_jacobian_blocks(sba_problem* p, const double* x, double* Jc, double* Jp)
+{
+    if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
+    double *dJc = nullptr, *dJp = nullptr;
+    if (Jc) SBA_TRY(dev_alloc(&dJc, (size_t)p->K * 2 * p->nc));
+    if (Jp) SBA_TRY(dev_alloc(&dJp, (size_t)p->K * 6));
+    const int grid = grid_for(p->K, 128, NUM_SMS * 16);
+#define L(MODEL, NC)                                                                                               \
+    k_jac_blocks<MODEL, NC><<<grid, 128, 0, p->stream>>>(obs_arrays(p), p->io_x + (size_t)p->M * p->nc, p->camrec_new, \
+                                                         p->rpc_tab, p->K, p->n_cam_fix, p->n_pts_fix, dJc, dJp)
+    SBA_DISPATCH(p, L);
+#undef L
+    SBA_TRY(check_launch(p));
+    if (Jc) SBA_CUDA(cudaMemcpyAsync(Jc, dJc, (size_t)p->K * 2 * p->nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (Jp) SBA_CUDA(cudaMemcpyAsync(Jp, dJp, (size_t)p->K * 6 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    if (dJc) cudaFree(dJc);
+    if (dJp) cudaFree(dJp);
+    return SBA_OK;
+}
+
+extern "C" int sba_normal_blocks(sba_problem* p, const double* x, int32_t loss, double f_scale, double* U, double* V,
+                                 double* g)
+{
+    if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    const size_t ns = (size_t)p->M * p->nc;
+    SBA_CUDA(cudaMemcpyAsync(p->x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    SBA_TRY(run_prepare(p, p->x, p->camrec));
+    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
+    if (U) SBA_CUDA(cudaMemcpyAsync(U, p->camsys, ns * p->nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (V) SBA_CUDA(cudaMemcpyAsync(V, p->V, 6 * (size_t)p->N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (g) {
+        SBA_CUDA(cudaMemcpyAsync(g, p->camsys + ns * p->nc, ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        SBA_CUDA(cudaMemcpyAsync(g + ns, p->g + ns, 3 * (size_t)p->N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
+extern "C" int sba_solve_device(sba_problem* p, const double* x0_dev, const sba_solve_opts* opts, double* x_dev,
+                                double* r_dev, sba_solve_info* info)
+{
+    if (!p || !x0_dev || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
+    if (p->world > 1 && !p->allreduce) { set_error("world_size > 1 needs sba_problem_set_allreduce"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    SBA_CUDA(cudaMemcpyAsync(p->x, x0_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    SBA_TRY(solve_on_device(p, opts, info));
+    if (x_dev) SBA_CUDA(cudaMemcpyAsync(x_dev, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (r_dev) {
+        SBA_TRY(run_residual(p, p->x, p->camrec, SBA_LOSS_LINEAR, 1.0, r_dev, SC_SCRATCH, p->rpc_f32));
+        info->gpu_launches = p->launches;
+    }
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
+extern "C" int sba_solve(sba_problem* p, const double* x0, const sba_solve_opts* opts, double* x, double* r,
+                         sba_solve_info* info)
+{
+    if (!p || !x0 || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    SBA_CUDA(cudaMemcpyAsync(p->io_x, x0, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    SBA_TRY(sba_solve_device(p, p->io_x, opts, nullptr, r ? p->r_out : nullptr, info));
+    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (r) SBA_CUDA(cudaMemcpyAsync(r, p->r_out, 2 * (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
+extern "C" int sba_assemble_device(sba_problem* p, const double* x_dev, int32_t loss, double f_scale, float* ms)
+{
+    if (!p || !x_dev) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    SBA_CUDA(cudaMemcpyAsync(p->x, x_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    SBA_TRY(run_prepare(p, p->x, p->camrec));
+    SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
+    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
+    SBA_CUDA(cudaEventRecord(p->ev1, p->stream));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    float t = 0.f;
+    SBA_CUDA(cudaEventElapsedTime(&t, p->ev0, p->ev1));
+    if (ms) *ms = t;
+    return SBA_OK;
+}
+
+extern "C" int sba_tr2d(const double B[4], const double g[2], double Delta, double p_out[2])
+{
+    return sba::solve_trust_region_2d(B[0], B[1], B[3], g[0], g[1], Delta, p_out) ? 1 : 0;
+}

@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libsba_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sba_b200.h"
+#include "sba_models.cuh"
+
+namespace sba {
+
+void set_error(const std::string& msg);
+
+#define SBA_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::sba::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                             std::to_string(__LINE__) + ")");                                       \
+            return SBA_E_CUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+#define SBA_TRY(expr)                \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != SBA_OK) return _r; \
+    } while (0)
+
+constexpr int NUM_SMS = 148;   // B200
+
+// ---- scalar block (device, mirrored to pinned host memory) --------------------------------------
+// Grouped so that every multi-GPU exchange is one contiguous SUM all-reduce.
+enum Scal {
+    // group A (SUM over ranks): after assembly + scale update + first J*v
+    SC_COST = 0,          // 0.5 sum rho at x (assembly pass)
+    SC_GG,                // |g_h|^2
+    SC_XS,                // |x * scale_inv|^2
+    SC_XX,                // |x|^2
+    SC_A,                 // |J_h g_h|^2
+    SC_GMAX_SLOTS,        // max |g|, one slot per rank (16 slots), combined on the host
+    // group B
+    SC_GGN = SC_GMAX_SLOTS + 16,   // g_h . gn_h
+    // group C: after the second basis vector and J*[t1 t2]
+    SC_WW, SC_WG, SC_T11, SC_T12, SC_T22, SC_B11, SC_B12, SC_B22,
+    // group D
+    SC_COST_NEW,
+    // local diagnostics (never reduced)
+    SC_BAD_POINTS,        // points whose damped 3x3 block was not positive definite
+    SC_CHOL_FAIL,         // reduced camera system factorisation failed (pivot index + 1)
+    SC_SCRATCH,
+    SC_COUNT
+};
+
+struct ChunkTable {          // camera-major work items
+    int n = 0;
+    int* cam = nullptr;      // device
+    int* beg = nullptr;
+    int* end = nullptr;
+    std::vector<int> h_cam, h_first_of_cam;   // host: chunk -> camera ; camera -> first chunk (size M+1)
+};
+
+}  // namespace sba
+
+struct sba_problem {
+    // description
+    int model = 0, M = 0, N = 0, nc = 0, P = 0, n_cam_fix = 0, n_pts_fix = 0, rpc_f32 = 0;
+    int64_t K = 0;
+    int64_t n = 0;           // number of variables
+    int rank = 0, world = 1;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    sba_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+
+    // static device data, track-major (the reference's observation order)
+    int *cam_ind = nullptr, *pts_ind = nullptr, *track_ptr = nullptr;
+    double *pts2d = nullptr, *w = nullptr, *cam_static = nullptr, *rpc_tab = nullptr;
+    // static device data, camera-major copy
+    int *cm_obs = nullptr, *cm_pts = nullptr, *cam_ptr = nullptr, *obs_of = nullptr;
+    double *cm_pts2d = nullptr, *cm_w = nullptr;
+    sba::ChunkTable chunks;
+    int n_schur_items = 0;   // (j, j', chunk) work items
+    int *si_j = nullptr, *si_jp = nullptr, *si_chunk = nullptr;                         // device: work items
+    int *sb_first = nullptr, *sb_j = nullptr, *sb_jp = nullptr;                          // device: (j,j') blocks
+    int n_schur_blocks = 0;
+
+    // iteration state (device)
+    double *x = nullptr, *x_new = nullptr, *g = nullptr, *sinv = nullptr, *delta = nullptr, *t1 = nullptr, *t2 = nullptr;
+    double *camrec = nullptr, *camrec_new = nullptr;
+    double *V = nullptr, *F = nullptr, *q = nullptr, *Z = nullptr;
+    double *camsys_local = nullptr, *camsys = nullptr;     // [U (M*nc*nc) | g_c (M*nc)]
+    double *S = nullptr;                                   // [S (ns*ns) | rhs (ns)], ns = M*nc
+    double *cam_partials = nullptr, *schur_partials = nullptr, *red_partials = nullptr;
+    unsigned* counters = nullptr;
+    double* scal = nullptr;          // device scalar block
+    double* h_scal = nullptr;        // pinned host mirror
+    double* r_out = nullptr;         // (2K) residual output buffer
+    double *io_x = nullptr;          // (n) staging for host-pointer entry points
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int launches = 0;
+};

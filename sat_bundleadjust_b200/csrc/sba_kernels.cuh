@@ -1,0 +1,675 @@
+// Device kernels of the bundle-adjustment hot path (sm_100a).  Included by sba_ba.cu only.
+//
+// Data layout in HBM (all FP64 values, int32 indices):
+//   track-major (the reference's observation order, bundle_adjust/ba_params.py:138-149):
+//       cam_ind[K], pts_ind[K], pts2d[K] (double2), w[K], track_ptr[N+1]
+//   camera-major copy (static, built once): cm_obs[K] (observation id), cm_pts[K], cm_pts2d[K], cm_w[K],
+//       cam_ptr[M+1]; chunk table = (camera, [beg,end)) work items of <= CHUNK observations
+//   obs_of[M][N]: observation id of (camera, track) or -1
+//   variables x[n] = [camera blocks M*nc | points 3N]  (bundle_adjust/ba_params.py:151-173)
+//   camrec[M][16]: per-camera prepared record (cos/sin of the Euler angles + parameters)
+//   V[N][6], F[N][6] (inverse Cholesky factor of the damped point block), q[N][3], Z[K][nc][3]
+//   camsys = [U (M, nc, nc) | g_c (M*nc)],  S = [S (ns x ns, column-major) | rhs (ns)]
+// J itself is never stored: every pass recomputes the per-observation Jacobian in registers.
+#pragma once
+#include "sba_internal.cuh"
+
+namespace sba {
+
+constexpr int TPB = 128;          // threads per block of the reduction kernels
+constexpr int CHUNK = 2048;       // observations per camera-major work item
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void warp_reduce_sum(double (&v)[NV])
+{
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        v[k] = x;
+    }
+}
+
+// Sum of v[k] over the block; the result for value k is returned in thread k (k < NV <= NT).
+// sm must hold NV * (NT / 32) doubles.
+template <int NV, int NT>
+__device__ __forceinline__ double block_reduce_sum(double (&v)[NV], double* sm)
+{
+    static_assert(NV <= NT, "more values than threads");
+    warp_reduce_sum<NV>(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < NV) {
+#pragma unroll
+        for (int wq = 0; wq < NT / 32; ++wq) s += sm[wq * NV + threadIdx.x];
+    }
+    __syncthreads();
+    return s;
+}
+
+// Grid-wide deterministic sum: every block stores its NV partial sums, the last block to arrive adds
+// them up in a fixed order and writes out[k].  counter must be zero on entry and is reset on exit.
+template <int NV, int NT>
+__device__ __forceinline__ void grid_sum_finalize(double block_total, double* partials, unsigned* counter,
+                                                  double* out, const int* out_slot)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x < NV) partials[(size_t)blockIdx.x * NV + threadIdx.x] = block_total;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < NV; k += NT / 32) {
+        double s = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * NV + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) out[out_slot[k]] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+struct Slots {
+    int s[8];
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-camera preparation
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prepare_cameras(const double* __restrict__ x, const double* __restrict__ cam_static,
+                                  double* __restrict__ camrec, int M, int P, int nc, int n_cam_fix, int model)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    double v[MAX_CAM_PARAMS];
+#pragma unroll
+    for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
+        double val = 0.0;
+        if (s < P) val = (s < nc && j >= n_cam_fix) ? x[(size_t)j * nc + s] : cam_static[(size_t)j * P + s];
+        v[s] = val;
+    }
+    double* r = camrec + (size_t)j * CAMREC_STRIDE;
+    double sn, cs;
+    sincos(v[0], &sn, &cs); r[0] = cs; r[1] = sn;
+    sincos(v[1], &sn, &cs); r[2] = cs; r[3] = sn;
+    sincos(v[2], &sn, &cs); r[4] = cs; r[5] = sn;
+    if (model == MODEL_PERSPECTIVE) {
+        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
+        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = v[9]; r[13] = v[10];
+    } else if (model == MODEL_AFFINE) {
+        r[6] = v[3]; r[7] = v[4]; r[8] = 0.0;
+        r[9] = v[5]; r[10] = v[6]; r[11] = v[7]; r[12] = 0.0; r[13] = 0.0;
+    } else {
+        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
+        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = 0.0; r[13] = 0.0;
+    }
+    r[14] = 0.0; r[15] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observation evaluation shared by all passes: weighted, robust-rescaled residual and Jacobian rows
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+struct ObsEval {
+    double f0, f1, cost;
+    double Jc[2 * (NC > 0 ? NC : 1)];
+    double Jp[6];
+};
+
+template <int MODEL, int NC>
+__device__ __forceinline__ void eval_obs(const CamRec& c, const double* __restrict__ rpc_j, double X, double Y,
+                                         double Z, double ox, double oy, double w, int loss, double f_scale,
+                                         bool cam_free, bool pt_free, ObsEval<MODEL, NC>& e)
+{
+    double u, v;
+    project_jac<MODEL, NC>(c, rpc_j, X, Y, Z, u, v, e.Jc, e.Jp);
+    double f0 = w * (u - ox), f1 = w * (v - oy), c0, c1;
+    const double s0 = w * loss_rescale(loss, f_scale, f0, c0);
+    const double s1 = w * loss_rescale(loss, f_scale, f1, c1);
+    e.f0 = f0; e.f1 = f1; e.cost = c0 + c1;
+    const double a0 = cam_free ? s0 : 0.0, a1 = cam_free ? s1 : 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { e.Jc[k] *= a0; e.Jc[NC + k] *= a1; }
+    const double b0 = pt_free ? s0 : 0.0, b1 = pt_free ? s1 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { e.Jp[k] *= b0; e.Jp[3 + k] *= b1; }
+}
+
+struct ObsArrays {
+    const int* cam_ind;
+    const int* pts_ind;
+    const double2* pts2d;
+    const double* w;
+    const int* track_ptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// G1: residual `fun` (+ robust cost)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
+           const double* __restrict__ rpc_tab, long long K, int loss, double f_scale, int rpc_f32,
+           double2* __restrict__ r_out, double* partials, unsigned* counter, double* scal, int slot)
+{
+    __shared__ double sm[1 * (256 / 32)];
+    double acc[1] = {0.0};
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
+        const int j = o.cam_ind[a], i = o.pts_ind[a];
+        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        double u, v;
+        project<MODEL>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, u, v);
+        if (MODEL == MODEL_RPC && rpc_f32) { u = (double)(float)u; v = (double)(float)v; }
+        const double2 ob = o.pts2d[a];
+        const double w = o.w[a];
+        const double f0 = w * (u - ob.x), f1 = w * (v - ob.y);
+        if (r_out) r_out[a] = make_double2(f0, f1);
+        acc[0] += loss_cost(loss, f0, f_scale) + loss_cost(loss, f1, f_scale);
+    }
+    const double tot = block_reduce_sum<1, 256>(acc, sm);
+    __shared__ int slots[1];
+    if (threadIdx.x == 0) slots[0] = slot;
+    __syncthreads();
+    grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// G2a: point side of the assembly -- V_i = sum Jp^T Jp, g_p = sum Jp^T f, one thread per track
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(TPB)
+k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
+                  const double* __restrict__ rpc_tab, int N, int n_pts_fix, int loss, double f_scale,
+                  double* __restrict__ V, double* __restrict__ gp_out, double* partials, unsigned* counter,
+                  double* scal)
+{
+    __shared__ double sm[1 * (TPB / 32)];
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int beg = o.track_ptr[i], end = o.track_ptr[i + 1];
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        const bool pt_free = i >= n_pts_fix;
+        double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        for (int a = beg; a < end; ++a) {
+            const int j = o.cam_ind[a];
+            const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+            const double2 ob = o.pts2d[a];
+            ObsEval<MODEL, 0> e;
+            eval_obs<MODEL, 0>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x,
+                               ob.y, o.w[a], loss, f_scale, false, pt_free, e);
+            acc[0] += e.cost;
+            v[0] += e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
+            v[1] += e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
+            v[2] += e.Jp[0] * e.Jp[2] + e.Jp[3] * e.Jp[5];
+            v[3] += e.Jp[1] * e.Jp[1] + e.Jp[4] * e.Jp[4];
+            v[4] += e.Jp[1] * e.Jp[2] + e.Jp[4] * e.Jp[5];
+            v[5] += e.Jp[2] * e.Jp[2] + e.Jp[5] * e.Jp[5];
+            g[0] += e.Jp[0] * e.f0 + e.Jp[3] * e.f1;
+            g[1] += e.Jp[1] * e.f0 + e.Jp[4] * e.f1;
+            g[2] += e.Jp[2] * e.f0 + e.Jp[5] * e.f1;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[6 * (size_t)i + k] = v[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gp_out[3 * (size_t)i + k] = g[k];
+    }
+    const double tot = block_reduce_sum<1, TPB>(acc, sm);
+    __shared__ int slots[1];
+    if (threadIdx.x == 0) slots[0] = SC_COST;
+    __syncthreads();
+    grid_sum_finalize<1, TPB>(tot, partials, counter, scal, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// G2b: camera side of the assembly -- U_j = sum Jc^T Jc, g_c = sum Jc^T f.
+// Camera-major: every block works on one chunk of ONE camera, so the camera record is block-uniform,
+// the accumulators stay in registers and no atomics are needed; partial sums per chunk are combined
+// in a fixed order by k_reduce_cameras.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(TPB)
+k_assemble_cameras(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg,
+                   const int* __restrict__ chunk_end, const int* __restrict__ cm_pts,
+                   const double2* __restrict__ cm_pts2d, const double* __restrict__ cm_w,
+                   const double* __restrict__ xp, const double* __restrict__ camrec,
+                   const double* __restrict__ rpc_tab, int n_cam_fix, int loss, double f_scale,
+                   double* __restrict__ cam_partials)
+{
+    constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
+    __shared__ double sm[NV * (TPB / 32)];
+    const int ch = blockIdx.x, j = chunk_cam[ch];
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    if (j >= n_cam_fix) {
+        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+        const double* rpc_j = MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr;
+        for (int t = chunk_beg[ch] + threadIdx.x; t < chunk_end[ch]; t += TPB) {
+            const int i = cm_pts[t];
+            const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+            const double2 ob = cm_pts2d[t];
+            ObsEval<MODEL, NC> e;
+            eval_obs<MODEL, NC>(c, rpc_j, X, Y, Z, ob.x, ob.y, cm_w[t], loss, f_scale, true, false, e);
+            int k = 0;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) {
+#pragma unroll
+                for (int s = 0; s <= r; ++s) {
+                    acc[k] += e.Jc[r] * e.Jc[s] + e.Jc[NC + r] * e.Jc[NC + s];
+                    ++k;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NC; ++r) acc[NU + r] += e.Jc[r] * e.f0 + e.Jc[NC + r] * e.f1;
+        }
+    }
+    const double tot = block_reduce_sum<NV, TPB>(acc, sm);
+    if (threadIdx.x < NV) cam_partials[(size_t)ch * NV + threadIdx.x] = tot;
+}
+
+// one block per camera: fixed-order sum of its chunks -> camsys_local = [U (M,nc,nc) | g_c (M*nc)]
+template <int NC>
+__global__ void k_reduce_cameras(const double* __restrict__ cam_partials, const int* __restrict__ first_chunk,
+                                 int M, double* __restrict__ camsys)
+{
+    constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
+    const int j = blockIdx.x, k = threadIdx.x;
+    if (k >= NV) return;
+    double s = 0.0;
+    for (int ch = first_chunk[j]; ch < first_chunk[j + 1]; ++ch) s += cam_partials[(size_t)ch * NV + k];
+    if (k < NU) {
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= k) ++r;
+        const int c = k - r * (r + 1) / 2;
+        camsys[(size_t)j * NC * NC + r * NC + c] = s;
+        camsys[(size_t)j * NC * NC + c * NC + r] = s;
+    } else {
+        camsys[(size_t)M * NC * NC + (size_t)j * NC + (k - NU)] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_scale='jac' update + first vector of the 2-D subspace + norms
+//   sinv = max-so-far column norm of J (zero columns -> 1 on the first call)   scipy common.py:598-610
+//   t1   = g / sinv^2   (= d * g_h, the scaled steepest-descent direction mapped back to x space)
+// sums: |g_h|^2, |x sinv|^2, |x|^2 ; max |g|
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_scale_dots(const double* __restrict__ camsys, const double* __restrict__ V, const double* __restrict__ x,
+             double* __restrict__ g, double* __restrict__ sinv, double* __restrict__ t1, long long n, int ns, int nc,
+             int M, int first, int count_cameras, int rank, double* partials, unsigned* counter, double* scal)
+{
+    __shared__ double sm[4 * (256 / 32)];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // gg, xs, xx, gmax
+    double gmax = 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double diag, gv;
+        if (idx < ns) {
+            const int j = (int)idx / nc, s = (int)idx % nc;
+            diag = camsys[(size_t)j * nc * nc + s * nc + s];
+            gv = camsys[(size_t)M * nc * nc + idx];
+            g[idx] = gv;
+        } else {
+            const long long e = idx - ns;
+            const long long i = e / 3;
+            const int k = (int)(e - 3 * i);
+            diag = V[6 * i + (k == 0 ? 0 : (k == 1 ? 3 : 5))];
+            gv = g[idx];
+        }
+        const double nrm = sqrt(diag);
+        double si;
+        if (first) si = (nrm == 0.0) ? 1.0 : nrm;
+        else si = fmax(sinv[idx], nrm);
+        sinv[idx] = si;
+        const double xv = x[idx];
+        t1[idx] = gv / (si * si);
+        gmax = fmax(gmax, fabs(gv));
+        if (idx >= ns || count_cameras) {
+            const double gh = gv / si, xsv = xv * si;
+            acc[0] += gh * gh;
+            acc[1] += xsv * xsv;
+            acc[2] += xv * xv;
+        }
+    }
+    // block max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
+    __shared__ double smax[256 / 32];
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = gmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int k = 0; k < 256 / 32; ++k) m = fmax(m, smax[k]);
+        // non-negative doubles order like their bit patterns
+        atomicMax((unsigned long long*)(scal + SC_GMAX_SLOTS + rank), (unsigned long long)__double_as_longlong(m));
+    }
+    acc[3] = 0.0;
+    const double tot = block_reduce_sum<4, 256>(acc, sm);
+    __shared__ int slots[4];
+    if (threadIdx.x == 0) { slots[0] = SC_GG; slots[1] = SC_XS; slots[2] = SC_XX; slots[3] = SC_SCRATCH; }
+    __syncthreads();
+    grid_sum_finalize<4, 256>(tot, partials, counter, scal, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// J * [v1 v2] over all observations; sums |Jv1|^2 (, Jv1.Jv2, |Jv2|^2)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC, int NVEC>
+__global__ void __launch_bounds__(TPB)
+k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
+      const double* __restrict__ rpc_tab, long long K, int ns, int n_cam_fix, int n_pts_fix, int loss, double f_scale,
+      const double* __restrict__ v1, const double* __restrict__ v2, double* partials, unsigned* counter, double* scal,
+      Slots out)
+{
+    __shared__ double sm[3 * (TPB / 32)];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
+        const int j = o.cam_ind[a], i = o.pts_ind[a];
+        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        const double2 ob = o.pts2d[a];
+        ObsEval<MODEL, NC> e;
+        eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x, ob.y,
+                            o.w[a], loss, f_scale, j >= n_cam_fix, i >= n_pts_fix, e);
+        double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const double a1 = v1[(size_t)j * NC + k];
+            y0 += e.Jc[k] * a1; y1 += e.Jc[NC + k] * a1;
+            if (NVEC == 2) { const double a2 = v2[(size_t)j * NC + k]; z0 += e.Jc[k] * a2; z1 += e.Jc[NC + k] * a2; }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double a1 = v1[ns + 3 * (size_t)i + k];
+            y0 += e.Jp[k] * a1; y1 += e.Jp[3 + k] * a1;
+            if (NVEC == 2) { const double a2 = v2[ns + 3 * (size_t)i + k]; z0 += e.Jp[k] * a2; z1 += e.Jp[3 + k] * a2; }
+        }
+        acc[0] += y0 * y0 + y1 * y1;
+        if (NVEC == 2) { acc[1] += y0 * z0 + y1 * z1; acc[2] += z0 * z0 + z1 * z1; }
+    }
+    const double tot = block_reduce_sum<3, TPB>(acc, sm);
+    __shared__ int slots[3];
+    if (threadIdx.x < 3) slots[threadIdx.x] = out.s[threadIdx.x];
+    __syncthreads();
+    grid_sum_finalize<3, TPB>(tot, partials, counter, scal, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// G3a: point elimination prep -- damped 3x3 block -> inverse Cholesky factor G (lower, 6 values),
+//      q = G g_p, and per observation Z = (Jc^T Jp) G^T  (nc x 3), one thread per track
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(TPB)
+k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
+             const double* __restrict__ rpc_tab, int N, int ns, int n_cam_fix, int n_pts_fix, int loss,
+             double f_scale, double reg, const double* __restrict__ V, const double* __restrict__ g,
+             const double* __restrict__ sinv, double* __restrict__ F, double* __restrict__ q, double* __restrict__ Zout,
+             double* scal)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int beg = o.track_ptr[i], end = o.track_ptr[i + 1];
+        double G[6] = {0, 0, 0, 0, 0, 0};   // g00 g10 g11 g20 g21 g22
+        double qq[3] = {0, 0, 0};
+        const bool pt_free = i >= n_pts_fix;
+        if (pt_free) {
+            const double* v = V + 6 * (size_t)i;
+            const double s0 = sinv[ns + 3 * (size_t)i], s1 = sinv[ns + 3 * (size_t)i + 1], s2 = sinv[ns + 3 * (size_t)i + 2];
+            const double a00 = v[0] + reg * s0 * s0, a10 = v[1], a20 = v[2];
+            const double a11 = v[3] + reg * s1 * s1, a21 = v[4], a22 = v[5] + reg * s2 * s2;
+            bool ok = a00 > 0.0;
+            const double c00 = sqrt(a00), c10 = a10 / c00, c20 = a20 / c00;
+            const double d11 = a11 - c10 * c10;
+            ok = ok && d11 > 0.0;
+            const double c11 = sqrt(d11), c21 = (a21 - c20 * c10) / c11;
+            const double d22 = a22 - c20 * c20 - c21 * c21;
+            ok = ok && d22 > 0.0;
+            const double c22 = sqrt(d22);
+            if (ok) {
+                G[0] = 1.0 / c00; G[2] = 1.0 / c11; G[5] = 1.0 / c22;
+                G[1] = -c10 * G[0] * G[2];
+                G[4] = -c21 * G[2] * G[5];
+                G[3] = -(c20 * G[0] + c21 * G[1]) * G[5];
+                const double g0 = g[ns + 3 * (size_t)i], g1 = g[ns + 3 * (size_t)i + 1], g2 = g[ns + 3 * (size_t)i + 2];
+                qq[0] = G[0] * g0;
+                qq[1] = G[1] * g0 + G[2] * g1;
+                qq[2] = G[3] * g0 + G[4] * g1 + G[5] * g2;
+            } else {
+                atomicAdd(scal + SC_BAD_POINTS, 1.0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[6 * (size_t)i + k] = G[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[3 * (size_t)i + k] = qq[k];
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        for (int a = beg; a < end; ++a) {
+            const int j = o.cam_ind[a];
+            const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+            const double2 ob = o.pts2d[a];
+            ObsEval<MODEL, NC> e;
+            eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x,
+                                ob.y, o.w[a], loss, f_scale, j >= n_cam_fix, pt_free, e);
+            double* z = Zout + (size_t)a * NC * 3;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) {
+                const double w0 = e.Jc[r] * e.Jp[0] + e.Jc[NC + r] * e.Jp[3];
+                const double w1 = e.Jc[r] * e.Jp[1] + e.Jc[NC + r] * e.Jp[4];
+                const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
+                z[3 * r + 0] = w0 * G[0];
+                z[3 * r + 1] = w0 * G[1] + w1 * G[2];
+                z[3 * r + 2] = w0 * G[3] + w1 * G[4] + w2 * G[5];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G3b: Schur complement blocks.  Work item = (camera j, camera j' >= j, chunk of camera j's
+// observations); for every track seen by both, acc += Z_a Z_b^T in registers (rows ROW0..ROW0+NR-1);
+// the diagonal items also accumulate Z_a q_i for the right-hand side.  No atomics.
+// ------------------------------------------------------------------------------------------------
+template <int NC, int ROW0, int NR>
+__global__ void __launch_bounds__(TPB)
+k_schur(const int* __restrict__ si_j, const int* __restrict__ si_jp, const int* __restrict__ si_chunk,
+        const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end, const int* __restrict__ cm_obs,
+        const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N, const double* __restrict__ Zin,
+        const double* __restrict__ q, double* __restrict__ schur_partials)
+{
+    constexpr int NV = NR * NC + NR, NVALL = NC * NC + NC;
+    __shared__ double sm[NV * (TPB / 32)];
+    const int item = blockIdx.x, j = si_j[item], jp = si_jp[item], ch = si_chunk[item];
+    const bool diag = (j == jp);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    const int* row = obs_of + (size_t)jp * N;
+    for (int t = chunk_beg[ch] + threadIdx.x; t < chunk_end[ch]; t += TPB) {
+        const int a = cm_obs[t], i = cm_pts[t];
+        const int b = diag ? a : row[i];
+        if (b < 0) continue;
+        const double* za = Zin + (size_t)a * NC * 3 + ROW0 * 3;
+        const double* zb = Zin + (size_t)b * NC * 3;
+        double A[NR * 3];
+#pragma unroll
+        for (int k = 0; k < NR * 3; ++k) A[k] = za[k];
+#pragma unroll
+        for (int s = 0; s < NC; ++s) {
+            const double b0 = zb[3 * s], b1 = zb[3 * s + 1], b2 = zb[3 * s + 2];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r * NC + s] += A[3 * r] * b0 + A[3 * r + 1] * b1 + A[3 * r + 2] * b2;
+        }
+        if (diag) {
+            const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;
+        }
+    }
+    const double tot = block_reduce_sum<NV, TPB>(acc, sm);
+    if (threadIdx.x < NV) {
+        const int k = threadIdx.x;
+        const int pos = (k < NR * NC) ? (ROW0 * NC + k) : (NC * NC + ROW0 + (k - NR * NC));
+        schur_partials[(size_t)item * NVALL + pos] = tot;
+    }
+}
+
+// one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum items ; rhs_j = -g_j + sum
+template <int NC>
+__global__ void k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ sb_first,
+                                 const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M, int n_cam_fix,
+                                 const double* __restrict__ camsys_local, const double* __restrict__ sinv, double reg,
+                                 int add_diag, double* __restrict__ S)
+{
+    constexpr int NVALL = NC * NC + NC;
+    const int blk = blockIdx.x, k = threadIdx.x;
+    if (k >= NVALL) return;
+    const int j = sb_j[blk], jp = sb_jp[blk];
+    const int ns = M * NC;
+    double s = 0.0;
+    for (int it = sb_first[blk]; it < sb_first[blk + 1]; ++it) s += schur_partials[(size_t)it * NVALL + k];
+    if (k < NC * NC) {
+        const int r = k / NC, c = k % NC;
+        double val = -s;
+        if (j == jp) {
+            val += camsys_local[(size_t)j * NC * NC + r * NC + c];
+            if (r == c && add_diag) {
+                const double si = sinv[(size_t)j * NC + r];
+                val += (j < n_cam_fix) ? 1.0 : reg * si * si;
+            }
+        }
+        S[(size_t)(j * NC + r) + (size_t)(jp * NC + c) * ns] = val;
+        if (j != jp) S[(size_t)(jp * NC + c) + (size_t)(j * NC + r) * ns] = val;
+    } else if (j == jp) {
+        const int r = k - NC * NC;
+        S[(size_t)ns * ns + (size_t)j * NC + r] = -camsys_local[(size_t)M * NC * NC + (size_t)j * NC + r] + s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G6: back-substitution  dp_i = -G^T (q_i + sum_a Z_a^T dc_cam(a)), one thread per track
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(TPB)
+k_backsub(ObsArrays o, int N, int ns, const double* __restrict__ F, const double* __restrict__ q,
+          const double* __restrict__ Zin, double* __restrict__ delta)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double s0 = q[3 * (size_t)i], s1 = q[3 * (size_t)i + 1], s2 = q[3 * (size_t)i + 2];
+        for (int a = o.track_ptr[i]; a < o.track_ptr[i + 1]; ++a) {
+            const int j = o.cam_ind[a];
+            const double* z = Zin + (size_t)a * NC * 3;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) {
+                const double dc = delta[(size_t)j * NC + r];
+                s0 += z[3 * r] * dc; s1 += z[3 * r + 1] * dc; s2 += z[3 * r + 2] * dc;
+            }
+        }
+        const double* G = F + 6 * (size_t)i;
+        delta[ns + 3 * (size_t)i + 0] = -(G[0] * s0 + G[1] * s1 + G[3] * s2);
+        delta[ns + 3 * (size_t)i + 1] = -(G[2] * s1 + G[4] * s2);
+        delta[ns + 3 * (size_t)i + 2] = -(G[5] * s2);
+    }
+}
+
+// g_h . gn_h = sum g * delta
+__global__ void __launch_bounds__(256)
+k_dot_g_delta(const double* __restrict__ g, const double* __restrict__ delta, long long n, int ns, int count_cameras,
+              double* partials, unsigned* counter, double* scal)
+{
+    __shared__ double sm[1 * (256 / 32)];
+    double acc[1] = {0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x)
+        if (idx >= ns || count_cameras) acc[0] += g[idx] * delta[idx];
+    const double tot = block_reduce_sum<1, 256>(acc, sm);
+    __shared__ int slots[1];
+    if (threadIdx.x == 0) slots[0] = SC_GGN;
+    __syncthreads();
+    grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots);
+}
+
+// second basis vector: t2 = delta - alpha t1 with alpha = (g_h.gn_h)/|g_h|^2 read from the scalar block
+__global__ void __launch_bounds__(256)
+k_build_t2(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
+           const double* __restrict__ t1, double* __restrict__ t2, long long n, int ns, int count_cameras,
+           double* partials, unsigned* counter, double* scal)
+{
+    __shared__ double sm[5 * (256 / 32)];
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // ww, wg, t11, t12, t22
+    const double gg = scal[SC_GG];
+    const double alpha = gg > 0.0 ? scal[SC_GGN] / gg : 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const double a = t1[idx], b = delta[idx] - alpha * a;
+        t2[idx] = b;
+        if (idx >= ns || count_cameras) {
+            const double wv = sinv[idx] * b;
+            acc[0] += wv * wv;
+            acc[1] += b * g[idx];
+            acc[2] += a * a;
+            acc[3] += a * b;
+            acc[4] += b * b;
+        }
+    }
+    const double tot = block_reduce_sum<5, 256>(acc, sm);
+    __shared__ int slots[5];
+    if (threadIdx.x == 0) { slots[0] = SC_WW; slots[1] = SC_WG; slots[2] = SC_T11; slots[3] = SC_T12; slots[4] = SC_T22; }
+    __syncthreads();
+    grid_sum_finalize<5, 256>(tot, partials, counter, scal, slots);
+}
+
+__global__ void __launch_bounds__(256)
+k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ t2, double c1,
+       double c2, double* __restrict__ x_new, long long n)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x)
+        x_new[idx] = x[idx] + (c1 * t1[idx] + c2 * t2[idx]);
+}
+
+// per-observation Jacobian blocks for tests (weights applied, no robust rescale)
+template <int MODEL, int NC>
+__global__ void k_jac_blocks(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
+                             const double* __restrict__ rpc_tab, long long K, int n_cam_fix, int n_pts_fix,
+                             double* __restrict__ Jc, double* __restrict__ Jp)
+{
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
+        const int j = o.cam_ind[a], i = o.pts_ind[a];
+        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+        const double2 ob = o.pts2d[a];
+        ObsEval<MODEL, NC> e;
+        eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, xp[3 * (size_t)i],
+                            xp[3 * (size_t)i + 1], xp[3 * (size_t)i + 2], ob.x, ob.y, o.w[a], LOSS_LINEAR, 1.0,
+                            j >= n_cam_fix, i >= n_pts_fix, e);
+        if (Jc)
+            for (int k = 0; k < 2 * NC; ++k) Jc[(size_t)a * 2 * NC + k] = e.Jc[k];
+        if (Jp)
+            for (int k = 0; k < 6; ++k) Jp[(size_t)a * 6 + k] = e.Jp[k];
+    }
+}
+
+// scatter for obs_of[M][N]
+__global__ void k_fill_obs_of(const int* __restrict__ cam_ind, const int* __restrict__ pts_ind, long long K, int N,
+                              int* __restrict__ obs_of)
+{
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x)
+        obs_of[(size_t)cam_ind[a] * N + pts_ind[a]] = (int)a;
+}
+
+}  // namespace sba

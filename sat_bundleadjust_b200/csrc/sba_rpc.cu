@@ -1,0 +1,305 @@
+// Batched RPC kernels: projection, iterative localisation and two-view triangulation, one thread per
+// point / match.  They replace, for whole arrays at once,
+//   rpcm.RPCModel.projection / .localization  (third-party, call sites bundle_adjust/cam_utils.py:229,247,
+//                                              bundle_adjust/ba_rpcfit.py:81,245,323,364)
+//   eval_rpci / eval_rpc / rpc_height         (c/rpc.c:442-452, :378-439, :480-514)
+//   stereo_corresp_to_lonlatalt               (c/disp_to_h.c:40-65, a serial loop over the matches)
+// The reference algorithms are kept (same probes, same stopping rules) so that results agree to
+// rounding; only the execution is different: coefficients staged once per block in shared memory,
+// one match per thread, arrays of structure-of-arrays inputs read coalesced.
+#include "sba_internal.cuh"
+
+namespace sba {
+
+// `struct rpc` of the reference (c/rpc.h:14-32) as offsets into an array of 181 doubles
+constexpr int R_NUMX = 0, R_DENX = 20, R_NUMY = 40, R_DENY = 60, R_SCALE = 80, R_OFFSET = 83, R_INUMX = 86,
+              R_IDENX = 106, R_INUMY = 126, R_IDENY = 146, R_ISCALE = 166, R_IOFFSET = 169, R_DELTA = 180,
+              R_STRUCT_DOUBLES = 181;
+constexpr int LOCALIZE_MAX_IT = 200;
+
+// normalised (lon,lat,alt) -> normalised (col,row)      c/rpc.c:337-349 (eval_nrpci)
+__device__ __forceinline__ void s_nproject(const double* r, double lon, double lat, double alt, double& x, double& y)
+{
+    x = poly20(r + R_INUMX, lon, lat, alt) / poly20(r + R_IDENX, lon, lat, alt);
+    y = poly20(r + R_INUMY, lon, lat, alt) / poly20(r + R_IDENY, lon, lat, alt);
+}
+
+// (lon,lat,alt) -> (col,row)                               c/rpc.c:442-452 (eval_rpci)
+__device__ __forceinline__ void s_project(const double* r, double lon, double lat, double alt, double& col, double& row)
+{
+    double x, y;
+    s_nproject(r, (lon - r[R_IOFFSET]) / r[R_ISCALE], (lat - r[R_IOFFSET + 1]) / r[R_ISCALE + 1],
+               (alt - r[R_IOFFSET + 2]) / r[R_ISCALE + 2], x, y);
+    col = x * r[R_SCALE] + r[R_OFFSET];
+    row = y * r[R_SCALE + 1] + r[R_OFFSET + 1];
+}
+
+// (col,row,alt) -> (lon,lat): direct model when present, else the iterative inversion of the projection
+// by repeated affine fits (c/rpc.c:378-411): first probe at -delta with step 2 delta, then step 0.1,
+// stop when the squared normalised image distance drops to 1e-18.
+__device__ __forceinline__ void s_localize(const double* r, double col, double row, double alt, double& lon, double& lat)
+{
+    const double x = (col - r[R_OFFSET]) / r[R_SCALE];
+    const double y = (row - r[R_OFFSET + 1]) / r[R_SCALE + 1];
+    const double z = (alt - r[R_OFFSET + 2]) / r[R_SCALE + 2];
+    double nlon, nlat;
+    if (isfinite(r[R_NUMX])) {
+        nlon = poly20(r + R_NUMX, x, y, z) / poly20(r + R_DENX, x, y, z);
+        nlat = poly20(r + R_NUMY, x, y, z) / poly20(r + R_DENY, x, y, z);
+    } else {
+        const double d = r[R_DELTA] != 0.0 ? r[R_DELTA] : 1.0;
+        nlon = -d; nlat = -d;
+        double eps = 2.0 * d;
+        double x0, y0, x1, y1, x2, y2;
+        s_nproject(r, nlon, nlat, z, x0, y0);
+        s_nproject(r, nlon + eps, nlat, z, x1, y1);
+        s_nproject(r, nlon, nlat + eps, z, x2, y2);
+        for (int it = 0; it < LOCALIZE_MAX_IT && (x0 - x) * (x0 - x) + (y0 - y) * (y0 - y) > 1e-18; ++it) {
+            const double ux = x - x0, uy = y - y0;
+            const double ax = x1 - x0, ay = y1 - y0, bx = x2 - x0, by = y2 - y0;
+            const double det = ax * by - ay * bx;
+            const double c0 = (by * ux - bx * uy) / det;
+            const double c1 = (-ay * ux + ax * uy) / det;
+            nlon += c0 * eps;
+            nlat += c1 * eps;
+            eps = 0.1;
+            s_nproject(r, nlon, nlat, z, x0, y0);
+            s_nproject(r, nlon + eps, nlat, z, x1, y1);
+            s_nproject(r, nlon, nlat + eps, z, x2, y2);
+        }
+    }
+    lon = nlon * r[R_ISCALE] + r[R_IOFFSET];
+    lat = nlat * r[R_ISCALE + 1] + r[R_IOFFSET + 1];
+}
+
+__device__ __forceinline__ void load_struct(double* sh, const double* g, int count)
+{
+    for (int k = threadIdx.x; k < count; k += blockDim.x) sh[k] = g[k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_rpc_projection(const double* __restrict__ rs, const double* __restrict__ lon, const double* __restrict__ lat,
+                 const double* __restrict__ alt, long long n, double* __restrict__ col, double* __restrict__ row)
+{
+    __shared__ double r[R_STRUCT_DOUBLES];
+    load_struct(r, rs, R_STRUCT_DOUBLES);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s_project(r, lon[i], lat[i], alt[i], col[i], row[i]);
+}
+
+__global__ void __launch_bounds__(256)
+k_rpc_projection_ecef(const double* __restrict__ rs, const double* __restrict__ xyz, long long n,
+                      double* __restrict__ colrow)
+{
+    __shared__ double r[R_STRUCT_DOUBLES];
+    load_struct(r, rs, R_STRUCT_DOUBLES);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double la, lo, al, c, w;
+        ecef_to_geodetic(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], la, lo, al);
+        s_project(r, lo, la, al, c, w);
+        colrow[2 * i] = c;
+        colrow[2 * i + 1] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rpc_localization(const double* __restrict__ rs, const double* __restrict__ col, const double* __restrict__ row,
+                   const double* __restrict__ alt, long long n, double* __restrict__ lon, double* __restrict__ lat)
+{
+    __shared__ double r[R_STRUCT_DOUBLES];
+    load_struct(r, rs, R_STRUCT_DOUBLES);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s_localize(r, col[i], row[i], alt[i], lon[i], lat[i]);
+}
+
+// c/rpc.c:480-514 (rpc_height) + c/disp_to_h.c:40-65, one match per thread
+__global__ void __launch_bounds__(128)
+k_rpc_triangulate(const double* __restrict__ rsa, const double* __restrict__ rsb, const float2* __restrict__ kp_a,
+                  const float2* __restrict__ kp_b, long long n, double* __restrict__ lonlatalt, float* __restrict__ err)
+{
+    __shared__ double ra[R_STRUCT_DOUBLES], rb[R_STRUCT_DOUBLES];
+    for (int k = threadIdx.x; k < R_STRUCT_DOUBLES; k += blockDim.x) { ra[k] = rsa[k]; rb[k] = rsb[k]; }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 a = kp_a[i], b = kp_b[i];
+        const double xa = a.x, ya = a.y, xb = b.x, yb = b.y;
+        double h = 0.0, e = 0.0;
+        for (int t = 0; t < 100; ++t) {
+            double lo, la, px, py, qx, qy;
+            s_localize(ra, xa, ya, h, lo, la);
+            s_project(rb, lo, la, h, px, py);
+            s_localize(ra, xa, ya, h + 1.0, lo, la);
+            s_project(rb, lo, la, h + 1.0, qx, qy);
+            const double dx = qx - px, dy = qy - py, ex = xb - px, ey = yb - py;
+            const double lambda = (dx * ex + dy * ey) / (dx * dx + dy * dy);
+            const double zx = px + lambda * dx, zy = py + lambda * dy;
+            e = hypot(zx - xb, zy - yb);
+            h += lambda;
+            if (fabs(lambda) < 0.00001) break;
+        }
+        double lo, la;
+        s_localize(ra, xa, ya, h, lo, la);
+        lonlatalt[3 * i] = lo;
+        lonlatalt[3 * i + 1] = la;
+        lonlatalt[3 * i + 2] = h;
+        err[i] = (float)e;
+    }
+}
+
+// 90-double table (sba_b200.h layout) -> 181-double struct with the direct model marked absent
+static void table_to_struct(const double* t, double delta, double* s)
+{
+    for (int k = 0; k < R_STRUCT_DOUBLES; ++k) s[k] = 0.0;
+    for (int k = 0; k < 80; ++k) s[k] = NAN;
+    s[R_OFFSET] = t[1]; s[R_OFFSET + 1] = t[0]; s[R_OFFSET + 2] = t[4];
+    s[R_SCALE] = t[6]; s[R_SCALE + 1] = t[5]; s[R_SCALE + 2] = t[9];
+    s[R_IOFFSET] = t[3]; s[R_IOFFSET + 1] = t[2]; s[R_IOFFSET + 2] = t[4];
+    s[R_ISCALE] = t[8]; s[R_ISCALE + 1] = t[7]; s[R_ISCALE + 2] = t[9];
+    for (int k = 0; k < 20; ++k) {
+        s[R_INUMX + k] = t[50 + k]; s[R_IDENX + k] = t[70 + k];
+        s[R_INUMY + k] = t[10 + k]; s[R_IDENY + k] = t[30 + k];
+    }
+    s[R_DELTA] = delta;
+}
+
+struct DevBuf {   // small RAII helper for the per-call staging buffers
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { SBA_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); return SBA_OK; }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+static int require_device()
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: sat_bundleadjust_b200 has no CPU fallback");
+        return SBA_E_CUDA;
+    }
+    return SBA_OK;
+}
+
+static inline int grid_n(long long n, int threads)
+{
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > NUM_SMS * 16) b = NUM_SMS * 16;
+    return (int)b;
+}
+
+int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, cudaStream_t stream);
+
+}  // namespace sba
+
+using namespace sba;
+
+extern "C" int sba_rpc_projection(const double* rpc, const double* lon, const double* lat, const double* alt, int64_t n,
+                                  double* col, double* row)
+{
+    if (!rpc || !lon || !lat || !alt || !col || !row || n < 0) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    double s[R_STRUCT_DOUBLES];
+    table_to_struct(rpc, 1.0, s);
+    DevBuf ds, in, out;
+    SBA_TRY(ds.alloc(sizeof(s))); SBA_TRY(in.alloc(3 * n * sizeof(double))); SBA_TRY(out.alloc(2 * n * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(ds.p, s, sizeof(s), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>(), lon, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + n, lat, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + 2 * n, alt, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_rpc_projection<<<grid_n(n, 256), 256>>>(ds.as<double>(), in.as<double>(), in.as<double>() + n, in.as<double>() + 2 * n,
+                                             n, out.as<double>(), out.as<double>() + n);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(col, out.as<double>(), n * sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(row, out.as<double>() + n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+extern "C" int sba_rpc_projection_ecef(const double* rpc, const double* xyz, int64_t n, double* colrow)
+{
+    if (!rpc || !xyz || !colrow || n < 0) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    double s[R_STRUCT_DOUBLES];
+    table_to_struct(rpc, 1.0, s);
+    DevBuf ds, in, out;
+    SBA_TRY(ds.alloc(sizeof(s))); SBA_TRY(in.alloc(3 * n * sizeof(double))); SBA_TRY(out.alloc(2 * n * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(ds.p, s, sizeof(s), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    k_rpc_projection_ecef<<<grid_n(n, 256), 256>>>(ds.as<double>(), in.as<double>(), n, out.as<double>());
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(colrow, out.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+extern "C" int sba_rpc_localization(const double* rpc, const double* col, const double* row, const double* alt, int64_t n,
+                                    double delta, double* lon, double* lat)
+{
+    if (!rpc || !col || !row || !alt || !lon || !lat || n < 0) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    double s[R_STRUCT_DOUBLES];
+    table_to_struct(rpc, delta, s);
+    DevBuf ds, in, out;
+    SBA_TRY(ds.alloc(sizeof(s))); SBA_TRY(in.alloc(3 * n * sizeof(double))); SBA_TRY(out.alloc(2 * n * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(ds.p, s, sizeof(s), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>(), col, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + n, row, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + 2 * n, alt, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_rpc_localization<<<grid_n(n, 256), 256>>>(ds.as<double>(), in.as<double>(), in.as<double>() + n,
+                                               in.as<double>() + 2 * n, n, out.as<double>(), out.as<double>() + n);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(lon, out.as<double>(), n * sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(lat, out.as<double>() + n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+extern "C" int sba_stereo_corresp_to_lonlatalt(double* lonlatalt, float* err, const float* kp_a, const float* kp_b,
+                                               int64_t n, const void* rpc_a, const void* rpc_b)
+{
+    if (!lonlatalt || !err || !kp_a || !kp_b || !rpc_a || !rpc_b || n < 0) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    DevBuf sa, sb, ka, kb, out, e;
+    const size_t sbytes = R_STRUCT_DOUBLES * sizeof(double);
+    SBA_TRY(sa.alloc(sbytes)); SBA_TRY(sb.alloc(sbytes));
+    SBA_TRY(ka.alloc(2 * n * sizeof(float))); SBA_TRY(kb.alloc(2 * n * sizeof(float)));
+    SBA_TRY(out.alloc(3 * n * sizeof(double))); SBA_TRY(e.alloc(n * sizeof(float)));
+    SBA_CUDA(cudaMemcpy(sa.p, rpc_a, sbytes, cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(sb.p, rpc_b, sbytes, cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(ka.p, kp_a, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(kb.p, kp_b, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    k_rpc_triangulate<<<grid_n(n, 128), 128>>>(sa.as<double>(), sb.as<double>(), ka.as<float2>(), kb.as<float2>(), n,
+                                              out.as<double>(), e.as<float>());
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(lonlatalt, out.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(err, e.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+// the reference's symbol, same signature (returns void; errors are reported on stderr, never exit())
+extern "C" void stereo_corresp_to_lonlatalt(double* lonlatalt, float* err, float* kp_a, float* kp_b, int n_kp,
+                                            void* rpc_a, void* rpc_b)
+{
+    const int rc = sba_stereo_corresp_to_lonlatalt(lonlatalt, err, kp_a, kp_b, n_kp, rpc_a, rpc_b);
+    if (rc != SBA_OK) fprintf(stderr, "stereo_corresp_to_lonlatalt (sba_b200): %s\n", sba_last_error());
+}
+
+extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info)
+{
+    if (!A || !b || n < 1) { set_error("bad argument"); return SBA_E_INVALID; }
+    SBA_TRY(require_device());
+    DevBuf dA, db, dx, df;
+    SBA_TRY(dA.alloc((size_t)n * n * sizeof(double))); SBA_TRY(db.alloc(n * sizeof(double)));
+    SBA_TRY(dx.alloc(n * sizeof(double))); SBA_TRY(df.alloc(sizeof(double)));
+    SBA_CUDA(cudaMemcpy(dA.p, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), 0));
+    double fail = 0.0;
+    SBA_CUDA(cudaMemcpy(&fail, df.p, sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(A, dA.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(b, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (info) *info = (int32_t)fail;
+    return SBA_OK;
+}

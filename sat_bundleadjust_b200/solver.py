@@ -1,0 +1,164 @@
+"""
+Device-resident bundle-adjustment problem: thin Python owner of a `sba_problem` handle.
+
+Consumes the arrays of a `BundleAdjustmentParameters` object (ours or the reference's own,
+bundle_adjust/ba_params.py:78-181) and drives libsba_b200.so through its C ABI.  All arithmetic of the
+hot path runs in the sm_100a kernels of csrc/; this module only packs pointers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import LOSS_IDS, MODEL_IDS, ProblemDesc, SolveInfo, SolveOpts, check, dptr, f64
+
+N_CAM_PARAMS = {"affine": 8, "perspective": 11, "rpc": 9}
+
+
+def rpc_table(rpc):
+    """rpcm-style RPC object -> the 90-double table of include/sba_b200.h."""
+    return np.concatenate([[rpc.row_offset, rpc.col_offset, rpc.lat_offset, rpc.lon_offset, rpc.alt_offset,
+                            rpc.row_scale, rpc.col_scale, rpc.lat_scale, rpc.lon_scale, rpc.alt_scale],
+                           np.asarray(rpc.row_num, dtype=np.float64), np.asarray(rpc.row_den, dtype=np.float64),
+                           np.asarray(rpc.col_num, dtype=np.float64), np.asarray(rpc.col_den, dtype=np.float64)])
+
+
+def check_supported(p):
+    opt = p.cam_params_to_optimize
+    if "K" in opt and "COMMON_K" in opt and "T" in opt and "R" in opt:
+        raise NotImplementedError("COMMON_K (one calibration shared by all cameras) is not supported by the "
+                                  "B200 solver yet")
+    if p.cam_model == "rpc" and p.n_params > 6:
+        raise ValueError("cam_model 'rpc' has no calibration parameters to optimise")
+
+
+def initial_vars(p):
+    """
+    The solver's starting vector: a copy of p.params_opt with the frozen cameras' slots overwritten by
+    p.cam_params, which is what the reference's first `fun` call does to its own copy in place
+    (bundle_adjust/ba_params.py:246-249 via ba_core.py:276-277).
+    """
+    x0 = np.array(p.params_opt, dtype=np.float64, copy=True)
+    if p.n_cam_fix > 0:
+        c = p.n_params
+        x0[: p.n_cam * c].reshape(p.n_cam, c)[: p.n_cam_fix] = p.cam_params[: p.n_cam_fix, :c]
+    return x0
+
+
+class DeviceProblem:
+    """RAII wrapper of sba_problem_create / sba_problem_destroy."""
+
+    def __init__(self, p, stream=0, rank=0, world_size=1, rpc_float32=True, track_range=None):
+        check_supported(p)
+        self.lib = _lib.load()
+        self.cam_model = p.cam_model
+        cam_ind, pts_ind, pts2d, w = p.cam_ind, p.pts_ind, p.pts2d, p.pts2d_w
+        n_pts, n_pts_fix = p.n_pts, p.n_pts_fix
+        if track_range is not None:       # this rank's shard: tracks [t0, t1) and the observations they own
+            t0, t1 = track_range
+            a0, a1 = np.searchsorted(pts_ind, [t0, t1], side="left")
+            cam_ind, pts_ind, pts2d, w = cam_ind[a0:a1], pts_ind[a0:a1] - t0, pts2d[a0:a1], w[a0:a1]
+            n_pts, n_pts_fix = t1 - t0, int(np.clip(p.n_pts_fix - t0, 0, t1 - t0))
+        self.n_cam, self.n_pts, self.n_obs, self.n_params = int(p.n_cam), int(n_pts), int(cam_ind.size), int(p.n_params)
+        self._keep = [np.ascontiguousarray(cam_ind, dtype=np.int64), np.ascontiguousarray(pts_ind, dtype=np.int64),
+                      f64(pts2d), f64(w), f64(p.cam_params)]
+        d = ProblemDesc()
+        d.cam_model = MODEL_IDS[p.cam_model]
+        d.n_cam, d.n_pts, d.n_obs = self.n_cam, self.n_pts, self.n_obs
+        d.n_params, d.n_cam_params = self.n_params, self._keep[4].shape[1]
+        d.n_cam_fix, d.n_pts_fix = int(p.n_cam_fix), int(n_pts_fix)
+        d.cam_ind = self._keep[0].ctypes.data_as(_lib.c_int64_p)
+        d.pts_ind = self._keep[1].ctypes.data_as(_lib.c_int64_p)
+        d.pts2d, d.pts2d_w, d.cam_params = dptr(self._keep[2]), dptr(self._keep[3]), dptr(self._keep[4])
+        if p.cam_model == "rpc":
+            self._keep.append(f64(np.array([rpc_table(c) for c in p.cameras])))
+            d.rpc_coefs = dptr(self._keep[-1])
+        d.rpc_float32 = 1 if rpc_float32 else 0
+        d.rank, d.world_size = rank, world_size
+        self.handle = ctypes.c_void_p()
+        check(self.lib.sba_problem_create(ctypes.byref(self.handle), ctypes.byref(d), ctypes.c_void_p(stream)))
+        self.n_vars = int(self.lib.sba_problem_num_vars(self.handle))
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sba_problem_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def residuals(self, x, loss="linear", f_scale=1.0):
+        x = f64(x)
+        assert x.size == self.n_vars
+        r = np.empty(2 * self.n_obs)
+        cost = ctypes.c_double()
+        check(self.lib.sba_residuals(self.handle, dptr(x), dptr(r), LOSS_IDS[loss], f_scale, ctypes.byref(cost)))
+        return r, cost.value
+
+    def jacobian_blocks(self, x):
+        x = f64(x)
+        Jc = np.empty((self.n_obs, 2, self.n_params))
+        Jp = np.empty((self.n_obs, 2, 3))
+        check(self.lib.sba_jacobian_blocks(self.handle, dptr(x), dptr(Jc), dptr(Jp)))
+        return Jc, Jp
+
+    def normal_blocks(self, x, loss="linear", f_scale=1.0):
+        x = f64(x)
+        c = self.n_params
+        U = np.empty((self.n_cam, c, c))
+        V = np.empty((self.n_pts, 6))
+        g = np.empty(self.n_vars)
+        check(self.lib.sba_normal_blocks(self.handle, dptr(x), LOSS_IDS[loss], f_scale, dptr(U), dptr(V), dptr(g)))
+        return U, V, g
+
+    @staticmethod
+    def make_opts(loss="linear", f_scale=1.0, ftol=1e-4, xtol=1e-10, gtol=1e-8, max_nfev=300, verbose=0):
+        o = SolveOpts()
+        o.loss, o.f_scale, o.ftol, o.xtol, o.gtol = LOSS_IDS[loss], f_scale, ftol, xtol, gtol
+        o.max_nfev, o.verbose = int(max_nfev), int(verbose)
+        return o
+
+    def solve(self, x0, want_residuals=True, **kw):
+        """Host buffers in, host buffers out (the end-to-end call)."""
+        x0 = f64(x0)
+        assert x0.size == self.n_vars
+        x = np.empty_like(x0)
+        r = np.empty(2 * self.n_obs) if want_residuals else None
+        info = SolveInfo()
+        opts = self.make_opts(**kw)
+        check(self.lib.sba_solve(self.handle, dptr(x0), ctypes.byref(opts), dptr(x), dptr(r) if r is not None else None,
+                                 ctypes.byref(info)))
+        return x, r, info.as_dict()
+
+    def solve_device(self, x0_ptr, x_ptr=None, r_ptr=None, **kw):
+        """Device pointers (ints) in and out; nothing but the steering scalars crosses PCIe."""
+        info = SolveInfo()
+        opts = self.make_opts(**kw)
+        check(self.lib.sba_solve_device(self.handle, ctypes.c_void_p(x0_ptr), ctypes.byref(opts),
+                                        ctypes.c_void_p(x_ptr) if x_ptr else None,
+                                        ctypes.c_void_p(r_ptr) if r_ptr else None, ctypes.byref(info)))
+        return info.as_dict()
+
+    def assemble_device(self, x_ptr, loss="linear", f_scale=1.0):
+        ms = ctypes.c_float()
+        check(self.lib.sba_assemble_device(self.handle, ctypes.c_void_p(x_ptr), LOSS_IDS[loss], f_scale, ctypes.byref(ms)))
+        return ms.value
+
+    def set_allreduce(self, fn):
+        """fn(device_ptr: int, count: int) must SUM-reduce `count` doubles in place across ranks."""
+        def trampoline(_user, ptr, count):
+            try:
+                fn(int(ptr), int(count))
+                return 0
+            except Exception as exc:   # never let an exception cross the C boundary
+                print("sba allreduce hook failed:", exc)
+                return 1
+        self._cb = _lib.ALLREDUCE_FN(trampoline)
+        check(self.lib.sba_problem_set_allreduce(self.handle, self._cb, None))

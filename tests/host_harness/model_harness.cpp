@@ -1,0 +1,50 @@
+// TEST INFRASTRUCTURE: host build (g++) of the header-only model math in csrc/sba_models.cuh so that
+// the analytic Jacobians can be checked on a machine without a GPU.  Not part of the product library.
+#include "../../sat_bundleadjust_b200/csrc/sba_models.cuh"
+#include "../../sat_bundleadjust_b200/csrc/sba_tr2d.h"
+
+using namespace sba;
+
+template <int MODEL, int NC>
+static void run(const double* camrec, const double* rpc, const double* X, double* uv, double* Jc, double* Jp)
+{
+    CamRec c = load_camrec(camrec);
+    project_jac<MODEL, NC>(c, rpc, X[0], X[1], X[2], uv[0], uv[1], Jc, Jp);
+}
+
+extern "C" {
+
+// camrec: prepared record (cos/sin + params); returns 0 on success
+int hh_project(int model, const double* camrec, const double* rpc, const double* X, double* uv)
+{
+    CamRec c = load_camrec(camrec);
+    if (model == MODEL_PERSPECTIVE) project<MODEL_PERSPECTIVE>(c, rpc, X[0], X[1], X[2], uv[0], uv[1]);
+    else if (model == MODEL_AFFINE) project<MODEL_AFFINE>(c, rpc, X[0], X[1], X[2], uv[0], uv[1]);
+    else project<MODEL_RPC>(c, rpc, X[0], X[1], X[2], uv[0], uv[1]);
+    return 0;
+}
+
+int hh_project_jac(int model, int nc, const double* camrec, const double* rpc, const double* X,
+                   double* uv, double* Jc, double* Jp)
+{
+#define CASE(M, N) if (model == M && nc == N) { run<M, N>(camrec, rpc, X, uv, Jc, Jp); return 0; }
+    CASE(MODEL_PERSPECTIVE, 3) CASE(MODEL_PERSPECTIVE, 6) CASE(MODEL_PERSPECTIVE, 11)
+    CASE(MODEL_AFFINE, 3) CASE(MODEL_AFFINE, 5) CASE(MODEL_AFFINE, 8)
+    CASE(MODEL_RPC, 3) CASE(MODEL_RPC, 6)
+#undef CASE
+    return 1;
+}
+
+double hh_loss_rescale(int loss, double f_scale, double f, double* f_out, double* cost)
+{
+    double s = loss_rescale(loss, f_scale, f, *cost);
+    *f_out = f;
+    return s;
+}
+
+int hh_tr2d(const double* B, const double* g, double Delta, double* p)
+{
+    return solve_trust_region_2d(B[0], B[1], B[3], g[0], g[1], Delta, p) ? 1 : 0;
+}
+
+}
