@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""
+Benchmark of the bundle-adjustment hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|1m|small]
+
+One JSON line on stdout (rank 0).  A "step" is one trust-region (Levenberg-Marquardt) iteration of the
+BASELINE.json config-2 problem: synthetic 10-view perspective BA, 1e5 tracks / ~5e5 observations,
+soft_l1 loss, correction_params R+T.  At N > 1 every rank gets its own 1e5 tracks (weak scaling, the
+10 cameras are shared) and the per-iteration exchange is the SUM all-reduce of the partial camera system.
+
+  value   = observations x iterations / second, device time (CUDA events) summed over exactly K
+            iterations, inputs resident in HBM, L2 overwritten between iterations, max over ranks
+  e2e     = the same unit through the public API ba_core.run_ba_optimization (host numpy buffers in,
+            host numpy buffers out; problem upload, the whole solve and the read-back inside the timed region)
+  roofline= algorithmic bytes / measured device time of the dominant phase of the iteration, against the
+            measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline = the reference's path (oracle port: numpy residual + scipy TRF/2-point/LSMR) on this box's CPU
+`--impl reference` times that CPU path alone, in the same unit, on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_cam, tracks per GPU, p_vis, cam_model, correction_params, description)
+    "cfg2": (10, 100000, 0.5, "perspective", ["R", "T"],
+             "BASELINE config 2: synthetic 10-view perspective BA, 1e5 tracks / ~5e5 observations, soft_l1, R+T"),
+    "1m": (10, 200000, 0.5, "perspective", ["R", "T"],
+           "config 2 doubled: 10-view perspective BA, 2e5 tracks / ~1e6 observations, soft_l1, R+T"),
+    "small": (6, 4000, 0.5, "perspective", ["R", "T"], "smoke-size: 6 views, 4e3 tracks"),
+}
+LS = {"loss": "soft_l1", "f_scale": 1.0}
+L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (recipe of B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(workload, world):
+    from sat_bundleadjust_b200 import synth
+    n_cam, tracks, p_vis, model, corr, _ = WORKLOADS[workload]
+    scene = synth.make_scene(n_cam=n_cam, n_tracks=tracks * world, p_vis=p_vis, cam_model=model, seed=0)
+    return synth.scene_to_params(scene, corr)
+
+
+def algorithmic_bytes(K, N, M, c):
+    """SURVEY.md section 8d, int32 indices + FP64 values, J never materialised (per LM iteration pass)."""
+    return {
+        "assemble": 48 * K + 96 * N + 4 * M * c * (c + 3),          # G2: one fused residual+Jacobian+assembly pass
+        "step_eval": 48 * K + 24 * N + 8 * 16 * M,                  # G1: one residual pass (no r written)
+        "scale_jvp": 48 * K + 48 * N + 5 * 8 * (M * c + 3 * N),     # vector update + one J*v pass
+        "subspace": 48 * K + 48 * N + 9 * 8 * (M * c + 3 * N),      # vector work + one J*[v1 v2] pass
+        "point_prep": 48 * K + 24 * N + 48 * N + 48 * N + 72 * N + 24 * c * K,   # + Z write (non-algorithmic 24cK)
+        "schur": 24 * c * K + 8 * (M * c) ** 2,                     # read Z once + write S
+        "backsub": 24 * c * K + 72 * N + 24 * N + 4 * K,
+        "cholesky": 8 * (M * c) ** 2,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference path (numpy fun + scipy TRF)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_iterations(p, n_iter, n_warm=0):
+    """Runs scipy TRF exactly as ba_core.py:284-297 does and returns seconds per trust-region iteration
+    measured over iterations [n_warm, n_warm + n_iter) (the Jacobian + solve + evaluation of each)."""
+    from scipy.optimize import least_squares
+    from oracle import ba_oracle
+    stamps = [time.perf_counter()]
+
+    def cb(intermediate_result):
+        stamps.append(time.perf_counter())
+        if len(stamps) - 1 >= n_warm + n_iter:
+            raise StopIteration      # scipy halts the iteration on StopIteration (status -2)
+
+    x0 = p.params_opt.copy()
+    A = ba_oracle.jacobian_sparsity(p)
+    t0 = time.perf_counter()
+    warnings.simplefilter("ignore")
+    least_squares(ba_oracle.residuals, x0, jac_sparsity=A, verbose=0, x_scale="jac", method="trf", ftol=1e-15, xtol=0.0,
+                  gtol=0.0, loss=LS["loss"], f_scale=LS["f_scale"], max_nfev=8 * (n_warm + n_iter) + 8, args=(p,), callback=cb)
+    setup = stamps[0] - t0
+    done = len(stamps) - 1
+    if done <= n_warm:
+        return None, done, setup
+    dt = stamps[-1] - stamps[n_warm]
+    return dt / (done - n_warm), done - n_warm, setup
+
+
+def subsample_tracks(p, frac):
+    """Bounded sample of the workload: keep the first `frac` of the tracks (observations are track-major)."""
+    import copy
+    n_keep = max(10, int(p.n_pts * frac))
+    q = copy.copy(p)
+    a = int(np.searchsorted(p.pts_ind, n_keep))
+    q.n_pts, q.n_obs = n_keep, a
+    q.pts_ind, q.cam_ind, q.pts2d, q.pts2d_w = p.pts_ind[:a], p.cam_ind[:a], p.pts2d[:a], p.pts2d_w[:a]
+    q.pts3d = p.pts3d[:n_keep]
+    ncv = p.n_cam * p.n_params
+    q.params_opt = np.concatenate([p.params_opt[:ncv], p.params_opt[ncv: ncv + 3 * n_keep]])
+    q.n_pts_fix = min(p.n_pts_fix, n_keep)
+    return q
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    p = build_problem(args.workload, 1)
+    K_full = p.n_obs
+    # ~4.3 s per TRF iteration at 5e5 observations on one core; keep the whole run within ~4 minutes
+    budget_s, per_it_full = 240.0, 4.3e-6 * 2 * K_full
+    frac = min(1.0, budget_s / ((args.steps + args.warmup + 1) * per_it_full))
+    q = p if frac >= 1.0 else subsample_tracks(p, frac)
+    sec_it, done, setup = cpu_reference_iterations(q, args.steps, args.warmup)
+    if sec_it is None:
+        print(json.dumps({"impl": "reference", "unavailable": "scipy TRF terminated before the timed iterations"}))
+        return 0
+    value = q.n_obs / sec_it
+    sample = ("%d TRF iterations (after %d warm-up) of scipy least_squares(trf, 2-point sparse differences, LSMR) on %s"
+              % (done, args.warmup, "the full workload" if frac >= 1.0 else
+                 "the first %.0f%% of the tracks (%d observations); obs x it/s is size-normalised" % (100 * frac, q.n_obs)))
+    line = {
+        "impl": "reference", "metric": "lm_observation_iterations_per_s", "value": value, "unit": "obs*it/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * sec_it,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][5], "n_obs": int(q.n_obs), "n_tracks": int(q.n_pts),
+                   "n_cam": int(q.n_cam), "loss": LS["loss"]},
+        "lm_iters_per_s": 1.0 / sec_it,
+        "cpu_baseline": {"value": value, "unit": "obs*it/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample + "; numpy/scipy free to use all host threads (the path is mostly serial)"},
+        "e2e": {"value": value, "unit": "obs*it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from sat_bundleadjust_b200 import ba_core
+    from sat_bundleadjust_b200 import dist as sdist
+    from sat_bundleadjust_b200.solver import DeviceProblem, initial_vars
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, K = args.warmup, args.steps
+    p = build_problem(args.workload, world)
+    ranges = sdist.shard_ranges(p.pts_ind, p.n_pts, world)
+    ncv = p.n_cam * p.n_params
+    x0 = initial_vars(p)
+    stream = torch.cuda.current_stream().cuda_stream
+    prob = DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank] if world > 1 else None)
+    if world > 1:
+        def hook(ptr, count):
+            t = torch.as_tensor(sdist._CudaView(ptr, count), device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        prob.set_allreduce(hook)
+    xl0 = sdist.local_vars(x0, ncv, ranges[rank]) if world > 1 else x0
+    x_dev = torch.from_numpy(xl0).cuda()
+    out_dev = torch.empty_like(x_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # untimed: one short solve so that every kernel is loaded and the NCCL communicator is warm
+    prob.solve_device(x_dev.data_ptr(), out_dev.data_ptr(), None, ftol=0.0, xtol=0.0, gtol=0.0, max_nfev=10 ** 6,
+                      max_iterations=2, **LS)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # exactly K timed iterations; long runs are cut into solves of <= SEG timed iterations that each restart from
+    # x0 (with W untimed iterations first), so that every timed iteration is a productive pre-convergence one
+    SEG, left, info = 25, K, None
+    while left > 0:
+        k = min(SEG, left)
+        part = prob.solve_device(x_dev.data_ptr(), out_dev.data_ptr(), None, ftol=0.0, xtol=0.0, gtol=0.0,
+                                 max_nfev=10 ** 6, max_iterations=W + k, timed_from=W, l2_flush_bytes=L2_FLUSH_BYTES, **LS)
+        assert part["timed_iterations"] == k, part
+        if info is None:
+            info = part
+        else:
+            info["iter_ms"] += part["iter_ms"]
+            info["timed_iterations"] += k
+            info["gpu_launches"] += part["gpu_launches"]
+            for ph in info["phase_ms"]:
+                info["phase_ms"][ph] += part["phase_ms"][ph]
+        left -= k
+    barrier()
+    t = torch.tensor([info["iter_ms"]] + [info["phase_ms"][k] for k in info["phase_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.cpu().numpy()
+    iter_ms = float(t[0])
+    phase_ms = {k: float(v) / K for k, v in zip(info["phase_ms"].keys(), t[1:])}
+
+    # Jacobian pass alone (fused residual + analytic Jacobian + robust weights + block assembly), L2-cold
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    jac_ms = []
+    for i in range(3 + 10):
+        flush.fill_(i & 0xff)
+        ms = prob.assemble_device(x_dev.data_ptr(), **LS)
+        if i >= 3:
+            jac_ms.append(ms)
+    jac = torch.tensor([float(np.mean(jac_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(jac, op=dist.ReduceOp.MAX)
+    jac_ms_mean = float(jac.item())
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the public API (host buffers; rank 0's wall clock, all ranks take part)
+    e2e = None
+    barrier()
+    ls = dict(LS, max_iter=300, verbose=0)
+    t0 = time.perf_counter()
+    if world > 1:
+        out = sdist.run_ba_optimization_distributed(p, ls)
+        info_e = out[5]
+    else:
+        out = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+        info_e = out[5]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    Kobs = int(p.n_obs)
+    n_loc = prob.n_vars
+    h2d = 2 * (4 + 4 + 16 + 8) * prob.n_obs + 8 * (2 * n_loc) + 8 * p.cam_params.size     # both layouts + x0 (fun + solve)
+    d2h = 8 * n_loc + 2 * 16 * prob.n_obs                                                  # x + residuals (init and final)
+    e2e = {"value": Kobs * info_e["iterations"] / wall, "unit": "obs*it/s",
+           "h2d_bytes_per_step": int(h2d / max(1, info_e["iterations"])),
+           "d2h_bytes_per_step": int(d2h / max(1, info_e["iterations"])),
+           "wall_s": wall, "iterations": info_e["iterations"], "nfev": info_e["nfev"], "status": info_e["status"],
+           "cost": info_e["cost"], "device_ms": info_e["solve_ms"],
+           "call": "ba_core.run_ba_optimization(p, {'loss': 'soft_l1', 'f_scale': 1.0, 'max_iter': 300})"}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        M, c = p.n_cam, p.n_params
+        K_loc, N_loc = prob.n_obs, prob.n_pts
+        ab = algorithmic_bytes(K_loc, N_loc, M, c)
+        dominant = max(phase_ms, key=lambda k: phase_ms[k])
+        roof_all = {k: {"ms": phase_ms[k], "algorithmic_bytes": ab[k],
+                        "achieved_GBps": ab[k] / (phase_ms[k] * 1e-3) / 1e9 if phase_ms[k] > 0 else None}
+                    for k in phase_ms}
+        ach = ab[dominant] / (phase_ms[dominant] * 1e-3) / 1e9
+        jac_ach = ab["assemble"] / (jac_ms_mean * 1e-3) / 1e9
+        line = {
+            "metric": "lm_observation_iterations_per_s", "value": Kobs * K / (iter_ms * 1e-3), "unit": "obs*it/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": iter_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][5], "n_obs": Kobs, "n_tracks": int(p.n_pts), "n_cam": int(M),
+                       "n_params_per_cam": int(c), "loss": LS["loss"], "tracks_per_gpu": int(N_loc),
+                       "parallelism": "tracks sharded over %d GPU(s), cameras replicated" % world,
+                       "l2": "256 MiB scratch overwritten between timed iterations (outside the event pairs)"},
+            "lm_iters_per_s": K / (iter_ms * 1e-3),
+            "jacobian_obs_per_s": Kobs / (jac_ms_mean * 1e-3),
+            "jacobian_pass_ms": jac_ms_mean,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(info["gpu_launches"]),
+            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "jacobian_assembly": {"achieved": jac_ach, "frac": jac_ach / peak, "ms": jac_ms_mean,
+                                               "algorithmic_bytes": ab["assemble"]}},
+            "phases_ms_per_iteration": phase_ms, "phases": roof_all,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            q = p
+            sec_it, done, _ = cpu_reference_iterations(q, 3, 0)
+            line["cpu_baseline"] = {"value": q.n_obs / sec_it, "unit": "obs*it/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "lm_iters_per_s": 1.0 / sec_it,
+                                    "sample": "3 TRF iterations of scipy least_squares (2-point sparse differences + LSMR) "
+                                              "on the full workload, 1 of %d host cores (the path is single-threaded)"
+                                              % (os.cpu_count() or 1)}
+        print(json.dumps(line))
+    prob.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -61,7 +61,23 @@ typedef struct sba_solve_opts {
     double ftol, xtol, gtol;  /* scipy.optimize.least_squares meanings */
     int32_t max_nfev;         /* "max_iter" of the reference = max residual evaluations */
     int32_t verbose;
+    /* measurement controls (not in the reference; 0 = off) */
+    int32_t max_iterations;   /* stop after this many outer trust-region iterations (status 0) */
+    int32_t timed_from;       /* iter_ms / phase_ms accumulate over iterations >= timed_from */
+    int64_t l2_flush_bytes;   /* > 0: overwrite a scratch buffer of this size between iterations, outside
+                                 the per-iteration event pairs, so that every timed iteration starts L2-cold */
 } sba_solve_opts;
+
+/* phases of one trust-region iteration, for sba_solve_info.phase_ms */
+enum { SBA_PH_ASSEMBLE = 0,   /* fused residual + Jacobian + robust weights + U/V/g blocks (G2) */
+       SBA_PH_SCALE_JVP,      /* x_scale update, |g|, J*(D^2 g) for the damping (scipy reg_term) */
+       SBA_PH_POINT_PREP,     /* damped 3x3 inverse factors + Z = (Jc^T Jp) G^T */
+       SBA_PH_SCHUR,          /* reduced camera system S, rhs (G3) */
+       SBA_PH_CHOLESKY,       /* dense FP64 factorisation + solves (G4) */
+       SBA_PH_BACKSUB,        /* point updates (G6) */
+       SBA_PH_SUBSPACE,       /* second basis vector, norms, J*[t1 t2] */
+       SBA_PH_STEP_EVAL,      /* x + step, residual + cost at the trial point (G1) */
+       SBA_PH_COUNT };
 
 typedef struct sba_solve_info {
     int32_t status;           /* scipy status: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 ftol+xtol */
@@ -72,6 +88,9 @@ typedef struct sba_solve_info {
     double solve_ms;          /* device time of the iteration loop (CUDA events) */
     int32_t chol_retries;     /* times the reduced camera system had to be re-damped */
     int32_t gpu_launches;     /* kernels launched by this call */
+    int32_t timed_iterations; /* iterations that contributed to iter_ms / phase_ms */
+    double iter_ms;           /* sum of per-iteration device times (CUDA events) over the timed iterations */
+    double phase_ms[8];       /* the same, split by phase (SBA_PH_*) */
 } sba_solve_info;
 
 /* Optional hook for the multi-GPU exchange step: must SUM `count` doubles at device pointer `buf`

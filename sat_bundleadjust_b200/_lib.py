@@ -36,17 +36,24 @@ class ProblemDesc(ctypes.Structure):
 class SolveOpts(ctypes.Structure):
     _fields_ = [("loss", ctypes.c_int32), ("f_scale", ctypes.c_double), ("ftol", ctypes.c_double),
                 ("xtol", ctypes.c_double), ("gtol", ctypes.c_double), ("max_nfev", ctypes.c_int32),
-                ("verbose", ctypes.c_int32)]
+                ("verbose", ctypes.c_int32), ("max_iterations", ctypes.c_int32), ("timed_from", ctypes.c_int32),
+                ("l2_flush_bytes", ctypes.c_int64)]
 
 
 class SolveInfo(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("nfev", ctypes.c_int32), ("njev", ctypes.c_int32),
                 ("iterations", ctypes.c_int32), ("cost_init", ctypes.c_double), ("cost", ctypes.c_double),
                 ("optimality", ctypes.c_double), ("solve_ms", ctypes.c_double), ("chol_retries", ctypes.c_int32),
-                ("gpu_launches", ctypes.c_int32)]
+                ("gpu_launches", ctypes.c_int32), ("timed_iterations", ctypes.c_int32), ("iter_ms", ctypes.c_double),
+                ("phase_ms", ctypes.c_double * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_ms"] = dict(zip(PHASES, list(self.phase_ms)))
+        return d
+
+
+PHASES = ["assemble", "scale_jvp", "point_prep", "schur", "cholesky", "backsub", "subspace", "step_eval"]
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)

@@ -94,6 +94,51 @@ static int check_launch(sba_problem* p)
     return SBA_OK;
 }
 
+// ---- per-phase / per-iteration device timing (CUDA events on the solver's stream) --------------------
+struct PhaseTimer {
+    sba_problem* p;
+    bool on = false;
+    struct Rec { int phase, e0, e1; };
+    std::vector<Rec> recs;
+    int open_e0 = -1, open_phase = -1;
+    int get_event()
+    {
+        if (p->ev_used == (int)p->ev_pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            p->ev_pool.push_back(e);
+        }
+        return p->ev_used++;
+    }
+    void begin(int phase)
+    {
+        if (!on) return;
+        open_e0 = get_event();
+        open_phase = phase;
+        if (open_e0 >= 0) cudaEventRecord(p->ev_pool[open_e0], p->stream);
+    }
+    void end()
+    {
+        if (!on || open_e0 < 0) return;
+        const int e1 = get_event();
+        if (e1 >= 0) {
+            cudaEventRecord(p->ev_pool[e1], p->stream);
+            recs.push_back({open_phase, open_e0, e1});
+        }
+        open_e0 = -1;
+    }
+    // phase == -1 marks a whole iteration
+    void resolve(sba_solve_info* info)
+    {
+        for (const Rec& r : recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p->ev_pool[r.e0], p->ev_pool[r.e1]) != cudaSuccess) continue;
+            if (r.phase < 0) { info->iter_ms += ms; info->timed_iterations++; }
+            else info->phase_ms[r.phase] += ms;
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
@@ -200,11 +245,12 @@ static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out
 }
 
 // Schur complement + Cholesky solve + back-substitution for a given damping `reg`
-static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, double reg)
+static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, double reg, PhaseTimer& tm)
 {
     const int ns = p->M * p->nc;
     const double* xp = p->x + (size_t)ns;
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
+    tm.begin(SBA_PH_POINT_PREP);
     {
         const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
 #define L(MODEL, NC)                                                                                                    \
@@ -215,6 +261,8 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
 #undef L
         SBA_TRY(check_launch(p));
     }
+    tm.end();
+    tm.begin(SBA_PH_SCHUR);
     {
 #define SCHUR_ARGS                                                                                                     \
     p->si_j, p->si_jp, p->si_chunk, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->Z, p->q,   \
@@ -251,8 +299,12 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
             return SBA_E_INVALID;
         }
     }
+    tm.end();
+    tm.begin(SBA_PH_CHOLESKY);
     SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->stream));
     p->launches++;
+    tm.end();
+    tm.begin(SBA_PH_BACKSUB);
     {
         const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
         switch (p->nc) {
@@ -264,8 +316,10 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
         }
         SBA_TRY(check_launch(p));
     }
+    tm.end();
     return SBA_OK;
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // the iteration
@@ -287,12 +341,28 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0;
     double cost = 0.0, Delta = 0.0, g_norm = 0.0;
     bool first = true;
+    PhaseTimer tm, it_tm;
+    tm.p = it_tm.p = p;
+    p->ev_used = 0;
+    if (o->l2_flush_bytes > 0 && (size_t)o->l2_flush_bytes > p->flush_bytes) {
+        if (p->flush_buf) cudaFree(p->flush_buf);
+        p->flush_buf = nullptr; p->flush_bytes = 0;
+        SBA_CUDA(cudaMalloc(&p->flush_buf, (size_t)o->l2_flush_bytes));
+        p->flush_bytes = (size_t)o->l2_flush_bytes;
+    }
 
     while (true) {
+        if (o->max_iterations > 0 && iteration >= o->max_iterations) break;
+        tm.on = it_tm.on = iteration >= o->timed_from && (o->timed_from > 0 || o->l2_flush_bytes > 0 || o->max_iterations > 0);
+        if (o->l2_flush_bytes > 0)
+            SBA_CUDA(cudaMemsetAsync(p->flush_buf, iteration & 0xff, (size_t)o->l2_flush_bytes, p->stream));
+        it_tm.begin(-1);
+        tm.begin(SBA_PH_SCALE_JVP);
         SBA_TRY(run_scale_dots(p, first ? 1 : 0));
         Slots sa; sa.s[0] = SC_A; sa.s[1] = SC_SCRATCH; sa.s[2] = SC_SCRATCH;
         SBA_TRY(run_jvp(p, loss, fs, 1, sa));
         SBA_TRY(allreduce_scal(p, SC_COST, SC_GGN - SC_COST));
+        tm.end();
         SBA_TRY(fetch_scal(p));
         const double* h = p->h_scal;
         if (first) {
@@ -309,7 +379,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         if (g_norm < o->gtol) status = 1;
         if (o->verbose >= 2)
             printf("[sba] it %3d nfev %3d cost %.10e |g|inf %.3e Delta %.3e\n", iteration, nfev, cost, g_norm, Delta);
-        if (status >= 0 || nfev >= o->max_nfev) break;
+        if (status >= 0 || nfev >= o->max_nfev) break;   // (a partial iteration is not counted as timed)
 
         // damping from the Cauchy step (trf.py:485-490; build_quadratic_1d / minimize_quadratic_1d)
         const double qa = 0.5 * h[SC_A], qb = -gg;
@@ -325,7 +395,8 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         // Gauss-Newton step of the damped system, second basis vector, and B_S (one host sync)
         double ggn = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
         for (int attempt = 0;; ++attempt) {
-            SBA_TRY(run_gauss_newton_step(p, loss, fs, reg));
+            SBA_TRY(run_gauss_newton_step(p, loss, fs, reg, tm));
+            tm.begin(SBA_PH_SUBSPACE);
             k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->delta, p->n, ns, p->rank == 0, p->red_partials,
                                                             p->counters + 4, p->scal);
             SBA_TRY(check_launch(p));
@@ -336,6 +407,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
             Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
             SBA_TRY(run_jvp(p, loss, fs, 2, sb));
             SBA_TRY(allreduce_scal(p, SC_WW, SC_COST_NEW - SC_WW));
+            tm.end();
             SBA_TRY(fetch_scal(p));
             h = p->h_scal;
             const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_B22]);
@@ -364,11 +436,13 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
                                        gS0 * pS[0] + gS1 * pS[1]);
             const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
             const double step_h_norm = std::sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
+            tm.begin(SBA_PH_STEP_EVAL);
             k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, c1, c2, p->x_new, p->n);
             SBA_TRY(check_launch(p));
             SBA_TRY(run_prepare(p, p->x_new, p->camrec_new));
             SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
             SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
+            tm.end();
             SBA_TRY(fetch_scal(p));
             ++nfev;
             cost_new = p->h_scal[SC_COST_NEW];
@@ -395,10 +469,13 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
             std::swap(p->camrec, p->camrec_new);
             cost = cost_new;
             if (term < 0) {
+                tm.begin(SBA_PH_ASSEMBLE);
                 SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
+                tm.end();
                 ++njev;
             }
         }
+        it_tm.end();
         ++iteration;
         if (term >= 0) { status = term; break; }
     }
@@ -410,6 +487,8 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     info->status = status; info->nfev = nfev; info->njev = njev; info->iterations = iteration;
     info->cost = cost; info->optimality = g_norm; info->solve_ms = ms; info->chol_retries = chol_retries;
     info->gpu_launches = p->launches;
+    tm.resolve(info);
+    it_tm.resolve(info);
     return SBA_OK;
 }
 
@@ -438,6 +517,8 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p->flush_buf) cudaFree(p->flush_buf);
     delete p;
     return SBA_OK;
 }

@@ -101,4 +101,9 @@ struct sba_problem {
     double *io_x = nullptr;          // (n) staging for host-pointer entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
+    // measurement: event ring for per-phase timing, scratch for L2 flushes
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_used = 0;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
 };

@@ -8,7 +8,8 @@ oracle/_ref/disp_to_h.so) on small seeded inputs.  Run in the build container on
 Fixtures (all inputs are stored next to the outputs, so the tests never need the reference):
   ba_golden.npz     per case: scene inputs, reference packing (pts_ind/cam_ind/pts2d/params_opt/cam_params),
                     reference `fun` at the initial point and at a perturbed point, the sparsity pattern,
-                    and the reference `run_ba_optimization` result (x, err, nfev, cost)
+                    the reference `run_ba_optimization` result (x, err, nfev, cost), and the reference's cost
+                    function at a true local minimum (`conv_*`, oracle.ba_oracle.solve_converged)
   rpc_golden.npz    the two SkySat RPCs of the reference's tests/data/images (coefficients as arrays),
                     projections / localisations / two-view triangulations computed by the compiled reference C,
                     and the reference `fun` for cam_model='rpc' driven through oracle.rpc_oracle.RPCModel
@@ -92,6 +93,12 @@ def make_ba_golden(ref):
             out[pre + "ref_tight_vars_ba"], out[pre + "ref_tight_err_ba"] = v1t, e1t
             out[pre + "ref_tight_nfev"] = np.array(nfev_t)
             out[pre + "ref_tight_fun"] = ref.ba_core.fun(v1t.copy(), p)
+            # the reference's cost function at a true local minimum (scipy TRF, dense exact solver)
+            from oracle import ba_oracle
+            xc, cc, rc = ba_oracle.solve_converged(p, cfg.get("loss", "linear"), cfg.get("f_scale", 1.0), x_start=v1t)
+            assert np.array_equal(ba_oracle.residuals(xc.copy(), p), ref.ba_core.fun(xc.copy(), p))
+            out[pre + "conv_vars"], out[pre + "conv_cost"], out[pre + "conv_status"] = xc, np.array(cc), np.array(rc.status)
+            print("   converged cost %.12e status %d nfev %d" % (cc, rc.status, rc.nfev))
         print("ba case", name, "K =", p.pts_ind.size, "n =", p.params_opt.size)
     np.savez_compressed(os.path.join(HERE, "ba_golden.npz"), **out)
 

@@ -1,0 +1,288 @@
+"""
+CPU tests of the host-side mirror of the reference interface and of the C-ABI library's load/exports.
+No compute call is made on the library here (there is no GPU in the build container).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import ba_oracle
+from oracle.ref_loader import load_reference, reference_available
+from sat_bundleadjust_b200 import _lib, ba_core, ba_params, ba_rotate, cam_utils, geo_utils, synth
+from sat_bundleadjust_b200.solver import DeviceProblem, initial_vars
+
+G = util.load_ba_golden()
+CASES = [str(s) for s in G["cases"]]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_packing_bit_exact_vs_golden(name):
+    """track -> observation layout, camera vectors and params_opt equal the reference's, bit for bit."""
+    p = util.params_from_golden(G, name)
+    pre = name + "/"
+    for k in ["pts_ind", "cam_ind", "pts2d", "params_opt", "cam_params", "pts2d_w"]:
+        a, b = getattr(p, k), G[pre + "ref_" + k]
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), k
+    assert np.all(np.diff(p.pts_ind) >= 0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_build_jacobian_sparsity_bit_exact(name):
+    p = util.params_from_golden(G, name)
+    pre = name + "/"
+    A = ba_core.build_jacobian_sparsity(p).tocsr()
+    A.sort_indices()
+    assert tuple(A.shape) == tuple(G[pre + "ref_sparsity_shape"])
+    assert np.array_equal(A.indptr, G[pre + "ref_sparsity_indptr"])
+    assert np.array_equal(A.indices, G[pre + "ref_sparsity_indices"])
+    assert A.dtype == np.dtype(int)
+
+
+def test_get_vars_ready_for_fun_and_reconstruct():
+    p = util.params_from_golden(G, "persp_RT_fix")
+    v = p.params_opt.copy()
+    v[:12] += 1.0
+    pts, cams = p.get_vars_ready_for_fun(v)
+    o_pts, o_cams = ba_oracle.unpack_variables(p.params_opt.copy() + 0.0, p)
+    assert np.array_equal(cams[: p.n_cam_fix], p.cam_params[: p.n_cam_fix])      # frozen cameras restored
+    assert np.array_equal(v[: p.n_cam_fix * p.n_params].reshape(p.n_cam_fix, -1), p.cam_params[: p.n_cam_fix, : p.n_params])
+    assert np.array_equal(pts, o_pts)
+    x0 = initial_vars(p)
+    assert np.array_equal(x0, p.params_opt) or p.n_cam_fix > 0
+    pts3d, cameras = p.reconstruct_vars(p.params_opt.copy(), p.pts3d.copy(), list(p.cameras))
+    assert pts3d.shape == p.pts3d.shape and len(cameras) == p.n_cam
+    for P0, P1 in zip(p.cameras, cameras):
+        assert np.allclose(P0, P1, rtol=1e-9, atol=1e-9 * np.abs(P0).max())
+
+
+def test_empty_and_ragged_inputs():
+    C = np.full((4, 5), np.nan)
+    cams = [np.eye(3, 4), np.eye(3, 4)]
+    with pytest.raises(ValueError):      # same exception type as the reference (np.vstack of nothing)
+        ba_params.BundleAdjustmentParameters(C, np.zeros((5, 3)), cams, "perspective", [], [np.zeros(3)] * 2,
+                                             {"reduce": False, "verbose": False})
+    # ragged tracks: lengths 1..M are all packed, order is point-major
+    sc = synth.make_scene(n_cam=7, n_tracks=60, p_vis=0.4, seed=3, min_obs=1)
+    p = synth.scene_to_params(sc, ["R"])
+    assert p.n_obs == sc.n_obs and np.array_equal(p.pts_ind, sc.pts_ind) and np.array_equal(p.cam_ind, sc.cam_ind)
+
+
+def test_camera_utils_round_trips():
+    """Same checks as the reference's tests/test_functions.py:19-63, on satellite-scale matrices."""
+    sc = synth.make_scene(n_cam=2, n_tracks=10, p_vis=1.0, seed=1)
+    P = sc.cameras[0]
+    K, R, vecT, oC = cam_utils.decompose_perspective_camera(P)
+    P2 = cam_utils.compose_perspective_camera(K, R, oC)
+    assert np.allclose(P, P2 / P2[2, 3])
+    A = synth.affine_expansion(P, sc.pts3d_true[0])
+    K, R, vecT = cam_utils.decompose_affine_camera(A)
+    assert np.allclose(A, cam_utils.compose_affine_camera(K, R, vecT))
+    ang = ba_rotate.euler_angles_from_R(R)
+    assert np.allclose(R, ba_rotate.euler_angles_to_R(*ang))
+    lat, lon, alt = geo_utils.ecef_to_latlon_custom(*geo_utils.latlon_to_ecef_custom(11.0, -72.7, 3500.0))
+    assert abs(lat - 11.0) < 1e-9 and abs(lon + 72.7) < 1e-9 and abs(alt - 3500.0) < 1e-3
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_packing_against_live_reference_with_reduce():
+    ref = load_reference()
+    sc = synth.make_scene(n_cam=6, n_tracks=500, p_vis=0.3, cam_model="perspective", seed=2)
+    d = {"correction_params": ["R", "T"], "n_cam_fix": 2, "n_pts_fix": 50, "reduce": True, "verbose": False,
+         "ref_cam_weight": 3.0}
+    args = (sc.correspondence_matrix(), sc.pts3d_init, list(sc.cameras_init), "perspective", [(0, 1), (1, 2), (4, 5)],
+            list(sc.camera_centers), d)
+    p, q = ba_params.BundleAdjustmentParameters(*args), ref.ba_params.BundleAdjustmentParameters(*args)
+    for k in ["pts_ind", "cam_ind", "pts2d", "params_opt", "cam_params", "pts2d_w", "C", "pts3d", "pts_prev_indices",
+              "cam_prev_indices"]:
+        assert np.array_equal(getattr(p, k), getattr(q, k), equal_nan=True), k
+    assert (p.n_cam_fix, p.n_pts_fix, p.n_cam_opt, p.n_pts_opt) == (q.n_cam_fix, q.n_pts_fix, q.n_cam_opt, q.n_pts_opt)
+    assert p.pairs_to_triangulate == q.pairs_to_triangulate
+
+
+def test_reprojection_error_and_config():
+    r = np.array([3.0, 4.0, 0.0, -2.0])
+    assert np.allclose(ba_core.compute_reprojection_error(r), [5.0, 2.0])
+    assert np.allclose(ba_core.compute_reprojection_error(r, np.array([2.0, 1.0])), [2.5, 2.0])
+    assert ba_core.init_optimization_config(None) == {"loss": "linear", "ftol": 1e-4, "xtol": 1e-10, "f_scale": 1.0,
+                                                      "max_iter": 300, "verbose": 1}
+    assert ba_core.init_optimization_config({"loss": "soft_l1", "bogus": 1})["loss"] == "soft_l1"
+    err = np.array([1.0, 3.0, 5.0])
+    assert np.allclose(ba_core.compute_mean_reprojection_error_per_track(err, np.array([0, 0, 1]), np.array([0, 1, 0])), [2.0, 5.0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the C-ABI library: loads, exports everything the header declares, fails loudly without a GPU
+# ---------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(built):
+    import re
+    lib = _lib.load()
+    header = open(os.path.join(os.path.dirname(util.HERE), "include", "sba_b200.h")).read()
+    declared = set(re.findall(r"\b(sba_[a-z0-9_]+|stereo_corresp_to_lonlatalt)\s*\(", header))
+    declared -= {"sba_allreduce_fn"}
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.sba_version() >= 100
+
+
+def test_tr2d_matches_scipy(built):
+    from scipy.optimize._lsq.common import solve_trust_region_2d
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for t in range(3000):
+        A = rng.standard_normal((2, 2))
+        B = A @ A.T if t % 2 == 0 else A + A.T
+        g = rng.standard_normal(2) * 10 ** rng.uniform(-3, 3)
+        D = 10 ** rng.uniform(-3, 3)
+        p0, newton0 = solve_trust_region_2d(B, g, D)
+        p1 = np.zeros(2)
+        newton1 = lib.sba_tr2d(_lib.dptr(np.ascontiguousarray(B)), _lib.dptr(g), D, _lib.dptr(p1))
+        q = lambda p: 0.5 * p @ B @ p + g @ p
+        assert bool(newton1) == bool(newton0)
+        assert q(p1) <= q(p0) + 1e-9 * (abs(q(p0)) + 1e-12)
+        assert np.linalg.norm(p1) <= D * (1 + 1e-12)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the product path must raise, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = util.params_from_golden(G, "persp_R")
+    with pytest.raises(_lib.SbaError):
+        DeviceProblem(p)
+    with pytest.raises(_lib.SbaError):
+        ba_core.fun(p.params_opt.copy(), p)
+    with pytest.raises(_lib.SbaError):
+        ba_core.run_ba_optimization(p, None, False, False)
+
+
+def test_unsupported_configurations_raise():
+    p = util.params_from_golden(G, "persp_RTK_common")
+    with pytest.raises(NotImplementedError):
+        DeviceProblem(p)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the model math of csrc/sba_models.cuh compiled for the host (tests/host_harness)
+# ---------------------------------------------------------------------------------------------------
+def _harness():
+    lib = ctypes.CDLL(os.path.join(util.HERE, "host_harness", "libmodel_harness.so"))
+    return lib
+
+
+def _camrec(model, v):
+    r = np.zeros(16)
+    r[0:6] = [np.cos(v[0]), np.sin(v[0]), np.cos(v[1]), np.sin(v[1]), np.cos(v[2]), np.sin(v[2])]
+    if model == 1:
+        r[6:9], r[9:14] = v[3:6], v[6:11]
+    elif model == 0:
+        r[6:8], r[9:12] = v[3:5], v[5:8]
+    else:
+        r[6:9], r[9:12] = v[3:6], v[6:9]
+    return r
+
+
+@pytest.mark.parametrize("model,name,nc", [(1, "perspective", 6), (1, "perspective", 11), (0, "affine", 5), (0, "affine", 8)])
+def test_analytic_jacobian_matches_finite_differences(built, model, name, nc):
+    lib = _harness()
+    P = _lib.dptr
+    sc = synth.make_scene(n_cam=3, n_tracks=30, p_vis=0.9, cam_model=name, seed=5)
+    p = synth.scene_to_params(sc, ["R"])
+    rpc = np.zeros(90)
+
+    def proj(v, X):
+        uv = np.zeros(2)
+        lib.hh_project(model, P(_camrec(model, v)), P(rpc), P(np.ascontiguousarray(X)), P(uv))
+        return uv
+
+    proj_o = getattr(ba_oracle, "project_" + name)(p.pts3d.astype(np.float64), p.cam_params, p.pts_ind, p.cam_ind)
+    for k in range(0, p.n_obs, 5):
+        v, X = p.cam_params[p.cam_ind[k]].copy(), p.pts3d[p.pts_ind[k]].astype(np.float64)
+        uv, Jc, Jp = np.zeros(2), np.zeros(2 * nc), np.zeros(6)
+        assert lib.hh_project_jac(model, nc, P(_camrec(model, v)), P(rpc), P(X), P(uv), P(Jc), P(Jp)) == 0
+        assert np.array_equal(uv, proj_o[k])          # same operation order as the oracle, no FMA on the host
+        Jc, Jp = Jc.reshape(2, nc), Jp.reshape(2, 3)
+        for s in range(nc):
+            nT = 3 if model == 1 else 2
+            h = 1e-7 if s < 3 else (1.0 if s < 3 + nT else 1e-3 * max(1.0, abs(v[s])))
+            a, b = v.copy(), v.copy()
+            a[s] += h
+            b[s] -= h
+            fd = (proj(a, X) - proj(b, X)) / (a[s] - b[s])
+            assert np.allclose(fd, Jc[:, s], rtol=2e-6, atol=2e-6 * np.abs(fd).max() + 1e-12), (s, fd, Jc[:, s])
+        for s in range(3):
+            a, b = X.copy(), X.copy()
+            a[s] += 0.01
+            b[s] -= 0.01
+            fd = (proj(v, a) - proj(v, b)) / (a[s] - b[s])
+            assert np.allclose(fd, Jp[:, s], rtol=2e-6, atol=2e-6 * np.abs(fd).max())
+
+
+def test_rpc_jacobian_matches_finite_differences(built):
+    lib = _harness()
+    P = _lib.dptr
+    R = util.load_rpc_golden()
+    tab = np.ascontiguousarray(R["rpc_a"][:90])
+    rpc = util.rpc_from_array(R["rpc_a"])
+    from oracle import rpc_oracle
+    lla = R["lonlatalt"][:40]
+    X = np.stack(rpc_oracle.latlon_to_ecef(lla[:, 1], lla[:, 0], lla[:, 2]), axis=1)
+    v = np.array([2e-6, -1e-6, 3e-6, 0.5, -0.3, 0.2, 1.8e6, -6.1e6, 1.4e6])
+
+    def proj(vv, x):
+        uv = np.zeros(2)
+        lib.hh_project(2, P(_camrec(2, vv)), P(tab), P(np.ascontiguousarray(x)), P(uv))
+        return uv
+
+    ref = rpc.project_ecef(ba_oracle.adjust_pts3d(X, np.tile(v, (X.shape[0], 1))))
+    mine = np.array([proj(v, x) for x in X])
+    assert np.abs(mine - ref).max() < 1e-7
+    for x in X[::4]:
+        uv, Jc, Jp = np.zeros(2), np.zeros(12), np.zeros(6)
+        assert lib.hh_project_jac(2, 6, P(_camrec(2, v)), P(tab), P(x), P(uv), P(Jc), P(Jp)) == 0
+        Jc, Jp = Jc.reshape(2, 6), Jp.reshape(2, 3)
+        for s in range(6):
+            h = 1e-7 if s < 3 else 0.1
+            a, b = v.copy(), v.copy()
+            a[s] += h
+            b[s] -= h
+            fd = (proj(a, x) - proj(b, x)) / (a[s] - b[s])
+            assert np.allclose(fd, Jc[:, s], rtol=1e-5, atol=1e-6 * np.abs(fd).max())
+        for s in range(3):
+            a, b = x.copy(), x.copy()
+            a[s] += 0.1
+            b[s] -= 0.1
+            fd = (proj(v, a) - proj(v, b)) / (a[s] - b[s])
+            assert np.allclose(fd, Jp[:, s], rtol=1e-5, atol=1e-6 * np.abs(fd).max())
+
+
+@pytest.mark.parametrize("loss", ["linear", "huber", "soft_l1", "cauchy", "arctan"])
+def test_robust_rescale_matches_scipy(built, loss):
+    from scipy.optimize._lsq.common import scale_for_robust_loss_function
+    from scipy.optimize._lsq.least_squares import construct_loss_function
+    lib = _harness()
+    lib.hh_loss_rescale.restype = ctypes.c_double
+    lib.hh_loss_rescale.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]
+    f = np.array([-30.0, -2.0, -0.5, 0.0, 0.3, 1.0, 1.5, 4.0, 100.0])
+    fs = 1.7
+    if loss == "linear":
+        exp_scale, exp_f, exp_cost = np.ones_like(f), f.copy(), 0.5 * f ** 2
+    else:
+        lf = construct_loss_function(f.size, loss, fs)
+        rho = lf(f.copy())
+        exp_cost = 0.5 * rho[0].copy()
+        J = np.ones((f.size, 1))
+        ff = f.copy()
+        J, ff = scale_for_robust_loss_function(J, ff, rho)
+        exp_scale, exp_f = J[:, 0], ff
+    for i, fi in enumerate(f):
+        fo, co = ctypes.c_double(), ctypes.c_double()
+        s = lib.hh_loss_rescale(_lib.LOSS_IDS[loss], fs, fi, ctypes.byref(fo), ctypes.byref(co))
+        assert np.isclose(s, exp_scale[i], rtol=1e-10, atol=0)
+        assert np.isclose(fo.value, exp_f[i], rtol=1e-10, atol=1e-300)
+        assert np.isclose(co.value, exp_cost[i], rtol=1e-10, atol=1e-300)
