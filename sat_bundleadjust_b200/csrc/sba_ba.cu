@@ -15,6 +15,7 @@
 //     nfev == max_nfev                                                           (common.py:705-717)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "sba_kernels.cuh"
@@ -24,7 +25,8 @@ namespace sba {
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
-int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, cudaStream_t stream);
+int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
+                          cudaStream_t stream);
 
 static inline int grid_for(long long work, int threads, int max_blocks)
 {
@@ -301,7 +303,8 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     }
     tm.end();
     tm.begin(SBA_PH_CHOLESKY);
-    SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->stream));
+    SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->chol_work,
+                                  p->stream));
     p->launches++;
     tm.end();
     tm.begin(SBA_PH_BACKSUB);
@@ -392,37 +395,58 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         }
         double reg = -ag_value / (Delta * Delta);
 
-        // Gauss-Newton step of the damped system, second basis vector, and B_S (one host sync)
-        double ggn = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
+        // Gauss-Newton step of the damped system and the sums that define the 2-D subspace model (one host sync).
+        // With delta the exact solution of (H + reg D^2) delta = -g  (H = J^T J, D^2 = diag(sinv^2), t1 = D^-2 g):
+        //   t1'H delta = -|g_h|^2 - reg g_h.gn_h ,  delta'H delta = -g_h.gn_h - reg |gn_h|^2 ,  t1'H t1 = |J t1|^2 (known),
+        // so B_S = S'J_h'J_h S needs no further pass over the observations.  The explicit J*[t1 t2] pass is kept as
+        // a fall-back for the rare iteration in which a point block had to be frozen (the identities then miss its row).
+        double alpha = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
         for (int attempt = 0;; ++attempt) {
             SBA_TRY(run_gauss_newton_step(p, loss, fs, reg, tm));
             tm.begin(SBA_PH_SUBSPACE);
-            k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->delta, p->n, ns, p->rank == 0, p->red_partials,
-                                                            p->counters + 4, p->scal);
+            k_subspace_dots<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->n, ns, p->rank == 0,
+                                                              p->red_partials, p->counters + 4, p->scal);
             SBA_TRY(check_launch(p));
-            SBA_TRY(allreduce_scal(p, SC_GGN, 1));
-            k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
-                                                         p->red_partials, p->counters + 5, p->scal);
-            SBA_TRY(check_launch(p));
-            Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
-            SBA_TRY(run_jvp(p, loss, fs, 2, sb));
-            SBA_TRY(allreduce_scal(p, SC_WW, SC_COST_NEW - SC_WW));
+            SBA_TRY(allreduce_scal(p, SC_GGN, SC_B11 - SC_GGN));
             tm.end();
             SBA_TRY(fetch_scal(p));
             h = p->h_scal;
-            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_B22]);
+            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_DD]);
             if (!failed) break;
             if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
-            // re-damp: J_h has unit column norms, so reg is relative to 1
-            reg = std::max(reg * 10.0, 1e-12);
+            reg = std::max(reg * 10.0, 1e-12);   // re-damp: J_h has unit column norms, so reg is relative to 1
             ++chol_retries;
         }
-        ggn = h[SC_GGN]; ww = h[SC_WW]; wg = h[SC_WG]; t11 = h[SC_T11]; t12 = h[SC_T12]; t22 = h[SC_T22];
-        b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
-        (void)ggn;
-        // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|
+        {
+            const double ggn = h[SC_GGN], dd = h[SC_DD], t1d = h[SC_T1D], d2 = h[SC_D2];
+            t11 = h[SC_T11];
+            alpha = gg > 0.0 ? ggn / gg : 0.0;
+            ww = dd - 2.0 * alpha * ggn + alpha * alpha * gg;      // |gn_h - alpha g_h|^2
+            wg = ggn - alpha * gg;                                 // (gn_h - alpha g_h).g_h, zero up to rounding
+            t12 = t1d - alpha * t11;
+            t22 = d2 - 2.0 * alpha * t1d + alpha * alpha * t11;
+            b11 = h[SC_A];
+            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || p->explicit_subspace;
+            if (!explicit_pass) {
+                const double h1d = -gg - reg * ggn, hdd = -ggn - reg * dd;
+                b12 = h1d - alpha * b11;
+                b22 = hdd - 2.0 * alpha * h1d + alpha * alpha * b11;
+            } else {
+                tm.begin(SBA_PH_SUBSPACE);
+                k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->delta, p->t1, alpha, p->t2, p->n);
+                SBA_TRY(check_launch(p));
+                Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
+                SBA_TRY(run_jvp(p, loss, fs, 2, sb));
+                SBA_TRY(allreduce_scal(p, SC_B11, 3));
+                tm.end();
+                SBA_TRY(fetch_scal(p));
+                h = p->h_scal;
+                b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
+            }
+        }
+        // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|  (t2 = delta - alpha t1)
         const double n1 = std::sqrt(gg);
-        const bool rank2 = ww > 1e-30 * std::max(t22, 1e-300) && ww > 0.0;
+        const bool rank2 = ww > 1e-14 * h[SC_DD] && ww > 0.0;
         const double n2 = rank2 ? std::sqrt(ww) : 1.0;
         double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
         double gS0 = n1, gS1 = rank2 ? wg / n2 : 0.0;
@@ -437,9 +461,9 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
             const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
             const double step_h_norm = std::sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
             tm.begin(SBA_PH_STEP_EVAL);
-            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, c1, c2, p->x_new, p->n);
+            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->delta, c1 - c2 * alpha, c2, p->x_new, p->n,
+                                                     p->cam_static, p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->model);
             SBA_TRY(check_launch(p));
-            SBA_TRY(run_prepare(p, p->x_new, p->camrec_new));
             SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
             SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
             tm.end();
@@ -510,7 +534,7 @@ extern "C" int sba_problem_destroy(sba_problem* p)
                     p->cam_ptr, p->obs_of, p->cm_pts2d, p->cm_w, p->chunks.cam, p->chunks.beg, p->chunks.end, p->si_j,
                     p->si_jp, p->si_chunk, p->sb_first, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
                     p->t2, p->camrec, p->camrec_new, p->V, p->F, p->q, p->Z, p->camsys_local, p->S, p->cam_partials,
-                    p->schur_partials, p->red_partials, p->counters, p->scal, p->r_out, p->io_x};
+                    p->schur_partials, p->red_partials, p->counters, p->scal, p->r_out, p->io_x, p->chol_work};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->camsys && p->camsys != p->camsys_local) cudaFree(p->camsys);
@@ -617,6 +641,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     if (p->world > 1) SBA_TRY(dev_alloc(&p->camsys, ns * nc + ns));
     else p->camsys = p->camsys_local;
     SBA_TRY(dev_alloc(&p->S, ns * ns + ns));
+    if (ns > 160) SBA_TRY(dev_alloc(&p->chol_work, (ns + 1) * ns));
     const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
     SBA_TRY(dev_alloc(&p->cam_partials, (size_t)p->chunks.n * nv_cam));
     SBA_TRY(dev_alloc(&p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));
@@ -660,6 +685,7 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
+    if (const char* e = getenv("SBA_EXPLICIT_SUBSPACE")) p->explicit_subspace = atoi(e);
     const int rc = problem_create_impl(p, d);
     if (rc != SBA_OK) { sba_problem_destroy(p); return rc; }
     *out = p;

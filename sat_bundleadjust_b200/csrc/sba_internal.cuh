@@ -43,8 +43,12 @@ enum Scal {
     SC_GMAX_SLOTS,        // max |g|, one slot per rank (16 slots), combined on the host
     // group B
     SC_GGN = SC_GMAX_SLOTS + 16,   // g_h . gn_h
-    // group C: after the second basis vector and J*[t1 t2]
-    SC_WW, SC_WG, SC_T11, SC_T12, SC_T22, SC_B11, SC_B12, SC_B22,
+    SC_DD,                // |gn_h|^2
+    SC_T1D,               // t1 . delta
+    SC_D2,                // |delta|^2
+    SC_T11,               // |t1|^2
+    // group C (only the explicit J*[t1 t2] fallback)
+    SC_B11, SC_B12, SC_B22,
     // group D
     SC_COST_NEW,
     // local diagnostics (never reduced)
@@ -93,6 +97,8 @@ struct sba_problem {
     double *V = nullptr, *F = nullptr, *q = nullptr, *Z = nullptr;
     double *camsys_local = nullptr, *camsys = nullptr;     // [U (M*nc*nc) | g_c (M*nc)]
     double *S = nullptr;                                   // [S (ns*ns) | rhs (ns)], ns = M*nc
+    double *chol_work = nullptr;                           // (ns+1)*ns scratch of the factorisation when ns > 160
+    int explicit_subspace = 0;                             // 1: always run the explicit J*[t1 t2] pass (validation)
     double *cam_partials = nullptr, *schur_partials = nullptr, *red_partials = nullptr;
     unsigned* counters = nullptr;
     double* scal = nullptr;          // device scalar block

@@ -60,7 +60,7 @@ __device__ __forceinline__ double block_reduce_sum(double (&v)[NV], double* sm)
 // them up in a fixed order and writes out[k].  counter must be zero on entry and is reset on exit.
 template <int NV, int NT>
 __device__ __forceinline__ void grid_sum_finalize(double block_total, double* partials, unsigned* counter,
-                                                  double* out, const int* out_slot)
+                                                  double* out, const int* out_slot, double* sm)
 {
     __shared__ bool is_last;
     if (threadIdx.x < NV) partials[(size_t)blockIdx.x * NV + threadIdx.x] = block_total;
@@ -73,14 +73,17 @@ __device__ __forceinline__ void grid_sum_finalize(double block_total, double* pa
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < NV; k += NT / 32) {
-        double s = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * NV + k);
+    // every thread of the last block adds a fixed, strided subset of the per-block partials; the block
+    // reduction that follows has a fixed shape too, so the result does not depend on which block is last
+    double acc[NV];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) out[out_slot[k]] = s;
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += NT) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] += __ldcg(partials + (size_t)b * NV + k);
     }
+    const double tot = block_reduce_sum<NV, NT>(acc, sm);
+    if (threadIdx.x < NV) out[out_slot[threadIdx.x]] = tot;
     if (threadIdx.x == 0) *counter = 0u;
 }
 
@@ -91,19 +94,8 @@ struct Slots {
 // ------------------------------------------------------------------------------------------------
 // per-camera preparation
 // ------------------------------------------------------------------------------------------------
-__global__ void k_prepare_cameras(const double* __restrict__ x, const double* __restrict__ cam_static,
-                                  double* __restrict__ camrec, int M, int P, int nc, int n_cam_fix, int model)
+__device__ __forceinline__ void write_camrec(const double (&v)[MAX_CAM_PARAMS], double* __restrict__ r, int model)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= M) return;
-    double v[MAX_CAM_PARAMS];
-#pragma unroll
-    for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
-        double val = 0.0;
-        if (s < P) val = (s < nc && j >= n_cam_fix) ? x[(size_t)j * nc + s] : cam_static[(size_t)j * P + s];
-        v[s] = val;
-    }
-    double* r = camrec + (size_t)j * CAMREC_STRIDE;
     double sn, cs;
     sincos(v[0], &sn, &cs); r[0] = cs; r[1] = sn;
     sincos(v[1], &sn, &cs); r[2] = cs; r[3] = sn;
@@ -119,6 +111,21 @@ __global__ void k_prepare_cameras(const double* __restrict__ x, const double* __
         r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = 0.0; r[13] = 0.0;
     }
     r[14] = 0.0; r[15] = 0.0;
+}
+
+__global__ void k_prepare_cameras(const double* __restrict__ x, const double* __restrict__ cam_static,
+                                  double* __restrict__ camrec, int M, int P, int nc, int n_cam_fix, int model)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    double v[MAX_CAM_PARAMS];
+#pragma unroll
+    for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
+        double val = 0.0;
+        if (s < P) val = (s < nc && j >= n_cam_fix) ? x[(size_t)j * nc + s] : cam_static[(size_t)j * P + s];
+        v[s] = val;
+    }
+    write_camrec(v, camrec + (size_t)j * CAMREC_STRIDE, model);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,7 +193,7 @@ k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict_
     __shared__ int slots[1];
     if (threadIdx.x == 0) slots[0] = slot;
     __syncthreads();
-    grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots);
+    grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,7 +240,7 @@ k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __re
     __shared__ int slots[1];
     if (threadIdx.x == 0) slots[0] = SC_COST;
     __syncthreads();
-    grid_sum_finalize<1, TPB>(tot, partials, counter, scal, slots);
+    grid_sum_finalize<1, TPB>(tot, partials, counter, scal, slots, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,7 +372,7 @@ k_scale_dots(const double* __restrict__ camsys, const double* __restrict__ V, co
     __shared__ int slots[4];
     if (threadIdx.x == 0) { slots[0] = SC_GG; slots[1] = SC_XS; slots[2] = SC_XX; slots[3] = SC_SCRATCH; }
     __syncthreads();
-    grid_sum_finalize<4, 256>(tot, partials, counter, scal, slots);
+    grid_sum_finalize<4, 256>(tot, partials, counter, scal, slots, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,7 +415,7 @@ k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ cam
     __shared__ int slots[3];
     if (threadIdx.x < 3) slots[threadIdx.x] = out.s[threadIdx.x];
     __syncthreads();
-    grid_sum_finalize<3, TPB>(tot, partials, counter, scal, slots);
+    grid_sum_finalize<3, TPB>(tot, partials, counter, scal, slots, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,60 +594,76 @@ k_backsub(ObsArrays o, int N, int ns, const double* __restrict__ F, const double
     }
 }
 
-// g_h . gn_h = sum g * delta
+// All the sums the 2-D subspace step needs, in one pass over the variables:
+//   g_h.gn_h = sum g d ; |gn_h|^2 = sum (sinv d)^2 ; t1.d ; |d|^2 ; |t1|^2       (d = Gauss-Newton step delta)
 __global__ void __launch_bounds__(256)
-k_dot_g_delta(const double* __restrict__ g, const double* __restrict__ delta, long long n, int ns, int count_cameras,
-              double* partials, unsigned* counter, double* scal)
-{
-    __shared__ double sm[1 * (256 / 32)];
-    double acc[1] = {0.0};
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x)
-        if (idx >= ns || count_cameras) acc[0] += g[idx] * delta[idx];
-    const double tot = block_reduce_sum<1, 256>(acc, sm);
-    __shared__ int slots[1];
-    if (threadIdx.x == 0) slots[0] = SC_GGN;
-    __syncthreads();
-    grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots);
-}
-
-// second basis vector: t2 = delta - alpha t1 with alpha = (g_h.gn_h)/|g_h|^2 read from the scalar block
-__global__ void __launch_bounds__(256)
-k_build_t2(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
-           const double* __restrict__ t1, double* __restrict__ t2, long long n, int ns, int count_cameras,
-           double* partials, unsigned* counter, double* scal)
+k_subspace_dots(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
+                const double* __restrict__ t1, long long n, int ns, int count_cameras, double* partials,
+                unsigned* counter, double* scal)
 {
     __shared__ double sm[5 * (256 / 32)];
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // ww, wg, t11, t12, t22
-    const double gg = scal[SC_GG];
-    const double alpha = gg > 0.0 ? scal[SC_GGN] / gg : 0.0;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
-        const double a = t1[idx], b = delta[idx] - alpha * a;
-        t2[idx] = b;
         if (idx >= ns || count_cameras) {
-            const double wv = sinv[idx] * b;
-            acc[0] += wv * wv;
-            acc[1] += b * g[idx];
-            acc[2] += a * a;
-            acc[3] += a * b;
-            acc[4] += b * b;
+            const double d = delta[idx], a = t1[idx], sd = sinv[idx] * d;
+            acc[0] += g[idx] * d;
+            acc[1] += sd * sd;
+            acc[2] += a * d;
+            acc[3] += d * d;
+            acc[4] += a * a;
         }
     }
     const double tot = block_reduce_sum<5, 256>(acc, sm);
     __shared__ int slots[5];
-    if (threadIdx.x == 0) { slots[0] = SC_WW; slots[1] = SC_WG; slots[2] = SC_T11; slots[3] = SC_T12; slots[4] = SC_T22; }
+    if (threadIdx.x == 0) { slots[0] = SC_GGN; slots[1] = SC_DD; slots[2] = SC_T1D; slots[3] = SC_D2; slots[4] = SC_T11; }
     __syncthreads();
-    grid_sum_finalize<5, 256>(tot, partials, counter, scal, slots);
+    grid_sum_finalize<5, 256>(tot, partials, counter, scal, slots, sm);
 }
 
+// second basis vector t2 = delta - alpha t1, materialised only for the explicit J*[t1 t2] fallback
 __global__ void __launch_bounds__(256)
-k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ t2, double c1,
-       double c2, double* __restrict__ x_new, long long n)
+k_build_t2(const double* __restrict__ delta, const double* __restrict__ t1, double alpha, double* __restrict__ t2,
+           long long n)
 {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x)
-        x_new[idx] = x[idx] + (c1 * t1[idx] + c2 * t2[idx]);
+        t2[idx] = delta[idx] - alpha * t1[idx];
+}
+
+__device__ __forceinline__ double step_value(double x, double a, double d, double ca, double cb)
+{
+    return x + fma(ca, a, cb * d);
+}
+
+__global__ void __launch_bounds__(256)
+k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ delta, double ca,
+       double cb, double* __restrict__ x_new, long long n, const double* __restrict__ cam_static,
+       double* __restrict__ camrec_new, int M, int P, int nc, int n_cam_fix, int model)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long idx = gid; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        x_new[idx] = step_value(x[idx], t1[idx], delta[idx], ca, cb);
+    // the first M threads also prepare the camera records of the trial point (same expression as above,
+    // so the records match x_new bit for bit)
+    if (gid < M) {
+        const int j = (int)gid;
+        double v[MAX_CAM_PARAMS];
+#pragma unroll
+        for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
+            double val = 0.0;
+            if (s < P) {
+                if (s < nc && j >= n_cam_fix) {
+                    const size_t e = (size_t)j * nc + s;
+                    val = step_value(x[e], t1[e], delta[e], ca, cb);
+                } else {
+                    val = cam_static[(size_t)j * P + s];
+                }
+            }
+            v[s] = val;
+        }
+        write_camrec(v, camrec_new + (size_t)j * CAMREC_STRIDE, model);
+    }
 }
 
 // per-observation Jacobian blocks for tests (weights applied, no robust rescale)

@@ -188,7 +188,8 @@ static inline int grid_n(long long n, int threads)
     return (int)b;
 }
 
-int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, cudaStream_t stream);
+int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
+                          cudaStream_t stream);
 
 }  // namespace sba
 
@@ -290,12 +291,13 @@ extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info
 {
     if (!A || !b || n < 1) { set_error("bad argument"); return SBA_E_INVALID; }
     SBA_TRY(require_device());
-    DevBuf dA, db, dx, df;
+    DevBuf dA, db, dx, df, dw;
+    SBA_TRY(dw.alloc((size_t)(n + 1) * n * sizeof(double)));
     SBA_TRY(dA.alloc((size_t)n * n * sizeof(double))); SBA_TRY(db.alloc(n * sizeof(double)));
     SBA_TRY(dx.alloc(n * sizeof(double))); SBA_TRY(df.alloc(sizeof(double)));
     SBA_CUDA(cudaMemcpy(dA.p, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
     SBA_CUDA(cudaMemcpy(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice));
-    SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), 0));
+    SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), dw.as<double>(), 0));
     double fail = 0.0;
     SBA_CUDA(cudaMemcpy(&fail, df.p, sizeof(double), cudaMemcpyDeviceToHost));
     SBA_CUDA(cudaMemcpy(A, dA.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -60,6 +60,10 @@ class DeviceProblem:
             cam_ind, pts_ind, pts2d, w = cam_ind[a0:a1], pts_ind[a0:a1] - t0, pts2d[a0:a1], w[a0:a1]
             n_pts, n_pts_fix = t1 - t0, int(np.clip(p.n_pts_fix - t0, 0, t1 - t0))
         self.n_cam, self.n_pts, self.n_obs, self.n_params = int(p.n_cam), int(n_pts), int(cam_ind.size), int(p.n_params)
+        # frozen points always take their initial coordinates, whatever the caller's vector holds
+        # (bundle_adjust/ba_params.py:240-243); frozen cameras are handled on the device from cam_params
+        t_first = 0 if track_range is None else track_range[0]
+        self._fixed_pts = np.asarray(p.pts3d[t_first: t_first + n_pts_fix], dtype=np.float64).ravel().copy()
         self._keep = [np.ascontiguousarray(cam_ind, dtype=np.int64), np.ascontiguousarray(pts_ind, dtype=np.int64),
                       f64(pts2d), f64(w), f64(p.cam_params)]
         d = ProblemDesc()
@@ -93,24 +97,34 @@ class DeviceProblem:
     def __exit__(self, *a):
         self.close()
 
-    # -- evaluation ------------------------------------------------------------------------------
-    def residuals(self, x, loss="linear", f_scale=1.0):
+    def _vars(self, x):
+        """float64 copy-if-needed of a variable vector with the frozen points pinned to their initial values"""
         x = f64(x)
         assert x.size == self.n_vars
+        if self._fixed_pts.size:
+            off = self.n_cam * self.n_params
+            if not np.array_equal(x[off: off + self._fixed_pts.size], self._fixed_pts):
+                x = x.copy()
+                x[off: off + self._fixed_pts.size] = self._fixed_pts
+        return x
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def residuals(self, x, loss="linear", f_scale=1.0):
+        x = self._vars(x)
         r = np.empty(2 * self.n_obs)
         cost = ctypes.c_double()
         check(self.lib.sba_residuals(self.handle, dptr(x), dptr(r), LOSS_IDS[loss], f_scale, ctypes.byref(cost)))
         return r, cost.value
 
     def jacobian_blocks(self, x):
-        x = f64(x)
+        x = self._vars(x)
         Jc = np.empty((self.n_obs, 2, self.n_params))
         Jp = np.empty((self.n_obs, 2, 3))
         check(self.lib.sba_jacobian_blocks(self.handle, dptr(x), dptr(Jc), dptr(Jp)))
         return Jc, Jp
 
     def normal_blocks(self, x, loss="linear", f_scale=1.0):
-        x = f64(x)
+        x = self._vars(x)
         c = self.n_params
         U = np.empty((self.n_cam, c, c))
         V = np.empty((self.n_pts, 6))
@@ -129,8 +143,7 @@ class DeviceProblem:
 
     def solve(self, x0, want_residuals=True, **kw):
         """Host buffers in, host buffers out (the end-to-end call)."""
-        x0 = f64(x0)
-        assert x0.size == self.n_vars
+        x0 = self._vars(x0)
         x = np.empty_like(x0)
         r = np.empty(2 * self.n_obs) if want_residuals else None
         info = SolveInfo()

@@ -76,7 +76,7 @@ def test_normal_equation_blocks(built, loss):
         _, cost = prob.residuals(x0, loss, fs)
     J = util.dense_jacobian_from_blocks(p, Jc, Jp)
     f = ba_oracle.residuals(x0.copy(), p)
-    assert np.isclose(cost, ba_oracle.robust_cost(f, loss, fs), rtol=1e-12)
+    assert np.isclose(cost, ba_oracle.robust_cost(f, loss, fs), rtol=1e-10)
     if loss != "linear":
         rho = construct_loss_function(f.size, loss, fs)(f.copy())
         J, f = scale_for_robust_loss_function(J, f.copy(), rho)
@@ -146,7 +146,9 @@ def test_max_nfev_and_status(built):
         assert info["nfev"] == 1 and info["status"] == 0 and np.array_equal(x, x0)
         x, r, info = prob.solve(x0, loss="soft_l1", max_nfev=5, ftol=0.0, xtol=0.0, gtol=0.0)
         assert info["nfev"] == 5 and info["status"] == 0
-        assert info["cost"] < info["cost_init"]
+        assert info["cost"] <= info["cost_init"]        # early trial steps may all be rejected (Delta0 = |x0 D| is huge)
+        x, r, info = prob.solve(x0, loss="soft_l1", max_nfev=25, ftol=0.0, xtol=0.0, gtol=0.0)
+        assert info["nfev"] == 25 and info["cost"] < info["cost_init"]
         x, r, info = prob.solve(x0, loss="soft_l1", gtol=1e300)
         assert info["status"] == 1 and info["nfev"] == 1
         # determinism: two runs give bit-identical results (no atomics on the data path)
