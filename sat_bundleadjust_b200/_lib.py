@@ -45,7 +45,7 @@ class SolveInfo(ctypes.Structure):
                 ("iterations", ctypes.c_int32), ("cost_init", ctypes.c_double), ("cost", ctypes.c_double),
                 ("optimality", ctypes.c_double), ("solve_ms", ctypes.c_double), ("chol_retries", ctypes.c_int32),
                 ("gpu_launches", ctypes.c_int32), ("timed_iterations", ctypes.c_int32), ("iter_ms", ctypes.c_double),
-                ("phase_ms", ctypes.c_double * 8)]
+                ("phase_ms", ctypes.c_double * 8), ("explicit_subspace_passes", ctypes.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -341,7 +341,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
 
     SBA_TRY(run_prepare(p, p->x, p->camrec));
     SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
-    int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0;
+    int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0, explicit_passes = 0;
     double cost = 0.0, Delta = 0.0, g_norm = 0.0;
     bool first = true;
     PhaseTimer tm, it_tm;
@@ -404,37 +404,36 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         for (int attempt = 0;; ++attempt) {
             SBA_TRY(run_gauss_newton_step(p, loss, fs, reg, tm));
             tm.begin(SBA_PH_SUBSPACE);
-            k_subspace_dots<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->n, ns, p->rank == 0,
-                                                              p->red_partials, p->counters + 4, p->scal);
+            k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->n, ns, p->rank == 0, p->red_partials,
+                                                            p->counters + 4, p->scal);
             SBA_TRY(check_launch(p));
-            SBA_TRY(allreduce_scal(p, SC_GGN, SC_B11 - SC_GGN));
+            SBA_TRY(allreduce_scal(p, SC_GGN, 2));
+            k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
+                                                         p->red_partials, p->counters + 5, p->scal);
+            SBA_TRY(check_launch(p));
+            SBA_TRY(allreduce_scal(p, SC_WW, 5));
             tm.end();
             SBA_TRY(fetch_scal(p));
             h = p->h_scal;
-            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_DD]);
+            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_WW]);
             if (!failed) break;
             if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
             reg = std::max(reg * 10.0, 1e-12);   // re-damp: J_h has unit column norms, so reg is relative to 1
             ++chol_retries;
         }
         {
-            const double ggn = h[SC_GGN], dd = h[SC_DD], t1d = h[SC_T1D], d2 = h[SC_D2];
-            t11 = h[SC_T11];
+            const double ggn = h[SC_GGN], dd = h[SC_DD];
             alpha = gg > 0.0 ? ggn / gg : 0.0;
-            ww = dd - 2.0 * alpha * ggn + alpha * alpha * gg;      // |gn_h - alpha g_h|^2
-            wg = ggn - alpha * gg;                                 // (gn_h - alpha g_h).g_h, zero up to rounding
-            t12 = t1d - alpha * t11;
-            t22 = d2 - 2.0 * alpha * t1d + alpha * alpha * t11;
+            ww = h[SC_WW]; wg = h[SC_WG]; t11 = h[SC_T11]; t12 = h[SC_T12]; t22 = h[SC_T22];
             b11 = h[SC_A];
-            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || p->explicit_subspace;
+            // algebraic model only when gn_h is well separated from g_h (<= 3 digits lost in the differences below)
+            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || p->explicit_subspace || !(ww >= 1e-3 * dd);
             if (!explicit_pass) {
                 const double h1d = -gg - reg * ggn, hdd = -ggn - reg * dd;
                 b12 = h1d - alpha * b11;
                 b22 = hdd - 2.0 * alpha * h1d + alpha * alpha * b11;
             } else {
                 tm.begin(SBA_PH_SUBSPACE);
-                k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->delta, p->t1, alpha, p->t2, p->n);
-                SBA_TRY(check_launch(p));
                 Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
                 SBA_TRY(run_jvp(p, loss, fs, 2, sb));
                 SBA_TRY(allreduce_scal(p, SC_B11, 3));
@@ -442,11 +441,12 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
                 SBA_TRY(fetch_scal(p));
                 h = p->h_scal;
                 b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
+                ++explicit_passes;
             }
         }
         // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|  (t2 = delta - alpha t1)
         const double n1 = std::sqrt(gg);
-        const bool rank2 = ww > 1e-14 * h[SC_DD] && ww > 0.0;
+        const bool rank2 = ww > 0.0;
         const double n2 = rank2 ? std::sqrt(ww) : 1.0;
         double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
         double gS0 = n1, gS1 = rank2 ? wg / n2 : 0.0;
@@ -461,7 +461,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
             const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
             const double step_h_norm = std::sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
             tm.begin(SBA_PH_STEP_EVAL);
-            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->delta, c1 - c2 * alpha, c2, p->x_new, p->n,
+            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, c1, c2, p->x_new, p->n,
                                                      p->cam_static, p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->model);
             SBA_TRY(check_launch(p));
             SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
@@ -511,6 +511,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     info->status = status; info->nfev = nfev; info->njev = njev; info->iterations = iteration;
     info->cost = cost; info->optimality = g_norm; info->solve_ms = ms; info->chol_retries = chol_retries;
     info->gpu_launches = p->launches;
+    info->explicit_subspace_passes = explicit_passes;
     tm.resolve(info);
     it_tm.resolve(info);
     return SBA_OK;

@@ -44,10 +44,9 @@ enum Scal {
     // group B
     SC_GGN = SC_GMAX_SLOTS + 16,   // g_h . gn_h
     SC_DD,                // |gn_h|^2
-    SC_T1D,               // t1 . delta
-    SC_D2,                // |delta|^2
-    SC_T11,               // |t1|^2
-    // group C (only the explicit J*[t1 t2] fallback)
+    // group C: second basis vector t2 = delta - alpha t1
+    SC_WW, SC_WG, SC_T11, SC_T12, SC_T22,
+    // group C' (only the explicit J*[t1 t2] pass)
     SC_B11, SC_B12, SC_B22,
     // group D
     SC_COST_NEW,

@@ -594,41 +594,59 @@ k_backsub(ObsArrays o, int N, int ns, const double* __restrict__ F, const double
     }
 }
 
-// All the sums the 2-D subspace step needs, in one pass over the variables:
-//   g_h.gn_h = sum g d ; |gn_h|^2 = sum (sinv d)^2 ; t1.d ; |d|^2 ; |t1|^2       (d = Gauss-Newton step delta)
+// g_h.gn_h = sum g d  and  |gn_h|^2 = sum (sinv d)^2      (d = Gauss-Newton step delta)
 __global__ void __launch_bounds__(256)
-k_subspace_dots(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
-                const double* __restrict__ t1, long long n, int ns, int count_cameras, double* partials,
-                unsigned* counter, double* scal)
+k_dot_g_delta(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
+              long long n, int ns, int count_cameras, double* partials, unsigned* counter, double* scal)
 {
-    __shared__ double sm[5 * (256 / 32)];
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    __shared__ double sm[2 * (256 / 32)];
+    double acc[2] = {0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         if (idx >= ns || count_cameras) {
-            const double d = delta[idx], a = t1[idx], sd = sinv[idx] * d;
+            const double d = delta[idx], sd = sinv[idx] * d;
             acc[0] += g[idx] * d;
             acc[1] += sd * sd;
-            acc[2] += a * d;
-            acc[3] += d * d;
-            acc[4] += a * a;
+        }
+    }
+    const double tot = block_reduce_sum<2, 256>(acc, sm);
+    __shared__ int slots[2];
+    if (threadIdx.x == 0) { slots[0] = SC_GGN; slots[1] = SC_DD; }
+    __syncthreads();
+    grid_sum_finalize<2, 256>(tot, partials, counter, scal, slots, sm);
+}
+
+// second basis vector, orthogonalised explicitly (the Gauss-Newton step is nearly parallel to the gradient
+// whenever the damping is large, so forming |w|^2 from the Gram matrix would cancel catastrophically):
+//   t2 = delta - alpha t1 ,  alpha = (g_h.gn_h)/|g_h|^2 read from the scalar block (no host round trip)
+// sums: |w|^2 = |sinv t2|^2, w.g_h = t2.g, |t1|^2, t1.t2, |t2|^2
+__global__ void __launch_bounds__(256)
+k_build_t2(const double* __restrict__ g, const double* __restrict__ sinv, const double* __restrict__ delta,
+           const double* __restrict__ t1, double* __restrict__ t2, long long n, int ns, int count_cameras,
+           double* partials, unsigned* counter, double* scal)
+{
+    __shared__ double sm[5 * (256 / 32)];
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double gg = scal[SC_GG];
+    const double alpha = gg > 0.0 ? scal[SC_GGN] / gg : 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const double a = t1[idx], b = delta[idx] - alpha * a;
+        t2[idx] = b;
+        if (idx >= ns || count_cameras) {
+            const double wv = sinv[idx] * b;
+            acc[0] += wv * wv;
+            acc[1] += b * g[idx];
+            acc[2] += a * a;
+            acc[3] += a * b;
+            acc[4] += b * b;
         }
     }
     const double tot = block_reduce_sum<5, 256>(acc, sm);
     __shared__ int slots[5];
-    if (threadIdx.x == 0) { slots[0] = SC_GGN; slots[1] = SC_DD; slots[2] = SC_T1D; slots[3] = SC_D2; slots[4] = SC_T11; }
+    if (threadIdx.x == 0) { slots[0] = SC_WW; slots[1] = SC_WG; slots[2] = SC_T11; slots[3] = SC_T12; slots[4] = SC_T22; }
     __syncthreads();
     grid_sum_finalize<5, 256>(tot, partials, counter, scal, slots, sm);
-}
-
-// second basis vector t2 = delta - alpha t1, materialised only for the explicit J*[t1 t2] fallback
-__global__ void __launch_bounds__(256)
-k_build_t2(const double* __restrict__ delta, const double* __restrict__ t1, double alpha, double* __restrict__ t2,
-           long long n)
-{
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x)
-        t2[idx] = delta[idx] - alpha * t1[idx];
 }
 
 __device__ __forceinline__ double step_value(double x, double a, double d, double ca, double cb)
