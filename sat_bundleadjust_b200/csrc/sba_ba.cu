@@ -398,8 +398,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         // Gauss-Newton step of the damped system and the sums that define the 2-D subspace model (one host sync).
         // With delta the exact solution of (H + reg D^2) delta = -g  (H = J^T J, D^2 = diag(sinv^2), t1 = D^-2 g):
         //   t1'H delta = -|g_h|^2 - reg g_h.gn_h ,  delta'H delta = -g_h.gn_h - reg |gn_h|^2 ,  t1'H t1 = |J t1|^2 (known),
-        // so B_S = S'J_h'J_h S needs no further pass over the observations.  The explicit J*[t1 t2] pass is kept as
-        // a fall-back for the rare iteration in which a point block had to be frozen (the identities then miss its row).
+        // so B_S = S'J_h'J_h S could be had without a pass over the observations (see the note on cancellation below).
         double alpha = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
         for (int attempt = 0;; ++attempt) {
             SBA_TRY(run_gauss_newton_step(p, loss, fs, reg, tm));
@@ -412,6 +411,11 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
                                                          p->red_partials, p->counters + 5, p->scal);
             SBA_TRY(check_launch(p));
             SBA_TRY(allreduce_scal(p, SC_WW, 5));
+            if (!p->algebraic_subspace) {
+                Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
+                SBA_TRY(run_jvp(p, loss, fs, 2, sb));
+                SBA_TRY(allreduce_scal(p, SC_B11, 3));
+            }
             tm.end();
             SBA_TRY(fetch_scal(p));
             h = p->h_scal;
@@ -426,9 +430,13 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
             alpha = gg > 0.0 ? ggn / gg : 0.0;
             ww = h[SC_WW]; wg = h[SC_WG]; t11 = h[SC_T11]; t12 = h[SC_T12]; t22 = h[SC_T22];
             b11 = h[SC_A];
-            // algebraic model only when gn_h is well separated from g_h (<= 3 digits lost in the differences below)
-            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || p->explicit_subspace || !(ww >= 1e-3 * dd);
-            if (!explicit_pass) {
+            // The algebraic model (no pass over the observations) is exact in exact arithmetic but cancels badly
+            // whenever |J t1| >> |J t2| (stiff gradient direction), which robust losses make common: it is an opt-in
+            // experiment (SBA_ALGEBRAIC_SUBSPACE=1); the default is the explicit J*[t1 t2] pass, like scipy's J_h.dot(S).
+            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || !p->algebraic_subspace || !(ww >= 1e-3 * dd);
+            if (!p->algebraic_subspace) {
+                b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
+            } else if (!explicit_pass) {
                 const double h1d = -gg - reg * ggn, hdd = -ggn - reg * dd;
                 b12 = h1d - alpha * b11;
                 b22 = hdd - 2.0 * alpha * h1d + alpha * alpha * b11;
@@ -686,7 +694,7 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
-    if (const char* e = getenv("SBA_EXPLICIT_SUBSPACE")) p->explicit_subspace = atoi(e);
+    if (const char* e = getenv("SBA_ALGEBRAIC_SUBSPACE")) p->algebraic_subspace = atoi(e);
     const int rc = problem_create_impl(p, d);
     if (rc != SBA_OK) { sba_problem_destroy(p); return rc; }
     *out = p;

@@ -97,7 +97,7 @@ struct sba_problem {
     double *camsys_local = nullptr, *camsys = nullptr;     // [U (M*nc*nc) | g_c (M*nc)]
     double *S = nullptr;                                   // [S (ns*ns) | rhs (ns)], ns = M*nc
     double *chol_work = nullptr;                           // (ns+1)*ns scratch of the factorisation when ns > 160
-    int explicit_subspace = 0;                             // 1: always run the explicit J*[t1 t2] pass (validation)
+    int algebraic_subspace = 0;                            // 1: experimental B_S from normal-equation identities
     double *cam_partials = nullptr, *schur_partials = nullptr, *red_partials = nullptr;
     unsigned* counters = nullptr;
     double* scal = nullptr;          // device scalar block
