@@ -86,6 +86,7 @@ static ObsArrays obs_arrays(const sba_problem* p)
     ObsArrays o;
     o.cam_ind = p->cam_ind; o.pts_ind = p->pts_ind; o.pts2d = (const double2*)p->pts2d; o.w = p->w;
     o.track_ptr = p->track_ptr;
+    o.tile_obs = p->tile_obs; o.n_tiles = p->n_tiles;
     return o;
 }
 
@@ -169,9 +170,9 @@ static int run_assemble(sba_problem* p, const double* x, const double* camrec, i
 {
     const double* xp = x + (size_t)p->M * p->nc;
     {
-        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+        const int grid = (p->n_tiles + WPB - 1) / WPB;
 #define L(MODEL)                                                                                                      \
-    k_assemble_points<MODEL><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, camrec, p->rpc_tab, p->N, p->n_pts_fix, loss, \
+    k_assemble_points<MODEL><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, camrec, p->rpc_tab, p->n_pts_fix, loss,      \
                                                           f_scale, p->V, p->g + (size_t)p->M * p->nc, p->red_partials,   \
                                                           p->counters + 1, p->scal)
         SBA_DISPATCH_MODEL(p, L);
@@ -254,9 +255,9 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
     tm.begin(SBA_PH_POINT_PREP);
     {
-        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+        const int grid = (p->n_tiles + WPB - 1) / WPB;
 #define L(MODEL, NC)                                                                                                    \
-    k_point_prep<MODEL, NC><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, p->camrec, p->rpc_tab, p->N, ns, p->n_cam_fix, \
+    k_point_prep<MODEL, NC><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, p->camrec, p->rpc_tab, ns, p->n_cam_fix,       \
                                                          p->n_pts_fix, loss, f_scale, reg, p->V, p->g, p->sinv, p->F,    \
                                                          p->q, p->Z, p->scal)
         SBA_DISPATCH(p, L);
@@ -267,24 +268,25 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     tm.begin(SBA_PH_SCHUR);
     {
 #define SCHUR_ARGS                                                                                                     \
-    p->si_j, p->si_jp, p->si_chunk, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->Z, p->q,   \
+    p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->M, p->Z, p->q, p->item_base, \
         p->schur_partials
         switch (p->nc) {
-        case 3: k_schur<3, 0, 3><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 5: k_schur<5, 0, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 6: k_schur<6, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 8: k_schur<8, 0, 8><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 3: k_schur<3, 0, 3><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 5: k_schur<5, 0, 5><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 6: k_schur<6, 0, 6><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 8: k_schur<8, 0, 8><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 11:
-            k_schur<11, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            k_schur<11, 0, 6><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS);
             SBA_TRY(check_launch(p));
-            k_schur<11, 6, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            k_schur<11, 6, 5><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS);
             break;
         default: set_error("bad nc"); return SBA_E_INVALID;
         }
         SBA_TRY(check_launch(p));
 #undef SCHUR_ARGS
-#define FIN_ARGS                                                                                                  \
-    p->schur_partials, p->sb_first, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, reg, p->rank == 0, p->S
+#define FIN_ARGS                                                                                                       \
+    p->schur_partials, p->cam_ptr, p->item_base, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, reg,  \
+        p->rank == 0, p->S
         switch (p->nc) {
         case 3: k_schur_finalize<3><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
         case 5: k_schur_finalize<5><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
@@ -309,13 +311,13 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     tm.end();
     tm.begin(SBA_PH_BACKSUB);
     {
-        const int grid = grid_for(p->N, TPB, NUM_SMS * 16);
+        const int grid = (p->n_tiles + WPB - 1) / WPB;
         switch (p->nc) {
-        case 3: k_backsub<3><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
-        case 5: k_backsub<5><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
-        case 6: k_backsub<6><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
-        case 8: k_backsub<8><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
-        default: k_backsub<11><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->N, ns, p->F, p->q, p->Z, p->delta); break;
+        case 3: k_backsub<3><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
+        case 5: k_backsub<5><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
+        case 6: k_backsub<6><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
+        case 8: k_backsub<8><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
+        default: k_backsub<11><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
         }
         SBA_TRY(check_launch(p));
     }
@@ -340,6 +342,8 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
 
     SBA_TRY(run_prepare(p, p->x, p->camrec));
+    SBA_TRY(run_residual(p, p->x, p->camrec, loss, fs, nullptr, SC_COST_NEW, 0));   // cost at x0, same kernel as every later cost
+    SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
     SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
     int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0, explicit_passes = 0;
     double cost = 0.0, Delta = 0.0, g_norm = 0.0;
@@ -369,7 +373,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         SBA_TRY(fetch_scal(p));
         const double* h = p->h_scal;
         if (first) {
-            cost = h[SC_COST];
+            cost = h[SC_COST_NEW];
             if (!std::isfinite(cost)) { set_error("Residuals are not finite in the initial point."); return SBA_E_NUMERIC; }
             info->cost_init = cost;
             Delta = std::sqrt(h[SC_XS]);
@@ -540,8 +544,8 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     if (!p) return SBA_OK;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->cam_ind, p->pts_ind, p->track_ptr, p->pts2d, p->w, p->cam_static, p->rpc_tab, p->cm_obs, p->cm_pts,
-                    p->cam_ptr, p->obs_of, p->cm_pts2d, p->cm_w, p->chunks.cam, p->chunks.beg, p->chunks.end, p->si_j,
-                    p->si_jp, p->si_chunk, p->sb_first, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
+                    p->cam_ptr, p->obs_of, p->cm_pts2d, p->cm_w, p->chunks.cam, p->chunks.beg, p->chunks.end, p->item_base,
+                    p->tile_obs, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
                     p->t2, p->camrec, p->camrec_new, p->V, p->F, p->q, p->Z, p->camsys_local, p->S, p->cam_partials,
                     p->schur_partials, p->red_partials, p->counters, p->scal, p->r_out, p->io_x, p->chol_work};
     for (void* q : ptrs)
@@ -593,16 +597,28 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     p->chunks.n = (int)ch_cam.size();
     p->chunks.h_cam = ch_cam;
     p->chunks.h_first_of_cam = first_chunk;
-    // Schur work items: blocks (j <= j') x chunks of camera j
-    std::vector<int> si_j, si_jp, si_chunk, sb_first, sb_j, sb_jp;
+    // Schur: (j <= j') blocks; the partial of (chunk ch, partner j') lives at item_base[ch] + (j' - cam(ch))
+    std::vector<int> item_base(ch_cam.size() + 1, 0), sb_j, sb_jp;
+    for (size_t c = 0; c < ch_cam.size(); ++c) item_base[c + 1] = item_base[c] + (M - ch_cam[c]);
     for (int j = 0; j < M; ++j)
-        for (int jp = j; jp < M; ++jp) {
-            sb_first.push_back((int)si_j.size()); sb_j.push_back(j); sb_jp.push_back(jp);
-            for (int c = first_chunk[j]; c < first_chunk[j + 1]; ++c) { si_j.push_back(j); si_jp.push_back(jp); si_chunk.push_back(c); }
-        }
-    sb_first.push_back((int)si_j.size());
-    p->n_schur_items = (int)si_j.size();
+        for (int jp = j; jp < M; ++jp) { sb_j.push_back(j); sb_jp.push_back(jp); }
+    p->n_schur_items = item_base.back();
     p->n_schur_blocks = (int)sb_j.size();
+    // warp tiles: runs of whole tracks with <= 32 observations; a longer track is a tile of its own
+    std::vector<int> tile_obs;
+    tile_obs.push_back(0);
+    {
+        int cur = 0;   // observations in the open tile
+        for (int i = 0; i < N; ++i) {
+            const int L = track_ptr[i + 1] - track_ptr[i];
+            if (L == 0) continue;
+            if (cur > 0 && cur + L > 32) { tile_obs.push_back(track_ptr[i]); cur = 0; }
+            cur += L;
+            if (cur >= 32) { tile_obs.push_back(track_ptr[i + 1]); cur = 0; }
+        }
+        if (cur > 0) tile_obs.push_back(track_ptr[N]);
+    }
+    p->n_tiles = (int)tile_obs.size() - 1;
 
     SBA_TRY(dev_upload(&p->cam_ind, cam, s));
     SBA_TRY(dev_upload(&p->pts_ind, pts, s));
@@ -615,10 +631,8 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_upload(&p->chunks.cam, ch_cam, s));
     SBA_TRY(dev_upload(&p->chunks.beg, ch_beg, s));
     SBA_TRY(dev_upload(&p->chunks.end, ch_end, s));
-    SBA_TRY(dev_upload(&p->si_j, si_j, s));
-    SBA_TRY(dev_upload(&p->si_jp, si_jp, s));
-    SBA_TRY(dev_upload(&p->si_chunk, si_chunk, s));
-    SBA_TRY(dev_upload(&p->sb_first, sb_first, s));
+    SBA_TRY(dev_upload(&p->item_base, item_base, s));
+    SBA_TRY(dev_upload(&p->tile_obs, tile_obs, s));
     SBA_TRY(dev_upload(&p->sb_j, sb_j, s));
     SBA_TRY(dev_upload(&p->sb_jp, sb_jp, s));
 
@@ -646,6 +660,11 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_alloc(&p->camrec, (size_t)M * CAMREC_STRIDE)); SBA_TRY(dev_alloc(&p->camrec_new, (size_t)M * CAMREC_STRIDE));
     SBA_TRY(dev_alloc(&p->V, 6 * (size_t)N)); SBA_TRY(dev_alloc(&p->F, 6 * (size_t)N)); SBA_TRY(dev_alloc(&p->q, 3 * (size_t)N));
     SBA_TRY(dev_alloc(&p->Z, (size_t)K * nc * 3));
+    // tracks without observations are never touched by the tile kernels: their blocks must read as zero
+    for (double* buf : {p->g, p->sinv, p->delta, p->t1, p->t2, p->x_new}) SBA_CUDA(cudaMemsetAsync(buf, 0, n * sizeof(double), s));
+    SBA_CUDA(cudaMemsetAsync(p->V, 0, 6 * (size_t)N * sizeof(double), s));
+    SBA_CUDA(cudaMemsetAsync(p->F, 0, 6 * (size_t)N * sizeof(double), s));
+    SBA_CUDA(cudaMemsetAsync(p->q, 0, 3 * (size_t)N * sizeof(double), s));
     SBA_TRY(dev_alloc(&p->camsys_local, ns * nc + ns));
     if (p->world > 1) SBA_TRY(dev_alloc(&p->camsys, ns * nc + ns));
     else p->camsys = p->camsys_local;
@@ -655,7 +674,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_alloc(&p->cam_partials, (size_t)p->chunks.n * nv_cam));
     SBA_TRY(dev_alloc(&p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));
     SBA_CUDA(cudaMemsetAsync(p->schur_partials, 0, (size_t)p->n_schur_items * (nc * nc + nc) * sizeof(double), s));
-    SBA_TRY(dev_alloc(&p->red_partials, (size_t)NUM_SMS * 16 * 8));
+    SBA_TRY(dev_alloc(&p->red_partials, (size_t)std::max(NUM_SMS * 16, (p->n_tiles + WPB - 1) / WPB + 1) * 8));
     SBA_TRY(dev_alloc(&p->counters, 16));
     SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));
     SBA_TRY(dev_alloc(&p->scal, SC_COUNT));

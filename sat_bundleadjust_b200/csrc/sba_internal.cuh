@@ -85,9 +85,11 @@ struct sba_problem {
     int *cm_obs = nullptr, *cm_pts = nullptr, *cam_ptr = nullptr, *obs_of = nullptr;
     double *cm_pts2d = nullptr, *cm_w = nullptr;
     sba::ChunkTable chunks;
-    int n_schur_items = 0;   // (j, j', chunk) work items
-    int *si_j = nullptr, *si_jp = nullptr, *si_chunk = nullptr;                         // device: work items
-    int *sb_first = nullptr, *sb_j = nullptr, *sb_jp = nullptr;                          // device: (j,j') blocks
+    int n_schur_items = 0;   // (chunk, partner camera) partial slots
+    int *item_base = nullptr;                                  // device: first slot of every chunk (n_chunks + 1)
+    int *sb_j = nullptr, *sb_jp = nullptr;                     // device: (j,j') blocks
+    int *tile_obs = nullptr;                                   // device: warp-tile observation offsets (n_tiles + 1)
+    int n_tiles = 0;
     int n_schur_blocks = 0;
 
     // iteration state (device)

@@ -3,6 +3,9 @@
 // Data layout in HBM (all FP64 values, int32 indices):
 //   track-major (the reference's observation order, bundle_adjust/ba_params.py:138-149):
 //       cam_ind[K], pts_ind[K], pts2d[K] (double2), w[K], track_ptr[N+1]
+//       tile_obs[T+1]: "warp tiles" = runs of whole tracks holding <= 32 observations (one observation per
+//       lane, point blocks reduced inside the warp through shared memory); a track longer than 32
+//       observations forms a tile of its own and is looped over by its warp
 //   camera-major copy (static, built once): cm_obs[K] (observation id), cm_pts[K], cm_pts2d[K], cm_w[K],
 //       cam_ptr[M+1]; chunk table = (camera, [beg,end)) work items of <= CHUNK observations
 //   obs_of[M][N]: observation id of (camera, track) or -1
@@ -17,7 +20,8 @@
 namespace sba {
 
 constexpr int TPB = 128;          // threads per block of the reduction kernels
-constexpr int CHUNK = 2048;       // observations per camera-major work item
+constexpr int CHUNK = 1024;       // observations per camera-major work item
+constexpr int WPB = TPB / 32;     // warps (= tiles) per block of the tile kernels
 
 // ------------------------------------------------------------------------------------------------
 // reductions
@@ -96,21 +100,7 @@ struct Slots {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void write_camrec(const double (&v)[MAX_CAM_PARAMS], double* __restrict__ r, int model)
 {
-    double sn, cs;
-    sincos(v[0], &sn, &cs); r[0] = cs; r[1] = sn;
-    sincos(v[1], &sn, &cs); r[2] = cs; r[3] = sn;
-    sincos(v[2], &sn, &cs); r[4] = cs; r[5] = sn;
-    if (model == MODEL_PERSPECTIVE) {
-        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
-        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = v[9]; r[13] = v[10];
-    } else if (model == MODEL_AFFINE) {
-        r[6] = v[3]; r[7] = v[4]; r[8] = 0.0;
-        r[9] = v[5]; r[10] = v[6]; r[11] = v[7]; r[12] = 0.0; r[13] = 0.0;
-    } else {
-        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
-        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = 0.0; r[13] = 0.0;
-    }
-    r[14] = 0.0; r[15] = 0.0;
+    build_camrec(v, model, r);
 }
 
 __global__ void k_prepare_cameras(const double* __restrict__ x, const double* __restrict__ cam_static,
@@ -138,13 +128,11 @@ struct ObsEval {
     double Jp[6];
 };
 
-template <int MODEL, int NC>
-__device__ __forceinline__ void eval_obs(const CamRec& c, const double* __restrict__ rpc_j, double X, double Y,
-                                         double Z, double ox, double oy, double w, int loss, double f_scale,
-                                         bool cam_free, bool pt_free, ObsEval<MODEL, NC>& e)
+// robust rescale of one observation's residual pair and Jacobian rows (weights folded in)
+template <int MODEL, int NC, bool WITH_JP>
+__device__ __forceinline__ void finish_obs(double u, double v, double ox, double oy, double w, int loss, double f_scale,
+                                           bool cam_free, bool pt_free, ObsEval<MODEL, NC>& e)
 {
-    double u, v;
-    project_jac<MODEL, NC>(c, rpc_j, X, Y, Z, u, v, e.Jc, e.Jp);
     double f0 = w * (u - ox), f1 = w * (v - oy), c0, c1;
     const double s0 = w * loss_rescale(loss, f_scale, f0, c0);
     const double s1 = w * loss_rescale(loss, f_scale, f1, c1);
@@ -152,9 +140,33 @@ __device__ __forceinline__ void eval_obs(const CamRec& c, const double* __restri
     const double a0 = cam_free ? s0 : 0.0, a1 = cam_free ? s1 : 0.0;
 #pragma unroll
     for (int k = 0; k < NC; ++k) { e.Jc[k] *= a0; e.Jc[NC + k] *= a1; }
-    const double b0 = pt_free ? s0 : 0.0, b1 = pt_free ? s1 : 0.0;
+    if (WITH_JP) {
+        const double b0 = pt_free ? s0 : 0.0, b1 = pt_free ? s1 : 0.0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { e.Jp[k] *= b0; e.Jp[3 + k] *= b1; }
+        for (int k = 0; k < 3; ++k) { e.Jp[k] *= b0; e.Jp[3 + k] *= b1; }
+    }
+}
+
+// camera block (+ point block) of one observation
+template <int MODEL, int NC, bool WITH_JP>
+__device__ __forceinline__ void eval_obs(const double* __restrict__ rec, const double* __restrict__ rpc_j, double X,
+                                         double Y, double Z, double ox, double oy, double w, int loss, double f_scale,
+                                         bool cam_free, bool pt_free, ObsEval<MODEL, NC>& e)
+{
+    double u, v;
+    full_side<MODEL, NC, WITH_JP>(rec, rpc_j, X, Y, Z, u, v, e.Jc, e.Jp);
+    finish_obs<MODEL, NC, WITH_JP>(u, v, ox, oy, w, loss, f_scale, cam_free, pt_free, e);
+}
+
+// point block only
+template <int MODEL>
+__device__ __forceinline__ void eval_obs_point(const double* __restrict__ rec, const double* __restrict__ rpc_j,
+                                               double X, double Y, double Z, double ox, double oy, double w, int loss,
+                                               double f_scale, bool pt_free, ObsEval<MODEL, 0>& e)
+{
+    double u, v;
+    point_side<MODEL>(rec, rpc_j, X, Y, Z, u, v, e.Jp);
+    finish_obs<MODEL, 0, true>(u, v, ox, oy, w, loss, f_scale, false, pt_free, e);
 }
 
 struct ObsArrays {
@@ -163,7 +175,29 @@ struct ObsArrays {
     const double2* pts2d;
     const double* w;
     const int* track_ptr;
+    const int* tile_obs;     // T+1 observation offsets of the warp tiles
+    int n_tiles;
 };
+
+// tile of this warp: first observation and number of observations (0 when the warp has no tile)
+__device__ __forceinline__ void warp_tile(const ObsArrays& o, int& ob, int& nobs)
+{
+    const int tile = blockIdx.x * WPB + (threadIdx.x >> 5);
+    ob = 0; nobs = 0;
+    if (tile < o.n_tiles) { ob = o.tile_obs[tile]; nobs = o.tile_obs[tile + 1] - ob; }
+}
+
+template <int NV>
+__device__ __forceinline__ void warp_allreduce_sum(double (&v)[NV])
+{
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        v[k] = x;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // G1: residual `fun` (+ robust cost)
@@ -197,44 +231,97 @@ k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// G2a: point side of the assembly -- V_i = sum Jp^T Jp, g_p = sum Jp^T f, one thread per track
+// G2a: point side of the assembly -- V_i = sum Jp^T Jp, g_p = sum Jp^T f.
+// One observation per lane (coalesced index / observation loads, no divergence in the Jacobian); the 9 sums
+// of each track are formed by the lane of its first observation from the warp's shared-memory slice.
 // ------------------------------------------------------------------------------------------------
 template <int MODEL>
 __global__ void __launch_bounds__(TPB)
 k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
-                  const double* __restrict__ rpc_tab, int N, int n_pts_fix, int loss, double f_scale,
+                  const double* __restrict__ rpc_tab, int n_pts_fix, int loss, double f_scale,
                   double* __restrict__ V, double* __restrict__ gp_out, double* partials, unsigned* counter,
                   double* scal)
 {
+    __shared__ double sv[WPB][9][32];
     __shared__ double sm[1 * (TPB / 32)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ob, nobs;
+    warp_tile(o, ob, nobs);
     double acc[1] = {0.0};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const int beg = o.track_ptr[i], end = o.track_ptr[i + 1];
-        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
-        const bool pt_free = i >= n_pts_fix;
-        double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-        for (int a = beg; a < end; ++a) {
+    if (nobs <= 32) {
+        double vals[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vals[k] = 0.0;
+        int i = -1, a = -1;
+        if (lane < nobs) {
+            a = ob + lane;
+            i = o.pts_ind[a];
             const int j = o.cam_ind[a];
-            const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
-            const double2 ob = o.pts2d[a];
+            const double2 ob2 = o.pts2d[a];
             ObsEval<MODEL, 0> e;
-            eval_obs<MODEL, 0>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x,
-                               ob.y, o.w[a], loss, f_scale, false, pt_free, e);
-            acc[0] += e.cost;
-            v[0] += e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
-            v[1] += e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
-            v[2] += e.Jp[0] * e.Jp[2] + e.Jp[3] * e.Jp[5];
-            v[3] += e.Jp[1] * e.Jp[1] + e.Jp[4] * e.Jp[4];
-            v[4] += e.Jp[1] * e.Jp[2] + e.Jp[4] * e.Jp[5];
-            v[5] += e.Jp[2] * e.Jp[2] + e.Jp[5] * e.Jp[5];
-            g[0] += e.Jp[0] * e.f0 + e.Jp[3] * e.f1;
-            g[1] += e.Jp[1] * e.f0 + e.Jp[4] * e.f1;
-            g[2] += e.Jp[2] * e.f0 + e.Jp[5] * e.f1;
+            eval_obs_point<MODEL>(camrec + (size_t)j * CAMREC_STRIDE,
+                                  MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, xp[3 * (size_t)i],
+                                  xp[3 * (size_t)i + 1], xp[3 * (size_t)i + 2], ob2.x, ob2.y, o.w[a], loss, f_scale,
+                                  i >= n_pts_fix, e);
+            acc[0] = e.cost;
+            vals[0] = e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
+            vals[1] = e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
+            vals[2] = e.Jp[0] * e.Jp[2] + e.Jp[3] * e.Jp[5];
+            vals[3] = e.Jp[1] * e.Jp[1] + e.Jp[4] * e.Jp[4];
+            vals[4] = e.Jp[1] * e.Jp[2] + e.Jp[4] * e.Jp[5];
+            vals[5] = e.Jp[2] * e.Jp[2] + e.Jp[5] * e.Jp[5];
+            vals[6] = e.Jp[0] * e.f0 + e.Jp[3] * e.f1;
+            vals[7] = e.Jp[1] * e.f0 + e.Jp[4] * e.f1;
+            vals[8] = e.Jp[2] * e.f0 + e.Jp[5] * e.f1;
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) V[6 * (size_t)i + k] = v[k];
+        for (int k = 0; k < 9; ++k) sv[warp][k][lane] = vals[k];
+        __syncwarp();
+        if (lane < nobs) {
+            const int beg = o.track_ptr[i];
+            if (a == beg) {
+                const int L = o.track_ptr[i + 1] - beg;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) gp_out[3 * (size_t)i + k] = g[k];
+                for (int k = 0; k < 9; ++k) {
+                    double t = 0.0;
+                    for (int m = 0; m < L; ++m) t += sv[warp][k][lane + m];
+                    if (k < 6) V[6 * (size_t)i + k] = t;
+                    else gp_out[3 * (size_t)i + (k - 6)] = t;
+                }
+            }
+        }
+    } else {
+        // a single long track: the warp strides over its observations
+        const int i = o.pts_ind[ob];
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        double vals[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vals[k] = 0.0;
+        for (int a = ob + lane; a < ob + nobs; a += 32) {
+            const int j = o.cam_ind[a];
+            const double2 ob2 = o.pts2d[a];
+            ObsEval<MODEL, 0> e;
+            eval_obs_point<MODEL>(camrec + (size_t)j * CAMREC_STRIDE,
+                                  MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob2.x, ob2.y,
+                                  o.w[a], loss, f_scale, i >= n_pts_fix, e);
+            acc[0] += e.cost;
+            vals[0] += e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
+            vals[1] += e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
+            vals[2] += e.Jp[0] * e.Jp[2] + e.Jp[3] * e.Jp[5];
+            vals[3] += e.Jp[1] * e.Jp[1] + e.Jp[4] * e.Jp[4];
+            vals[4] += e.Jp[1] * e.Jp[2] + e.Jp[4] * e.Jp[5];
+            vals[5] += e.Jp[2] * e.Jp[2] + e.Jp[5] * e.Jp[5];
+            vals[6] += e.Jp[0] * e.f0 + e.Jp[3] * e.f1;
+            vals[7] += e.Jp[1] * e.f0 + e.Jp[4] * e.f1;
+            vals[8] += e.Jp[2] * e.f0 + e.Jp[5] * e.f1;
+        }
+        warp_allreduce_sum<9>(vals);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) V[6 * (size_t)i + k] = vals[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gp_out[3 * (size_t)i + k] = vals[6 + k];
+        }
     }
     const double tot = block_reduce_sum<1, TPB>(acc, sm);
     __shared__ int slots[1];
@@ -260,25 +347,27 @@ k_assemble_cameras(const int* __restrict__ chunk_cam, const int* __restrict__ ch
 {
     constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
     __shared__ double sm[NV * (TPB / 32)];
+    __shared__ double srec[CAMREC_STRIDE];
     const int ch = blockIdx.x, j = chunk_cam[ch];
+    if (threadIdx.x < CAMREC_STRIDE) srec[threadIdx.x] = camrec[(size_t)j * CAMREC_STRIDE + threadIdx.x];
+    __syncthreads();
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
     if (j >= n_cam_fix) {
-        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
         const double* rpc_j = MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr;
         for (int t = chunk_beg[ch] + threadIdx.x; t < chunk_end[ch]; t += TPB) {
             const int i = cm_pts[t];
             const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
             const double2 ob = cm_pts2d[t];
             ObsEval<MODEL, NC> e;
-            eval_obs<MODEL, NC>(c, rpc_j, X, Y, Z, ob.x, ob.y, cm_w[t], loss, f_scale, true, false, e);
+            eval_obs<MODEL, NC, false>(srec, rpc_j, X, Y, Z, ob.x, ob.y, cm_w[t], loss, f_scale, true, false, e);
             int k = 0;
 #pragma unroll
             for (int r = 0; r < NC; ++r) {
 #pragma unroll
-                for (int s = 0; s <= r; ++s) {
-                    acc[k] += e.Jc[r] * e.Jc[s] + e.Jc[NC + r] * e.Jc[NC + s];
+                for (int c = 0; c <= r; ++c) {
+                    acc[k] += e.Jc[r] * e.Jc[c] + e.Jc[NC + r] * e.Jc[NC + c];
                     ++k;
                 }
             }
@@ -389,12 +478,12 @@ k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ cam
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
         const int j = o.cam_ind[a], i = o.pts_ind[a];
-        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
         const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
         const double2 ob = o.pts2d[a];
         ObsEval<MODEL, NC> e;
-        eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x, ob.y,
-                            o.w[a], loss, f_scale, j >= n_cam_fix, i >= n_pts_fix, e);
+        eval_obs<MODEL, NC, true>(camrec + (size_t)j * CAMREC_STRIDE,
+                                  MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x, ob.y,
+                                  o.w[a], loss, f_scale, j >= n_cam_fix, i >= n_pts_fix, e);
         double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -420,126 +509,203 @@ k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ cam
 
 // ------------------------------------------------------------------------------------------------
 // G3a: point elimination prep -- damped 3x3 block -> inverse Cholesky factor G (lower, 6 values),
-//      q = G g_p, and per observation Z = (Jc^T Jp) G^T  (nc x 3), one thread per track
+//      q = G g_p, and per observation Z = (Jc^T Jp) G^T  (nc x 3).
+// Warp tiles: the lane of a track's first observation inverts its block and publishes G through shared
+// memory; every lane then builds its observation's Z, which leaves the warp as one contiguous, coalesced
+// span (observations of a tile are adjacent in Z) staged through shared memory.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool invert_point_block(const double* __restrict__ v, double s0, double s1, double s2,
+                                                   double reg, double G[6])
+{
+    const double a00 = v[0] + reg * s0 * s0, a10 = v[1], a20 = v[2];
+    const double a11 = v[3] + reg * s1 * s1, a21 = v[4], a22 = v[5] + reg * s2 * s2;
+    bool ok = a00 > 0.0;
+    const double c00 = sqrt(a00), c10 = a10 / c00, c20 = a20 / c00;
+    const double d11 = a11 - c10 * c10;
+    ok = ok && d11 > 0.0;
+    const double c11 = sqrt(d11), c21 = (a21 - c20 * c10) / c11;
+    const double d22 = a22 - c20 * c20 - c21 * c21;
+    ok = ok && d22 > 0.0;
+    const double c22 = sqrt(d22);
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) G[k] = 0.0;
+        return false;
+    }
+    G[0] = 1.0 / c00; G[2] = 1.0 / c11; G[5] = 1.0 / c22;     // g00 g10 g11 g20 g21 g22
+    G[1] = -c10 * G[0] * G[2];
+    G[4] = -c21 * G[2] * G[5];
+    G[3] = -(c20 * G[0] + c21 * G[1]) * G[5];
+    return true;
+}
+
+// G, q of track i (frozen or degenerate points get G = 0, i.e. no step and no coupling)
+__device__ __forceinline__ void point_factor(int i, int ns, int n_pts_fix, double reg, const double* __restrict__ V,
+                                             const double* __restrict__ g, const double* __restrict__ sinv,
+                                             double* __restrict__ F, double* __restrict__ q, double* scal, double G[6])
+{
+    double qq[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) G[k] = 0.0;
+    if (i >= n_pts_fix) {
+        const size_t e = ns + 3 * (size_t)i;
+        if (invert_point_block(V + 6 * (size_t)i, sinv[e], sinv[e + 1], sinv[e + 2], reg, G)) {
+            const double g0 = g[e], g1 = g[e + 1], g2 = g[e + 2];
+            qq[0] = G[0] * g0;
+            qq[1] = G[1] * g0 + G[2] * g1;
+            qq[2] = G[3] * g0 + G[4] * g1 + G[5] * g2;
+        } else {
+            atomicAdd(scal + SC_BAD_POINTS, 1.0);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F[6 * (size_t)i + k] = G[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[3 * (size_t)i + k] = qq[k];
+}
+
+template <int MODEL, int NC>
+__device__ __forceinline__ void obs_Z(const ObsEval<MODEL, NC>& e, const double G[6], double* __restrict__ z)
+{
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+        const double w0 = e.Jc[r] * e.Jp[0] + e.Jc[NC + r] * e.Jp[3];
+        const double w1 = e.Jc[r] * e.Jp[1] + e.Jc[NC + r] * e.Jp[4];
+        const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
+        z[3 * r + 0] = w0 * G[0];
+        z[3 * r + 1] = w0 * G[1] + w1 * G[2];
+        z[3 * r + 2] = w0 * G[3] + w1 * G[4] + w2 * G[5];
+    }
+}
+
 template <int MODEL, int NC>
 __global__ void __launch_bounds__(TPB)
 k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
-             const double* __restrict__ rpc_tab, int N, int ns, int n_cam_fix, int n_pts_fix, int loss,
+             const double* __restrict__ rpc_tab, int ns, int n_cam_fix, int n_pts_fix, int loss,
              double f_scale, double reg, const double* __restrict__ V, const double* __restrict__ g,
              const double* __restrict__ sinv, double* __restrict__ F, double* __restrict__ q, double* __restrict__ Zout,
              double* scal)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const int beg = o.track_ptr[i], end = o.track_ptr[i + 1];
-        double G[6] = {0, 0, 0, 0, 0, 0};   // g00 g10 g11 g20 g21 g22
-        double qq[3] = {0, 0, 0};
-        const bool pt_free = i >= n_pts_fix;
-        if (pt_free) {
-            const double* v = V + 6 * (size_t)i;
-            const double s0 = sinv[ns + 3 * (size_t)i], s1 = sinv[ns + 3 * (size_t)i + 1], s2 = sinv[ns + 3 * (size_t)i + 2];
-            const double a00 = v[0] + reg * s0 * s0, a10 = v[1], a20 = v[2];
-            const double a11 = v[3] + reg * s1 * s1, a21 = v[4], a22 = v[5] + reg * s2 * s2;
-            bool ok = a00 > 0.0;
-            const double c00 = sqrt(a00), c10 = a10 / c00, c20 = a20 / c00;
-            const double d11 = a11 - c10 * c10;
-            ok = ok && d11 > 0.0;
-            const double c11 = sqrt(d11), c21 = (a21 - c20 * c10) / c11;
-            const double d22 = a22 - c20 * c20 - c21 * c21;
-            ok = ok && d22 > 0.0;
-            const double c22 = sqrt(d22);
-            if (ok) {
-                G[0] = 1.0 / c00; G[2] = 1.0 / c11; G[5] = 1.0 / c22;
-                G[1] = -c10 * G[0] * G[2];
-                G[4] = -c21 * G[2] * G[5];
-                G[3] = -(c20 * G[0] + c21 * G[1]) * G[5];
-                const double g0 = g[ns + 3 * (size_t)i], g1 = g[ns + 3 * (size_t)i + 1], g2 = g[ns + 3 * (size_t)i + 2];
-                qq[0] = G[0] * g0;
-                qq[1] = G[1] * g0 + G[2] * g1;
-                qq[2] = G[3] * g0 + G[4] * g1 + G[5] * g2;
-            } else {
-                atomicAdd(scal + SC_BAD_POINTS, 1.0);
+    constexpr int ZS = NC * 3, ZP = ZS + 1;      // padded lane stride (odd): conflict-free 64-bit accesses
+    __shared__ double sG[WPB][6][32];
+    __shared__ double sZ[WPB][32 * ZP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ob, nobs;
+    warp_tile(o, ob, nobs);
+    if (nobs == 0) return;
+    if (nobs <= 32) {
+        int i = -1, a = -1, beg = 0;
+        if (lane < nobs) {
+            a = ob + lane;
+            i = o.pts_ind[a];
+            beg = o.track_ptr[i];
+            if (a == beg) {
+                double G[6];
+                point_factor(i, ns, n_pts_fix, reg, V, g, sinv, F, q, scal, G);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sG[warp][k][lane] = G[k];
             }
         }
+        __syncwarp();
+        if (lane < nobs) {
+            double G[6];
+            const int hl = beg - ob;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) F[6 * (size_t)i + k] = G[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) q[3 * (size_t)i + k] = qq[k];
-        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
-        for (int a = beg; a < end; ++a) {
+            for (int k = 0; k < 6; ++k) G[k] = sG[warp][k][hl];
             const int j = o.cam_ind[a];
-            const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
-            const double2 ob = o.pts2d[a];
+            const double2 ob2 = o.pts2d[a];
             ObsEval<MODEL, NC> e;
-            eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob.x,
-                                ob.y, o.w[a], loss, f_scale, j >= n_cam_fix, pt_free, e);
-            double* z = Zout + (size_t)a * NC * 3;
+            eval_obs<MODEL, NC, true>(camrec + (size_t)j * CAMREC_STRIDE,
+                                      MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr,
+                                      xp[3 * (size_t)i], xp[3 * (size_t)i + 1], xp[3 * (size_t)i + 2], ob2.x, ob2.y, o.w[a],
+                                      loss, f_scale, j >= n_cam_fix, i >= n_pts_fix, e);
+            obs_Z<MODEL, NC>(e, G, &sZ[warp][lane * ZP]);
+        }
+        __syncwarp();
+        double* dst = Zout + (size_t)ob * ZS;
+        for (int t = lane; t < nobs * ZS; t += 32) dst[t] = sZ[warp][(t / ZS) * ZP + (t % ZS)];
+    } else {
+        const int i = o.pts_ind[ob];
+        double G[6];
+        if (lane == 0) point_factor(i, ns, n_pts_fix, reg, V, g, sinv, F, q, scal, G);
 #pragma unroll
-            for (int r = 0; r < NC; ++r) {
-                const double w0 = e.Jc[r] * e.Jp[0] + e.Jc[NC + r] * e.Jp[3];
-                const double w1 = e.Jc[r] * e.Jp[1] + e.Jc[NC + r] * e.Jp[4];
-                const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
-                z[3 * r + 0] = w0 * G[0];
-                z[3 * r + 1] = w0 * G[1] + w1 * G[2];
-                z[3 * r + 2] = w0 * G[3] + w1 * G[4] + w2 * G[5];
-            }
+        for (int k = 0; k < 6; ++k) G[k] = __shfl_sync(0xffffffffu, G[k], 0);
+        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
+        for (int a = ob + lane; a < ob + nobs; a += 32) {
+            const int j = o.cam_ind[a];
+            const double2 ob2 = o.pts2d[a];
+            ObsEval<MODEL, NC> e;
+            eval_obs<MODEL, NC, true>(camrec + (size_t)j * CAMREC_STRIDE,
+                                      MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, ob2.x,
+                                      ob2.y, o.w[a], loss, f_scale, j >= n_cam_fix, i >= n_pts_fix, e);
+            obs_Z<MODEL, NC>(e, G, Zout + (size_t)a * ZS);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// G3b: Schur complement blocks.  Work item = (camera j, camera j' >= j, chunk of camera j's
-// observations); for every track seen by both, acc += Z_a Z_b^T in registers (rows ROW0..ROW0+NR-1);
-// the diagonal items also accumulate Z_a q_i for the right-hand side.  No atomics.
+// G3b: Schur complement blocks.  Work item = one chunk (<= CHUNK observations) of camera j; the block
+// walks over the partner cameras j' = j..M-1 in turn and, for every track of the chunk also seen by j',
+// adds Z_a Z_b^T in registers (rows ROW0..ROW0+NR-1); j' = j also accumulates Z_a q_i for the right-hand
+// side.  The chunk's own Z_a records are re-read once per partner and stay L1-resident; the partners'
+// Z_b records are streamed past L1 (ld.global.cg).  No atomics: one partial per (chunk, j'), summed in a
+// fixed order by k_schur_finalize.
 // ------------------------------------------------------------------------------------------------
 template <int NC, int ROW0, int NR>
 __global__ void __launch_bounds__(TPB)
-k_schur(const int* __restrict__ si_j, const int* __restrict__ si_jp, const int* __restrict__ si_chunk,
-        const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end, const int* __restrict__ cm_obs,
-        const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N, const double* __restrict__ Zin,
-        const double* __restrict__ q, double* __restrict__ schur_partials)
+k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
+        const int* __restrict__ cm_obs, const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N, int M,
+        const double* __restrict__ Zin, const double* __restrict__ q, const int* __restrict__ item_base,
+        double* __restrict__ schur_partials)
 {
     constexpr int NV = NR * NC + NR, NVALL = NC * NC + NC;
     __shared__ double sm[NV * (TPB / 32)];
-    const int item = blockIdx.x, j = si_j[item], jp = si_jp[item], ch = si_chunk[item];
-    const bool diag = (j == jp);
-    double acc[NV];
+    const int ch = blockIdx.x, j = chunk_cam[ch], beg = chunk_beg[ch], end = chunk_end[ch];
+    for (int jp = j; jp < M; ++jp) {
+        const bool diag = (jp == j);
+        double acc[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    const int* row = obs_of + (size_t)jp * N;
-    for (int t = chunk_beg[ch] + threadIdx.x; t < chunk_end[ch]; t += TPB) {
-        const int a = cm_obs[t], i = cm_pts[t];
-        const int b = diag ? a : row[i];
-        if (b < 0) continue;
-        const double* za = Zin + (size_t)a * NC * 3 + ROW0 * 3;
-        const double* zb = Zin + (size_t)b * NC * 3;
-        double A[NR * 3];
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        const int* row = obs_of + (size_t)jp * N;
+        for (int t = beg + threadIdx.x; t < end; t += TPB) {
+            const int a = cm_obs[t], i = cm_pts[t];
+            const int b = diag ? a : row[i];
+            if (b < 0) continue;
+            const double* za = Zin + (size_t)a * NC * 3 + ROW0 * 3;
+            const double* zb = Zin + (size_t)b * NC * 3;
+            double A[NR * 3];
 #pragma unroll
-        for (int k = 0; k < NR * 3; ++k) A[k] = za[k];
+            for (int k = 0; k < NR * 3; ++k) A[k] = za[k];
 #pragma unroll
-        for (int s = 0; s < NC; ++s) {
-            const double b0 = zb[3 * s], b1 = zb[3 * s + 1], b2 = zb[3 * s + 2];
+            for (int s = 0; s < NC; ++s) {
+                const double b0 = diag ? zb[3 * s] : __ldcg(zb + 3 * s);
+                const double b1 = diag ? zb[3 * s + 1] : __ldcg(zb + 3 * s + 1);
+                const double b2 = diag ? zb[3 * s + 2] : __ldcg(zb + 3 * s + 2);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r * NC + s] += A[3 * r] * b0 + A[3 * r + 1] * b1 + A[3 * r + 2] * b2;
+                for (int r = 0; r < NR; ++r) acc[r * NC + s] += A[3 * r] * b0 + A[3 * r + 1] * b1 + A[3 * r + 2] * b2;
+            }
+            if (diag) {
+                const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;
+            }
         }
-        if (diag) {
-            const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;
+        const double tot = block_reduce_sum<NV, TPB>(acc, sm);
+        if (threadIdx.x < NV) {
+            const int k = threadIdx.x;
+            const int pos = (k < NR * NC) ? (ROW0 * NC + k) : (NC * NC + ROW0 + (k - NR * NC));
+            // partial of (chunk ch, partner jp): item = item_base[ch] + (jp - j)
+            schur_partials[(size_t)(item_base[ch] + (jp - j)) * NVALL + pos] = tot;
         }
-    }
-    const double tot = block_reduce_sum<NV, TPB>(acc, sm);
-    if (threadIdx.x < NV) {
-        const int k = threadIdx.x;
-        const int pos = (k < NR * NC) ? (ROW0 * NC + k) : (NC * NC + ROW0 + (k - NR * NC));
-        schur_partials[(size_t)item * NVALL + pos] = tot;
     }
 }
 
-// one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum items ; rhs_j = -g_j + sum
+// one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum over the chunks of camera j ;
+// rhs_j = -g_j + sum.  Items of chunk ch are laid out as item_base[ch] + (j' - j).
 template <int NC>
-__global__ void k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ sb_first,
-                                 const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M, int n_cam_fix,
+__global__ void k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ first_chunk,
+                                 const int* __restrict__ item_base, const int* __restrict__ sb_j,
+                                 const int* __restrict__ sb_jp, int M, int n_cam_fix,
                                  const double* __restrict__ camsys_local, const double* __restrict__ sinv, double reg,
                                  int add_diag, double* __restrict__ S)
 {
@@ -549,7 +715,8 @@ __global__ void k_schur_finalize(const double* __restrict__ schur_partials, cons
     const int j = sb_j[blk], jp = sb_jp[blk];
     const int ns = M * NC;
     double s = 0.0;
-    for (int it = sb_first[blk]; it < sb_first[blk + 1]; ++it) s += schur_partials[(size_t)it * NVALL + k];
+    for (int ch = first_chunk[j]; ch < first_chunk[j + 1]; ++ch)
+        s += schur_partials[(size_t)(item_base[ch] + (jp - j)) * NVALL + k];
     if (k < NC * NC) {
         const int r = k / NC, c = k % NC;
         double val = -s;
@@ -569,28 +736,71 @@ __global__ void k_schur_finalize(const double* __restrict__ schur_partials, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// G6: back-substitution  dp_i = -G^T (q_i + sum_a Z_a^T dc_cam(a)), one thread per track
+// G6: back-substitution  dp_i = -G^T (q_i + sum_a Z_a^T dc_cam(a)), warp tiles like k_point_prep
 // ------------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(TPB)
-k_backsub(ObsArrays o, int N, int ns, const double* __restrict__ F, const double* __restrict__ q,
+k_backsub(ObsArrays o, int ns, const double* __restrict__ F, const double* __restrict__ q,
           const double* __restrict__ Zin, double* __restrict__ delta)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        double s0 = q[3 * (size_t)i], s1 = q[3 * (size_t)i + 1], s2 = q[3 * (size_t)i + 2];
-        for (int a = o.track_ptr[i]; a < o.track_ptr[i + 1]; ++a) {
+    constexpr int ZS = NC * 3, ZP = ZS + 1;
+    __shared__ double sv[WPB][3][32];
+    __shared__ double sZ[WPB][32 * ZP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ob, nobs;
+    warp_tile(o, ob, nobs);
+    if (nobs == 0) return;
+    if (nobs <= 32) {
+        const double* src = Zin + (size_t)ob * ZS;
+        for (int t = lane; t < nobs * ZS; t += 32) sZ[warp][(t / ZS) * ZP + (t % ZS)] = src[t];
+        __syncwarp();
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        int i = -1, a = -1;
+        if (lane < nobs) {
+            a = ob + lane;
+            i = o.pts_ind[a];
             const int j = o.cam_ind[a];
-            const double* z = Zin + (size_t)a * NC * 3;
+            const double* z = &sZ[warp][lane * ZP];
 #pragma unroll
             for (int r = 0; r < NC; ++r) {
                 const double dc = delta[(size_t)j * NC + r];
                 s0 += z[3 * r] * dc; s1 += z[3 * r + 1] * dc; s2 += z[3 * r + 2] * dc;
             }
         }
-        const double* G = F + 6 * (size_t)i;
-        delta[ns + 3 * (size_t)i + 0] = -(G[0] * s0 + G[1] * s1 + G[3] * s2);
-        delta[ns + 3 * (size_t)i + 1] = -(G[2] * s1 + G[4] * s2);
-        delta[ns + 3 * (size_t)i + 2] = -(G[5] * s2);
+        sv[warp][0][lane] = s0; sv[warp][1][lane] = s1; sv[warp][2][lane] = s2;
+        __syncwarp();
+        if (lane < nobs) {
+            const int beg = o.track_ptr[i];
+            if (a == beg) {
+                const int L = o.track_ptr[i + 1] - beg;
+                double t0 = q[3 * (size_t)i], t1 = q[3 * (size_t)i + 1], t2 = q[3 * (size_t)i + 2];
+                for (int m = 0; m < L; ++m) { t0 += sv[warp][0][lane + m]; t1 += sv[warp][1][lane + m]; t2 += sv[warp][2][lane + m]; }
+                const double* G = F + 6 * (size_t)i;
+                delta[ns + 3 * (size_t)i + 0] = -(G[0] * t0 + G[1] * t1 + G[3] * t2);
+                delta[ns + 3 * (size_t)i + 1] = -(G[2] * t1 + G[4] * t2);
+                delta[ns + 3 * (size_t)i + 2] = -(G[5] * t2);
+            }
+        }
+    } else {
+        const int i = o.pts_ind[ob];
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int a = ob + lane; a < ob + nobs; a += 32) {
+            const int j = o.cam_ind[a];
+            const double* z = Zin + (size_t)a * ZS;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) {
+                const double dc = delta[(size_t)j * NC + r];
+                s[0] += z[3 * r] * dc; s[1] += z[3 * r + 1] * dc; s[2] += z[3 * r + 2] * dc;
+            }
+        }
+        warp_allreduce_sum<3>(s);
+        if (lane == 0) {
+            const double t0 = s[0] + q[3 * (size_t)i], t1 = s[1] + q[3 * (size_t)i + 1], t2 = s[2] + q[3 * (size_t)i + 2];
+            const double* G = F + 6 * (size_t)i;
+            delta[ns + 3 * (size_t)i + 0] = -(G[0] * t0 + G[1] * t1 + G[3] * t2);
+            delta[ns + 3 * (size_t)i + 1] = -(G[2] * t1 + G[4] * t2);
+            delta[ns + 3 * (size_t)i + 2] = -(G[5] * t2);
+        }
     }
 }
 
@@ -692,12 +902,12 @@ __global__ void k_jac_blocks(ObsArrays o, const double* __restrict__ xp, const d
 {
     for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
         const int j = o.cam_ind[a], i = o.pts_ind[a];
-        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
         const double2 ob = o.pts2d[a];
         ObsEval<MODEL, NC> e;
-        eval_obs<MODEL, NC>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, xp[3 * (size_t)i],
-                            xp[3 * (size_t)i + 1], xp[3 * (size_t)i + 2], ob.x, ob.y, o.w[a], LOSS_LINEAR, 1.0,
-                            j >= n_cam_fix, i >= n_pts_fix, e);
+        eval_obs<MODEL, NC, true>(camrec + (size_t)j * CAMREC_STRIDE,
+                                  MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, xp[3 * (size_t)i],
+                                  xp[3 * (size_t)i + 1], xp[3 * (size_t)i + 2], ob.x, ob.y, o.w[a], LOSS_LINEAR, 1.0,
+                                  j >= n_cam_fix, i >= n_pts_fix, e);
         if (Jc)
             for (int k = 0; k < 2 * NC; ++k) Jc[(size_t)a * 2 * NC + k] = e.Jc[k];
         if (Jp)

@@ -29,14 +29,18 @@ namespace sba {
 enum Model { MODEL_AFFINE = 0, MODEL_PERSPECTIVE = 1, MODEL_RPC = 2 };
 enum Loss { LOSS_LINEAR = 0, LOSS_HUBER = 1, LOSS_SOFT_L1 = 2, LOSS_CAUCHY = 3, LOSS_ARCTAN = 4 };
 
-constexpr int CAMREC_STRIDE = 16;   // doubles per prepared camera record
+constexpr int CAMREC_STRIDE = 40;   // doubles per prepared camera record
 constexpr int RPC_TAB_STRIDE = 90;  // 10 normalisation constants + 4 x 20 coefficients
 constexpr int MAX_CAM_PARAMS = 11;
 
-// Prepared camera record (built once per evaluation by k_prepare_cameras):
-//   [0..5]  cos a, sin a, cos b, sin b, cos g, sin g
-//   [6..8]  T (affine: T0 T1 -)
-//   perspective [9..13] fx fy skew cx cy ; affine [9..11] fx fy skew ; rpc [9..11] C
+// Prepared camera record (built once per evaluation by k_prepare_cameras / k_step), CAMREC_STRIDE doubles:
+//   [0..5]   cos a, sin a, cos b, sin b, cos g, sin g
+//   [6..8]   T (affine: T0 T1 -)
+//   [9..13]  perspective fx fy skew cx cy ; affine fx fy skew ; rpc C
+//   [14..22] R = Rz Ry Rx, row-major
+//   [23..31] KR, row-major: perspective (fx R0 + skew R1 + cx R2, fy R1 + cy R2, R2); affine (fx R0 + skew R1, fy R1, 0)
+//   [32..34] KT: perspective (fx T0 + skew T1 + cx T2, fy T1 + cy T2, T2); affine (fx T0 + skew T1, fy T1, 0)
+constexpr int CR_R = 14, CR_KR = 23, CR_KT = 32;
 struct CamRec {
     double ca, sa, cb, sb, cg, sg;
     double t0, t1, t2;
@@ -97,6 +101,61 @@ SBA_HD void rotation_derivs(const CamRec& c, const Rotated& r, double x,
     rot_yz(c, 0.0, -r.z1, r.y1, da[0], da[1], da[2]);
     db[0] = c.cg * r.z2;  db[1] = c.sg * r.z2;  db[2] = -r.x2;
     dg[0] = -r.y3;        dg[1] = r.x3;         dg[2] = 0.0;
+}
+
+// Fills a prepared camera record from the full parameter vector v (layout of ba_params.py:19-44).
+SBA_HD void build_camrec(const double* v, int model, double* __restrict__ r)
+{
+    double sn, cs;
+#ifdef __CUDA_ARCH__
+    sincos(v[0], &sn, &cs); r[0] = cs; r[1] = sn;
+    sincos(v[1], &sn, &cs); r[2] = cs; r[3] = sn;
+    sincos(v[2], &sn, &cs); r[4] = cs; r[5] = sn;
+#else
+    r[0] = cos(v[0]); r[1] = sin(v[0]); r[2] = cos(v[1]); r[3] = sin(v[1]); r[4] = cos(v[2]); r[5] = sin(v[2]);
+    (void)sn; (void)cs;
+#endif
+    if (model == MODEL_PERSPECTIVE) {
+        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
+        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = v[9]; r[13] = v[10];
+    } else if (model == MODEL_AFFINE) {
+        r[6] = v[3]; r[7] = v[4]; r[8] = 0.0;
+        r[9] = v[5]; r[10] = v[6]; r[11] = v[7]; r[12] = 0.0; r[13] = 0.0;
+    } else {
+        r[6] = v[3]; r[7] = v[4]; r[8] = v[5];
+        r[9] = v[6]; r[10] = v[7]; r[11] = v[8]; r[12] = 0.0; r[13] = 0.0;
+    }
+    const CamRec c = load_camrec(r);
+    double R[9];
+    rotation_matrix(c, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[CR_R + k] = R[k];
+    if (model == MODEL_PERSPECTIVE) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            r[CR_KR + k] = c.k0 * R[k] + c.k2 * R[3 + k] + c.k3 * R[6 + k];
+            r[CR_KR + 3 + k] = c.k1 * R[3 + k] + c.k4 * R[6 + k];
+            r[CR_KR + 6 + k] = R[6 + k];
+        }
+        r[CR_KT] = c.k0 * c.t0 + c.k2 * c.t1 + c.k3 * c.t2;
+        r[CR_KT + 1] = c.k1 * c.t1 + c.k4 * c.t2;
+        r[CR_KT + 2] = c.t2;
+    } else if (model == MODEL_AFFINE) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            r[CR_KR + k] = c.k0 * R[k] + c.k2 * R[3 + k];
+            r[CR_KR + 3 + k] = c.k1 * R[3 + k];
+            r[CR_KR + 6 + k] = 0.0;
+        }
+        r[CR_KT] = c.k0 * c.t0 + c.k2 * c.t1;
+        r[CR_KT + 1] = c.k1 * c.t1;
+        r[CR_KT + 2] = 0.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[CR_KR + k] = 0.0;
+    }
+#pragma unroll
+    for (int k = CR_KT + 3; k < CAMREC_STRIDE; ++k) r[k] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,6 +436,108 @@ SBA_HD void project_jac(const CamRec& c, const double* __restrict__ rpc_tab, dou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast Jacobian paths used by the solver's passes (the residual `fun` keeps the reference's operation
+// order above).  They use one reciprocal instead of the reference's two divisions and, for the point
+// block, the per-camera product K R:   (pu, pv, d) = KR X + KT ,  u = pu/d ,
+//     d(u,v)/dX = ( KR_0 - u KR_2 ; KR_1 - v KR_2 ) / d .
+// Values agree with `project` to ~1e-9 px at ECEF magnitudes (same rounding level as R X + T itself).
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+SBA_HD void point_side(const double* __restrict__ rec, const double* __restrict__ rpc_tab, double X, double Y,
+                       double Z, double& u, double& v, double Jp[6])
+{
+    if (MODEL == MODEL_PERSPECTIVE) {
+        const double* m = rec + CR_KR;
+        const double pu = m[0] * X + m[1] * Y + m[2] * Z + rec[CR_KT];
+        const double pv = m[3] * X + m[4] * Y + m[5] * Z + rec[CR_KT + 1];
+        const double d = m[6] * X + m[7] * Y + m[8] * Z + rec[CR_KT + 2];
+        const double invd = 1.0 / d;
+        u = pu * invd; v = pv * invd;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Jp[k] = (m[k] - u * m[6 + k]) * invd;
+            Jp[3 + k] = (m[3 + k] - v * m[6 + k]) * invd;
+        }
+    } else if (MODEL == MODEL_AFFINE) {
+        const double* m = rec + CR_KR;
+        u = m[0] * X + m[1] * Y + m[2] * Z + rec[CR_KT];
+        v = m[3] * X + m[4] * Y + m[5] * Z + rec[CR_KT + 1];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Jp[k] = m[k];
+    } else {
+        double dummy[2];
+        const CamRec c = load_camrec(rec);
+        project_jac<MODEL_RPC, 0>(c, rpc_tab, X, Y, Z, u, v, dummy, Jp);
+    }
+}
+
+// Camera block and (optionally) point block.  Jc[2][NC], Jp[2][3].
+template <int MODEL, int NC, bool WITH_JP>
+SBA_HD void full_side(const double* __restrict__ rec, const double* __restrict__ rpc_tab, double X, double Y,
+                      double Z, double& u, double& v, double Jc[2 * (NC > 0 ? NC : 1)], double Jp[6])
+{
+    const CamRec c = load_camrec(rec);
+    if (MODEL == MODEL_RPC) {
+        project_jac<MODEL_RPC, NC>(c, rpc_tab, X, Y, Z, u, v, Jc, Jp);
+        return;
+    }
+    double A[6], da[3], db[3], dg[3];
+    const Rotated r = rotate(c, X, Y, Z);
+    rotation_derivs(c, r, X, da, db, dg);
+    double a, b, invd = 1.0;
+    if (MODEL == MODEL_PERSPECTIVE) {
+        a = r.x3 + c.t0; b = r.y3 + c.t1;
+        const double d = r.z2 + c.t2;
+        invd = 1.0 / d;
+        u = (c.k0 * a + c.k2 * b + c.k3 * d) * invd;
+        v = (c.k1 * b + c.k4 * d) * invd;
+        A[0] = c.k0 * invd; A[1] = c.k2 * invd; A[2] = (c.k3 - u) * invd;
+        A[3] = 0.0;         A[4] = c.k1 * invd; A[5] = (c.k4 - v) * invd;
+    } else {
+        a = r.x3 + c.t0; b = r.y3 + c.t1;
+        u = c.k0 * a + c.k2 * b;
+        v = c.k1 * b;
+        A[0] = c.k0; A[1] = c.k2; A[2] = 0.0;
+        A[3] = 0.0;  A[4] = c.k1; A[5] = 0.0;
+    }
+    if (WITH_JP) {
+        const double* R = rec + CR_R;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Jp[k] = A[0] * R[k] + A[1] * R[3 + k] + A[2] * R[6 + k];
+            Jp[3 + k] = A[4] * R[3 + k] + A[5] * R[6 + k];
+        }
+    }
+    if (NC >= 3) {
+        Jc[0] = A[0] * da[0] + A[1] * da[1] + A[2] * da[2];
+        Jc[1] = A[0] * db[0] + A[1] * db[1] + A[2] * db[2];
+        Jc[2] = A[0] * dg[0] + A[1] * dg[1] + A[2] * dg[2];
+        Jc[NC + 0] = A[4] * da[1] + A[5] * da[2];
+        Jc[NC + 1] = A[4] * db[1] + A[5] * db[2];
+        Jc[NC + 2] = A[4] * dg[1] + A[5] * dg[2];
+    }
+    if (MODEL == MODEL_PERSPECTIVE) {
+        if (NC >= 6) {
+            Jc[3] = A[0]; Jc[4] = A[1]; Jc[5] = A[2];
+            Jc[NC + 3] = 0.0; Jc[NC + 4] = A[4]; Jc[NC + 5] = A[5];
+        }
+        if (NC >= 11) {
+            Jc[6] = a * invd; Jc[7] = 0.0; Jc[8] = b * invd; Jc[9] = 1.0; Jc[10] = 0.0;
+            Jc[NC + 6] = 0.0; Jc[NC + 7] = b * invd; Jc[NC + 8] = 0.0; Jc[NC + 9] = 0.0; Jc[NC + 10] = 1.0;
+        }
+    } else {
+        if (NC >= 5) {
+            Jc[3] = A[0]; Jc[4] = A[1];
+            Jc[NC + 3] = 0.0; Jc[NC + 4] = A[4];
+        }
+        if (NC >= 8) {
+            Jc[5] = a; Jc[6] = 0.0; Jc[7] = b;
+            Jc[NC + 5] = 0.0; Jc[NC + 6] = b; Jc[NC + 7] = 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // robust loss on one residual component (scipy semantics: per component, z = (f/f_scale)^2)
 //   rho0 = f_scale^2 rho(z)   (cost = 0.5 * sum rho0)
 //   returns the Jacobian row scale; f is replaced by the rescaled residual
@@ -419,6 +580,19 @@ SBA_HD double loss_cost(int loss, double f, double f_scale)
 SBA_HD double loss_rescale(int loss, double f_scale, double& f, double& cost)
 {
     if (loss == LOSS_LINEAR) { cost = 0.5 * f * f; return 1.0; }
+    if (loss == LOSS_SOFT_L1) {
+        // rho' = t^-1/2, rho'' = -1/2 t^-3/2  =>  rho' + 2 rho'' z = t^-3/2 exactly (t = 1 + z):
+        // scale = t^-3/4, f <- f t^1/4.  One sqrt and one reciprocal-sqrt instead of two sqrt + three divisions.
+        const double q = f / f_scale;
+        const double t = 1.0 + q * q;
+        if (t < 1e10) {                        // beyond that scipy's EPS clamp of the scale applies: generic path
+            const double s = sqrt(t);          // t^1/2
+            const double s4 = sqrt(s);         // t^1/4
+            cost = f_scale * f_scale * (s - 1.0);
+            f = f * s4;
+            return 1.0 / (s * s4);             // t^-3/4
+        }
+    }
     const double q = f / f_scale;
     double r0, r1, r2;
     loss_rho(loss, q * q, r0, r1, r2);

@@ -35,6 +35,28 @@ int hh_project_jac(int model, int nc, const double* camrec, const double* rpc, c
     return 1;
 }
 
+// v: full camera parameter vector; builds the prepared record the kernels use
+void hh_build_camrec(const double* v, int model, double* rec) { build_camrec(v, model, rec); }
+
+int hh_point_side(int model, const double* rec, const double* rpc, const double* X, double* uv, double* Jp)
+{
+    if (model == MODEL_PERSPECTIVE) point_side<MODEL_PERSPECTIVE>(rec, rpc, X[0], X[1], X[2], uv[0], uv[1], Jp);
+    else if (model == MODEL_AFFINE) point_side<MODEL_AFFINE>(rec, rpc, X[0], X[1], X[2], uv[0], uv[1], Jp);
+    else point_side<MODEL_RPC>(rec, rpc, X[0], X[1], X[2], uv[0], uv[1], Jp);
+    return 0;
+}
+
+int hh_full_side(int model, int nc, const double* rec, const double* rpc, const double* X, double* uv, double* Jc,
+                 double* Jp)
+{
+#define CASE(M, N) if (model == M && nc == N) { full_side<M, N, true>(rec, rpc, X[0], X[1], X[2], uv[0], uv[1], Jc, Jp); return 0; }
+    CASE(MODEL_PERSPECTIVE, 3) CASE(MODEL_PERSPECTIVE, 6) CASE(MODEL_PERSPECTIVE, 11)
+    CASE(MODEL_AFFINE, 3) CASE(MODEL_AFFINE, 5) CASE(MODEL_AFFINE, 8)
+    CASE(MODEL_RPC, 3) CASE(MODEL_RPC, 6)
+#undef CASE
+    return 1;
+}
+
 double hh_loss_rescale(int loss, double f_scale, double f, double* f_out, double* cost)
 {
     double s = loss_rescale(loss, f_scale, f, *cost);
