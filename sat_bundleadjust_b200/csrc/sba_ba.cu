@@ -269,16 +269,16 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     {
 #define SCHUR_ARGS                                                                                                     \
     p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->M, p->Z, p->q, p->item_base, \
-        p->schur_partials
+        p->item_chunk, p->schur_partials
         switch (p->nc) {
-        case 3: k_schur<3, 0, 3><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 5: k_schur<5, 0, 5><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 6: k_schur<6, 0, 6><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 8: k_schur<8, 0, 8><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 3: k_schur<3, 0, 3><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 5: k_schur<5, 0, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 6: k_schur<6, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 8: k_schur<8, 0, 8><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 11:
-            k_schur<11, 0, 6><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            k_schur<11, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
             SBA_TRY(check_launch(p));
-            k_schur<11, 6, 5><<<p->chunks.n, TPB, 0, p->stream>>>(SCHUR_ARGS);
+            k_schur<11, 6, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);
             break;
         default: set_error("bad nc"); return SBA_E_INVALID;
         }
@@ -288,11 +288,11 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
     p->schur_partials, p->cam_ptr, p->item_base, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, reg,  \
         p->rank == 0, p->S
         switch (p->nc) {
-        case 3: k_schur_finalize<3><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
-        case 5: k_schur_finalize<5><<<p->n_schur_blocks, 32, 0, p->stream>>>(FIN_ARGS); break;
-        case 6: k_schur_finalize<6><<<p->n_schur_blocks, 64, 0, p->stream>>>(FIN_ARGS); break;
-        case 8: k_schur_finalize<8><<<p->n_schur_blocks, 96, 0, p->stream>>>(FIN_ARGS); break;
-        default: k_schur_finalize<11><<<p->n_schur_blocks, 160, 0, p->stream>>>(FIN_ARGS); break;
+        case 3: k_schur_finalize<3><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
+        case 5: k_schur_finalize<5><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
+        case 6: k_schur_finalize<6><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
+        case 8: k_schur_finalize<8><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
+        default: k_schur_finalize<11><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
         }
         SBA_TRY(check_launch(p));
 #undef FIN_ARGS
@@ -545,7 +545,7 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     cudaSetDevice(p->device);
     void* ptrs[] = {p->cam_ind, p->pts_ind, p->track_ptr, p->pts2d, p->w, p->cam_static, p->rpc_tab, p->cm_obs, p->cm_pts,
                     p->cam_ptr, p->obs_of, p->cm_pts2d, p->cm_w, p->chunks.cam, p->chunks.beg, p->chunks.end, p->item_base,
-                    p->tile_obs, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
+                    p->item_chunk, p->tile_obs, p->sb_j, p->sb_jp, p->x, p->x_new, p->g, p->sinv, p->delta, p->t1,
                     p->t2, p->camrec, p->camrec_new, p->V, p->F, p->q, p->Z, p->camsys_local, p->S, p->cam_partials,
                     p->schur_partials, p->red_partials, p->counters, p->scal, p->r_out, p->io_x, p->chol_work};
     for (void* q : ptrs)
@@ -600,6 +600,9 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     // Schur: (j <= j') blocks; the partial of (chunk ch, partner j') lives at item_base[ch] + (j' - cam(ch))
     std::vector<int> item_base(ch_cam.size() + 1, 0), sb_j, sb_jp;
     for (size_t c = 0; c < ch_cam.size(); ++c) item_base[c + 1] = item_base[c] + (M - ch_cam[c]);
+    std::vector<int> item_chunk(item_base.back());
+    for (size_t c = 0; c < ch_cam.size(); ++c)
+        for (int t = item_base[c]; t < item_base[c + 1]; ++t) item_chunk[t] = (int)c;
     for (int j = 0; j < M; ++j)
         for (int jp = j; jp < M; ++jp) { sb_j.push_back(j); sb_jp.push_back(jp); }
     p->n_schur_items = item_base.back();
@@ -632,6 +635,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_upload(&p->chunks.beg, ch_beg, s));
     SBA_TRY(dev_upload(&p->chunks.end, ch_end, s));
     SBA_TRY(dev_upload(&p->item_base, item_base, s));
+    SBA_TRY(dev_upload(&p->item_chunk, item_chunk, s));
     SBA_TRY(dev_upload(&p->tile_obs, tile_obs, s));
     SBA_TRY(dev_upload(&p->sb_j, sb_j, s));
     SBA_TRY(dev_upload(&p->sb_jp, sb_jp, s));

@@ -87,6 +87,7 @@ struct sba_problem {
     sba::ChunkTable chunks;
     int n_schur_items = 0;   // (chunk, partner camera) partial slots
     int *item_base = nullptr;                                  // device: first slot of every chunk (n_chunks + 1)
+    int *item_chunk = nullptr;                                 // device: slot -> chunk
     int *sb_j = nullptr, *sb_jp = nullptr;                     // device: (j,j') blocks
     int *tile_obs = nullptr;                                   // device: warp-tile observation offsets (n_tiles + 1)
     int n_tiles = 0;

@@ -86,8 +86,8 @@ def test_normal_equation_blocks(built, loss):
     idx = ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))
     Vd = np.array([[H[off + 3 * i + a, off + 3 * i + b] for a, b in idx] for i in range(p.n_pts)])
     assert np.abs(U - Ud).max() <= 1e-9 * np.abs(Ud).max()
-    assert np.abs(V - Vd).max() <= 1e-9 * np.abs(Vd).max()
-    assert np.abs(g - gd).max() <= 1e-9 * np.abs(gd).max()
+    assert np.abs(V - Vd).max() <= 1e-8 * np.abs(Vd).max()   # point side uses the K R form (u differs by ~1e-9 px)
+    assert np.abs(g - gd).max() <= 1e-8 * np.abs(gd).max()
 
 
 @pytest.mark.parametrize("name", SOLVE_CASES)
