@@ -97,7 +97,9 @@ def test_solve_reaches_the_reference_minimum(built, name):
     pre = name + "/"
     cfg = util.ls_from_golden(G, name)
     loss, fs = cfg.get("loss", "linear"), cfg.get("f_scale", 1.0)
-    tight = dict(cfg, ftol=1e-14, xtol=1e-14, max_iter=400)
+    # xtol off: TRF's |dx| < xtol (xtol + |x|) test fires prematurely when Delta collapses (|x| ~ 1e8 at ECEF scale); the
+    # reference terminates the same way on the huber case, 11.7x above the minimum
+    tight = dict(cfg, ftol=1e-14, xtol=0.0, max_iter=1000)
     v0, v1, e0, e1, nfev, info = ba_core.run_ba_optimization(p, tight, False, False, return_info=True)
     cost_gpu = ba_oracle.robust_cost(ba_oracle.residuals(v1.copy(), p), loss, fs)      # evaluated by the ORACLE at the GPU solution
     conv = float(G[pre + "conv_cost"])
