@@ -125,3 +125,28 @@ def test_rpc_bundle_adjustment_converges(built):
         x, r, info = prob.solve(x0, loss="linear", ftol=1e-12, xtol=1e-14, max_nfev=200)
     assert info["cost"] < 0.2 * info["cost_init"]
     assert np.sqrt(np.mean(r ** 2)) < 1.0     # observations carry 0.5 px noise
+
+
+def test_rpc_model_class_and_triangulation_binding(built):
+    """The rpcm-style class and the reference-style ctypes binding (s2p/triangulation.py) on top of the GPU kernels."""
+    from sat_bundleadjust_b200 import triangulation
+    from sat_bundleadjust_b200.rpc_model import RPCModel
+    ra, rb = RPCModel(RA.to_dict()), RPCModel(RB.to_dict())
+    lla = R["lonlatalt"]
+    col, row = ra.projection(lla[:, 0], lla[:, 1], lla[:, 2])
+    assert np.abs(np.stack((col, row), axis=1) - R["ref_proj_a"]).max() < 1e-7
+    c0, r0 = ra.projection(float(lla[0, 0]), float(lla[0, 1]), float(lla[0, 2]))
+    assert abs(c0 - R["ref_proj_a"][0, 0]) < 1e-7 and isinstance(c0, float)
+    lon, lat = ra.localization(R["colrowalt"][:, 0], R["colrowalt"][:, 1], R["colrowalt"][:, 2])
+    assert np.abs(np.stack((lon, lat), axis=1) - R["ref_loc_a_delta1"]).max() < 1e-9
+    from oracle import rpc_oracle
+    X = np.stack(rpc_oracle.latlon_to_ecef(lla[:, 1], lla[:, 0], lla[:, 2]), axis=1)
+    assert np.abs(ra.projection_from_ecef(X) - RA.project_ecef(X)).max() < 1e-6
+    out, err = triangulation.stereo_corresp_to_xyz(ra, rb, R["kp_a"], R["kp_b"])
+    assert out.dtype == np.float64 and err.dtype == np.float32 and err.shape == (R["kp_a"].shape[0], 1)
+    assert np.abs(out[:, :2] - R["ref_tri_lonlatalt"][:, :2]).max() < 1e-8
+    assert np.abs(out[:, 2] - R["ref_tri_lonlatalt"][:, 2]).max() < 1e-3
+    xyz, _ = triangulation.rpc_triangulation(ra, rb, R["kp_a"], R["kp_b"])
+    ref_xyz = np.stack(rpc_oracle.latlon_to_ecef(R["ref_tri_lonlatalt"][:, 1], R["ref_tri_lonlatalt"][:, 0],
+                                                 R["ref_tri_lonlatalt"][:, 2]), axis=1)
+    assert np.abs(xyz - ref_xyz).max() < 2e-3

@@ -1,0 +1,49 @@
+"""
+Multi-GPU check (run under torchrun on >= 2 GPUs):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+Solves the same problem sharded over the ranks and on one GPU and compares.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from sat_bundleadjust_b200 import ba_core, synth  # noqa: E402
+from sat_bundleadjust_b200 import dist as sdist  # noqa: E402
+
+
+def main():
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for model, corr, ntr, loss in (("perspective", ["R", "T"], 20000, "soft_l1"), ("affine", ["R"], 5000, "linear")):
+        sc = synth.make_scene(n_cam=8, n_tracks=ntr, p_vis=0.5, cam_model=model, seed=3)
+        p = synth.scene_to_params(sc, corr, n_cam_fix=1, n_pts_fix=10)
+        ls = {"loss": loss, "f_scale": 1.0, "max_iter": 300, "verbose": 0}
+        v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
+        if rank == 0:
+            s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+            rel = abs(info["cost"] - info1["cost"]) / info1["cost"]
+            dx = np.abs(v1 - s1).max()
+            print("%s %s: dist cost %.12e nfev %d | single cost %.12e nfev %d | rel %.2e max|dx| %.2e | err %.4f vs %.4f" % (
+                model, loss, info["cost"], nfev, info1["cost"], nfev1, rel, dx, e1.mean(), f1.mean()), flush=True)
+            ok = ok and rel < 1e-9 and nfev == nfev1 and np.array_equal(v0, s0) and np.abs(e0 - f0).max() < 1e-9
+    # all ranks hold identical results
+    t = torch.from_numpy(v1[:100].copy()).cuda()
+    lst = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(lst, t)
+    same = all(torch.equal(lst[0], u) for u in lst)
+    if rank == 0:
+        print("identical across ranks:", same, "| all checks:", ok and same, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if (ok and same) or rank != 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
