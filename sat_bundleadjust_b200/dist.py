@@ -82,8 +82,9 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
                                   max_nfev=cfg["max_iter"])
     # gather the pieces (variable-length -> pad to the longest shard)
     def gather(v):
-        n_max = max(3 * (t1 - t0) for t0, t1 in ranges) * 2 + ncv + 8
-        buf = torch.zeros(n_max, dtype=torch.float64, device="cuda")
+        size = torch.tensor([v.size], dtype=torch.int64, device="cuda")
+        dist.all_reduce(size, op=dist.ReduceOp.MAX, group=group)
+        buf = torch.zeros(int(size.item()), dtype=torch.float64, device="cuda")
         buf[: v.size] = torch.from_numpy(v).cuda()
         out = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(out, buf, group=group)
