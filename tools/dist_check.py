@@ -24,15 +24,20 @@ def main():
     for model, corr, ntr, loss in (("perspective", ["R", "T"], 20000, "soft_l1"), ("affine", ["R"], 5000, "linear")):
         sc = synth.make_scene(n_cam=8, n_tracks=ntr, p_vis=0.5, cam_model=model, seed=3)
         p = synth.scene_to_params(sc, corr, n_cam_fix=1, n_pts_fix=10)
-        ls = {"loss": loss, "f_scale": 1.0, "max_iter": 300, "verbose": 0}
-        v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
-        if rank == 0:
-            s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
-            rel = abs(info["cost"] - info1["cost"]) / info1["cost"]
-            dx = np.abs(v1 - s1).max()
-            print("%s %s: dist cost %.12e nfev %d | single cost %.12e nfev %d | rel %.2e max|dx| %.2e | err %.4f vs %.4f" % (
-                model, loss, info["cost"], nfev, info1["cost"], nfev1, rel, dx, e1.mean(), f1.mean()), flush=True)
-            ok = ok and rel < 1e-9 and nfev == nfev1 and np.array_equal(v0, s0) and np.abs(e0 - f0).max() < 1e-9
+        # (a) a fixed, short run: the sharded and the single-GPU iterates must agree to rounding (only the order of the
+        #     sums over tracks differs); (b) the full solve: same minimum within the stopping tolerance (ftol 1e-4)
+        for max_iter, tol in ((12, 1e-9), (300, 2e-3)):
+            ls = {"loss": loss, "f_scale": 1.0, "max_iter": max_iter, "verbose": 0}
+            v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
+            if rank == 0:
+                s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+                rel = abs(info["cost"] - info1["cost"]) / info1["cost"]
+                dx = np.abs(v1 - s1).max()
+                print("%s %s max_iter %d: dist cost %.12e nfev %d | single cost %.12e nfev %d | rel %.2e max|dx| %.2e | err %.4f vs %.4f" % (
+                    model, loss, max_iter, info["cost"], nfev, info1["cost"], nfev1, rel, dx, e1.mean(), f1.mean()), flush=True)
+                ok = ok and rel < tol and np.array_equal(v0, s0) and np.abs(e0 - f0).max() < 1e-9
+                if max_iter == 12:
+                    ok = ok and nfev == nfev1
     # all ranks hold identical results
     t = torch.from_numpy(v1[:100].copy()).cuda()
     lst = [torch.empty_like(t) for _ in range(dist.get_world_size())]
