@@ -248,7 +248,7 @@ static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out
 }
 
 // Schur complement + Cholesky solve + back-substitution for a given damping `reg`
-static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, double reg, PhaseTimer& tm)
+static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, PhaseTimer& tm)
 {
     const int ns = p->M * p->nc;
     const double* xp = p->x + (size_t)ns;
@@ -258,7 +258,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
         const int grid = (p->n_tiles + WPB - 1) / WPB;
 #define L(MODEL, NC)                                                                                                    \
     k_point_prep<MODEL, NC><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), xp, p->camrec, p->rpc_tab, ns, p->n_cam_fix,       \
-                                                         p->n_pts_fix, loss, f_scale, reg, p->V, p->g, p->sinv, p->F,    \
+                                                         p->n_pts_fix, loss, f_scale, p->V, p->g, p->sinv, p->F,    \
                                                          p->q, p->Z, p->scal)
         SBA_DISPATCH(p, L);
 #undef L
@@ -285,8 +285,8 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, doubl
         SBA_TRY(check_launch(p));
 #undef SCHUR_ARGS
 #define FIN_ARGS                                                                                                       \
-    p->schur_partials, p->cam_ptr, p->item_base, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, reg,  \
-        p->rank == 0, p->S
+    p->schur_partials, p->cam_ptr, p->item_base, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv,       \
+        p->scal, p->rank == 0, p->S
         switch (p->nc) {
         case 3: k_schur_finalize<3><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
         case 5: k_schur_finalize<5><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
@@ -344,9 +344,13 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     SBA_TRY(run_prepare(p, p->x, p->camrec));
     SBA_TRY(run_residual(p, p->x, p->camrec, loss, fs, nullptr, SC_COST_NEW, 0));   // cost at x0, same kernel as every later cost
     SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
+    SBA_TRY(fetch_scal(p));
+    double cost = p->h_scal[SC_COST_NEW];
+    if (!std::isfinite(cost)) { set_error("Residuals are not finite in the initial point."); return SBA_E_NUMERIC; }
+    info->cost_init = cost;
     SBA_TRY(run_assemble(p, p->x, p->camrec, loss, fs));
-    int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0, explicit_passes = 0;
-    double cost = 0.0, Delta = 0.0, g_norm = 0.0;
+    int nfev = 1, njev = 1, iteration = 0, status = -1, chol_retries = 0;
+    double Delta = -1.0, g_norm = 0.0;   // Delta < 0: not initialised yet (the device sets |x0 * scale_inv|)
     bool first = true;
     PhaseTimer tm, it_tm;
     tm.p = it_tm.p = p;
@@ -358,147 +362,108 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         p->flush_bytes = (size_t)o->l2_flush_bytes;
     }
 
+    // enqueue: trial point x_new = x + c1 t1 + c2 t2 for radius `radius` (< 0: the one on the device) and its cost
+    auto enqueue_trial = [&](double radius) -> int {
+        tm.begin(SBA_PH_STEP_EVAL);
+        k_control_tr2d<<<1, 32, 0, p->stream>>>(p->scal, radius);
+        SBA_TRY(check_launch(p));
+        k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, p->scal, p->x_new, p->n, p->cam_static,
+                                                 p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->model);
+        SBA_TRY(check_launch(p));
+        SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
+        SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
+        tm.end();
+        return SBA_OK;
+    };
+    // enqueue: everything from the Jacobian blocks at x to the first trial point, with no host round trip
+    auto enqueue_iteration = [&](double reg_override) -> int {
+        if (reg_override < 0.0) {
+            tm.begin(SBA_PH_SCALE_JVP);
+            SBA_TRY(run_scale_dots(p, first ? 1 : 0));
+            Slots sa; sa.s[0] = SC_A; sa.s[1] = SC_SCRATCH; sa.s[2] = SC_SCRATCH;
+            SBA_TRY(run_jvp(p, loss, fs, 1, sa));
+            SBA_TRY(allreduce_scal(p, SC_COST, SC_GGN - SC_COST));
+            tm.end();
+        }
+        k_control_reg<<<1, 32, 0, p->stream>>>(p->scal, Delta, reg_override);
+        SBA_TRY(check_launch(p));
+        SBA_TRY(run_gauss_newton_step(p, loss, fs, tm));
+        tm.begin(SBA_PH_SUBSPACE);
+        k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->n, ns, p->rank == 0, p->red_partials,
+                                                        p->counters + 4, p->scal);
+        SBA_TRY(check_launch(p));
+        SBA_TRY(allreduce_scal(p, SC_GGN, 2));
+        k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
+                                                     p->red_partials, p->counters + 5, p->scal);
+        SBA_TRY(check_launch(p));
+        SBA_TRY(allreduce_scal(p, SC_WW, 5));
+        Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
+        SBA_TRY(run_jvp(p, loss, fs, 2, sb));
+        SBA_TRY(allreduce_scal(p, SC_B11, 3));
+        tm.end();
+        return enqueue_trial(-1.0);
+    };
+
     while (true) {
         if (o->max_iterations > 0 && iteration >= o->max_iterations) break;
+        if (nfev >= o->max_nfev) break;
         tm.on = it_tm.on = iteration >= o->timed_from && (o->timed_from > 0 || o->l2_flush_bytes > 0 || o->max_iterations > 0);
         if (o->l2_flush_bytes > 0)
             SBA_CUDA(cudaMemsetAsync(p->flush_buf, iteration & 0xff, (size_t)o->l2_flush_bytes, p->stream));
         it_tm.begin(-1);
-        tm.begin(SBA_PH_SCALE_JVP);
-        SBA_TRY(run_scale_dots(p, first ? 1 : 0));
-        Slots sa; sa.s[0] = SC_A; sa.s[1] = SC_SCRATCH; sa.s[2] = SC_SCRATCH;
-        SBA_TRY(run_jvp(p, loss, fs, 1, sa));
-        SBA_TRY(allreduce_scal(p, SC_COST, SC_GGN - SC_COST));
-        tm.end();
+        // One host read per trial point.  scipy tests |g|_inf < gtol before it computes a step; here the first trial
+        // point of the iteration is already in flight when the test is made, and is simply discarded if it fires.
+        SBA_TRY(enqueue_iteration(-1.0));
         SBA_TRY(fetch_scal(p));
         const double* h = p->h_scal;
-        if (first) {
-            cost = h[SC_COST_NEW];
-            if (!std::isfinite(cost)) { set_error("Residuals are not finite in the initial point."); return SBA_E_NUMERIC; }
-            info->cost_init = cost;
-            Delta = std::sqrt(h[SC_XS]);
-            if (Delta == 0.0) Delta = 1.0;
-            first = false;
-        }
-        const double gg = h[SC_GG], x_norm = std::sqrt(h[SC_XX]);
-        g_norm = 0.0;
-        for (int r = 0; r < 16; ++r) g_norm = std::max(g_norm, h[SC_GMAX_SLOTS + r]);
-        if (g_norm < o->gtol) status = 1;
-        if (o->verbose >= 2)
-            printf("[sba] it %3d nfev %3d cost %.10e |g|inf %.3e Delta %.3e\n", iteration, nfev, cost, g_norm, Delta);
-        if (status >= 0 || nfev >= o->max_nfev) break;   // (a partial iteration is not counted as timed)
-
-        // damping from the Cauchy step (trf.py:485-490; build_quadratic_1d / minimize_quadratic_1d)
-        const double qa = 0.5 * h[SC_A], qb = -gg;
-        const double to_tr = Delta / std::sqrt(gg);
-        double ag_value = 0.0;   // t = 0
-        ag_value = std::min(ag_value, to_tr * (qa * to_tr + qb));
-        if (qa != 0.0) {
-            const double ext = -0.5 * qb / qa;
-            if (ext > 0.0 && ext < to_tr) ag_value = std::min(ag_value, ext * (qa * ext + qb));
-        }
-        double reg = -ag_value / (Delta * Delta);
-
-        // Gauss-Newton step of the damped system and the sums that define the 2-D subspace model (one host sync).
-        // With delta the exact solution of (H + reg D^2) delta = -g  (H = J^T J, D^2 = diag(sinv^2), t1 = D^-2 g):
-        //   t1'H delta = -|g_h|^2 - reg g_h.gn_h ,  delta'H delta = -g_h.gn_h - reg |gn_h|^2 ,  t1'H t1 = |J t1|^2 (known),
-        // so B_S = S'J_h'J_h S could be had without a pass over the observations (see the note on cancellation below).
-        double alpha = 0, ww = 0, wg = 0, t11 = 0, t12 = 0, t22 = 0, b11 = 0, b12 = 0, b22 = 0;
-        for (int attempt = 0;; ++attempt) {
-            SBA_TRY(run_gauss_newton_step(p, loss, fs, reg, tm));
-            tm.begin(SBA_PH_SUBSPACE);
-            k_dot_g_delta<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->n, ns, p->rank == 0, p->red_partials,
-                                                            p->counters + 4, p->scal);
-            SBA_TRY(check_launch(p));
-            SBA_TRY(allreduce_scal(p, SC_GGN, 2));
-            k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
-                                                         p->red_partials, p->counters + 5, p->scal);
-            SBA_TRY(check_launch(p));
-            SBA_TRY(allreduce_scal(p, SC_WW, 5));
-            if (!p->algebraic_subspace) {
-                Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
-                SBA_TRY(run_jvp(p, loss, fs, 2, sb));
-                SBA_TRY(allreduce_scal(p, SC_B11, 3));
-            }
-            tm.end();
+        for (int attempt = 0; h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_B22]); ++attempt) {
+            if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
+            // re-damp: J_h has unit column norms, so reg is relative to 1
+            ++chol_retries;
+            SBA_TRY(enqueue_iteration(std::max(h[SC_REG] * 10.0, 1e-12)));
             SBA_TRY(fetch_scal(p));
             h = p->h_scal;
-            const bool failed = h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_WW]);
-            if (!failed) break;
-            if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
-            reg = std::max(reg * 10.0, 1e-12);   // re-damp: J_h has unit column norms, so reg is relative to 1
-            ++chol_retries;
         }
-        {
-            const double ggn = h[SC_GGN], dd = h[SC_DD];
-            alpha = gg > 0.0 ? ggn / gg : 0.0;
-            ww = h[SC_WW]; wg = h[SC_WG]; t11 = h[SC_T11]; t12 = h[SC_T12]; t22 = h[SC_T22];
-            b11 = h[SC_A];
-            // The algebraic model (no pass over the observations) is exact in exact arithmetic but cancels badly
-            // whenever |J t1| >> |J t2| (stiff gradient direction), which robust losses make common: it is an opt-in
-            // experiment (SBA_ALGEBRAIC_SUBSPACE=1); the default is the explicit J*[t1 t2] pass, like scipy's J_h.dot(S).
-            const bool explicit_pass = h[SC_BAD_POINTS] != 0.0 || !p->algebraic_subspace || !(ww >= 1e-3 * dd);
-            if (!p->algebraic_subspace) {
-                b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
-            } else if (!explicit_pass) {
-                const double h1d = -gg - reg * ggn, hdd = -ggn - reg * dd;
-                b12 = h1d - alpha * b11;
-                b22 = hdd - 2.0 * alpha * h1d + alpha * alpha * b11;
-            } else {
-                tm.begin(SBA_PH_SUBSPACE);
-                Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
-                SBA_TRY(run_jvp(p, loss, fs, 2, sb));
-                SBA_TRY(allreduce_scal(p, SC_B11, 3));
-                tm.end();
-                SBA_TRY(fetch_scal(p));
-                h = p->h_scal;
-                b11 = h[SC_B11]; b12 = h[SC_B12]; b22 = h[SC_B22];
-                ++explicit_passes;
-            }
-        }
-        // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|  (t2 = delta - alpha t1)
-        const double n1 = std::sqrt(gg);
-        const bool rank2 = ww > 0.0;
-        const double n2 = rank2 ? std::sqrt(ww) : 1.0;
-        double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
-        double gS0 = n1, gS1 = rank2 ? wg / n2 : 0.0;
+        first = false;
+        Delta = h[SC_DELTA];
+        const double x_norm = std::sqrt(h[SC_XX]);
+        g_norm = 0.0;
+        for (int r = 0; r < 16; ++r) g_norm = std::max(g_norm, h[SC_GMAX_SLOTS + r]);
+        if (o->verbose >= 2)
+            printf("[sba] it %3d nfev %3d cost %.10e |g|inf %.3e Delta %.3e reg %.3e\n", iteration, nfev, cost, g_norm, Delta,
+                   h[SC_REG]);
+        if (g_norm < o->gtol) { status = 1; break; }
 
-        double actual_reduction = -1.0, cost_new = cost, step_norm = 0.0;
+        double actual_reduction = -1.0, cost_new = cost;
         int term = -1;
-        while (actual_reduction <= 0.0 && nfev < o->max_nfev) {
-            double pS[2];
-            solve_trust_region_2d(B00, B01, B11, gS0, gS1, Delta, pS);
-            const double predicted = -(0.5 * (B00 * pS[0] * pS[0] + 2.0 * B01 * pS[0] * pS[1] + B11 * pS[1] * pS[1]) +
-                                       gS0 * pS[0] + gS1 * pS[1]);
-            const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
-            const double step_h_norm = std::sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
-            tm.begin(SBA_PH_STEP_EVAL);
-            k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, c1, c2, p->x_new, p->n,
-                                                     p->cam_static, p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->model);
-            SBA_TRY(check_launch(p));
-            SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
-            SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
-            tm.end();
-            SBA_TRY(fetch_scal(p));
+        while (true) {
             ++nfev;
-            cost_new = p->h_scal[SC_COST_NEW];
-            if (!std::isfinite(cost_new)) { Delta = 0.25 * step_h_norm; continue; }
-            actual_reduction = cost - cost_new;
-            // update_tr_radius (common.py:222-245)
-            double ratio;
-            if (predicted > 0.0) ratio = actual_reduction / predicted;
-            else if (predicted == 0.0 && actual_reduction == 0.0) ratio = 1.0;
-            else ratio = 0.0;
-            double Delta_new = Delta;
-            if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
-            else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
-            step_norm = std::sqrt(std::max(0.0, c1 * c1 * t11 + 2.0 * c1 * c2 * t12 + c2 * c2 * t22));
-            // check_termination (common.py:705-717)
-            const bool ftol_ok = actual_reduction < o->ftol * cost && ratio > 0.25;
-            const bool xtol_ok = step_norm < o->xtol * (o->xtol + x_norm);
-            if (ftol_ok && xtol_ok) term = 4; else if (ftol_ok) term = 2; else if (xtol_ok) term = 3;
-            if (term >= 0) break;
-            Delta = Delta_new;
+            cost_new = h[SC_COST_NEW];
+            const double predicted = h[SC_PRED], step_h_norm = h[SC_STEPH], step_norm = h[SC_STEPN];
+            if (!std::isfinite(cost_new)) {
+                Delta = 0.25 * step_h_norm;
+            } else {
+                actual_reduction = cost - cost_new;
+                // update_tr_radius (common.py:222-245)
+                double ratio;
+                if (predicted > 0.0) ratio = actual_reduction / predicted;
+                else if (predicted == 0.0 && actual_reduction == 0.0) ratio = 1.0;
+                else ratio = 0.0;
+                double Delta_new = Delta;
+                if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
+                else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
+                // check_termination (common.py:705-717)
+                const bool ftol_ok = actual_reduction < o->ftol * cost && ratio > 0.25;
+                const bool xtol_ok = step_norm < o->xtol * (o->xtol + x_norm);
+                if (ftol_ok && xtol_ok) term = 4; else if (ftol_ok) term = 2; else if (xtol_ok) term = 3;
+                if (term >= 0) break;
+                Delta = Delta_new;
+            }
+            if (actual_reduction > 0.0 || nfev >= o->max_nfev) break;
+            // rejected: same model, smaller radius, new trial point (no new factorisation, like scipy)
+            SBA_TRY(enqueue_trial(Delta));
+            SBA_TRY(fetch_scal(p));
+            h = p->h_scal;
         }
         if (actual_reduction > 0.0) {
             std::swap(p->x, p->x_new);
@@ -523,7 +488,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     info->status = status; info->nfev = nfev; info->njev = njev; info->iterations = iteration;
     info->cost = cost; info->optimality = g_norm; info->solve_ms = ms; info->chol_retries = chol_retries;
     info->gpu_launches = p->launches;
-    info->explicit_subspace_passes = explicit_passes;
+    info->explicit_subspace_passes = iteration;
     tm.resolve(info);
     it_tm.resolve(info);
     return SBA_OK;

@@ -54,6 +54,13 @@ enum Scal {
     SC_BAD_POINTS,        // points whose damped 3x3 block was not positive definite
     SC_CHOL_FAIL,         // reduced camera system factorisation failed (pivot index + 1)
     SC_SCRATCH,
+    // device-side control (single-thread kernels; identical on every rank because their inputs are all-reduced)
+    SC_DELTA,             // trust-region radius in use
+    SC_REG,               // damping of the Gauss-Newton system
+    SC_C1, SC_C2,         // step = c1 t1 + c2 t2
+    SC_PRED,              // predicted reduction of the 2-D model
+    SC_STEPH,             // |step_h| (scaled space)
+    SC_STEPN,             // |step|   (x space)
     SC_COUNT
 };
 

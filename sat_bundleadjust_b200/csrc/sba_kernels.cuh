@@ -16,6 +16,7 @@
 // J itself is never stored: every pass recomputes the per-observation Jacobian in registers.
 #pragma once
 #include "sba_internal.cuh"
+#include "sba_tr2d.h"
 
 namespace sba {
 
@@ -589,11 +590,12 @@ template <int MODEL, int NC>
 __global__ void __launch_bounds__(TPB)
 k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
              const double* __restrict__ rpc_tab, int ns, int n_cam_fix, int n_pts_fix, int loss,
-             double f_scale, double reg, const double* __restrict__ V, const double* __restrict__ g,
+             double f_scale, const double* __restrict__ V, const double* __restrict__ g,
              const double* __restrict__ sinv, double* __restrict__ F, double* __restrict__ q, double* __restrict__ Zout,
              double* scal)
 {
     constexpr int ZS = NC * 3, ZP = ZS + 1;      // padded lane stride (odd): conflict-free 64-bit accesses
+    const double reg = scal[SC_REG];
     __shared__ double sG[WPB][6][32];
     __shared__ double sZ[WPB][32 * ZP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -710,10 +712,11 @@ template <int NC>
 __global__ void __launch_bounds__(128)
 k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ first_chunk,
                  const int* __restrict__ item_base, const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M,
-                 int n_cam_fix, const double* __restrict__ camsys_local, const double* __restrict__ sinv, double reg,
-                 int add_diag, double* __restrict__ S)
+                 int n_cam_fix, const double* __restrict__ camsys_local, const double* __restrict__ sinv,
+                 const double* __restrict__ scal, int add_diag, double* __restrict__ S)
 {
     constexpr int NVALL = NC * NC + NC;
+    const double reg = scal[SC_REG];
     const int blk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = sb_j[blk], jp = sb_jp[blk];
     const int ns = M * NC;
@@ -873,10 +876,11 @@ __device__ __forceinline__ double step_value(double x, double a, double d, doubl
 }
 
 __global__ void __launch_bounds__(256)
-k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ delta, double ca,
-       double cb, double* __restrict__ x_new, long long n, const double* __restrict__ cam_static,
+k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ delta,
+       const double* __restrict__ scal, double* __restrict__ x_new, long long n, const double* __restrict__ cam_static,
        double* __restrict__ camrec_new, int M, int P, int nc, int n_cam_fix, int model)
 {
+    const double ca = scal[SC_C1], cb = scal[SC_C2];
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long idx = gid; idx < n; idx += (long long)gridDim.x * blockDim.x)
         x_new[idx] = step_value(x[idx], t1[idx], delta[idx], ca, cb);
@@ -900,6 +904,59 @@ k_step(const double* __restrict__ x, const double* __restrict__ t1, const double
         }
         write_camrec(v, camrec_new + (size_t)j * CAMREC_STRIDE, model);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side control: the damping rule and the 2-D trust-region solve run as single-thread kernels on the
+// already reduced scalars, so that the host reads the scalar block once per trial step instead of three times
+// ------------------------------------------------------------------------------------------------
+// damping from the Cauchy step (scipy trf.py:485-490): reg = -min_{0<=t<=Delta/|g_h|} (a t^2 + b t) / Delta^2
+// delta_arg < 0: first iteration, Delta = |x0 * scale_inv| (or 1);  reg_override >= 0: use that value (re-damping)
+__global__ void k_control_reg(double* scal, double delta_arg, double reg_override)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double Delta = delta_arg;
+    if (Delta < 0.0) {
+        Delta = sqrt(scal[SC_XS]);
+        if (Delta == 0.0) Delta = 1.0;
+    }
+    scal[SC_DELTA] = Delta;
+    if (reg_override >= 0.0) { scal[SC_REG] = reg_override; return; }
+    const double gg = scal[SC_GG];
+    const double qa = 0.5 * scal[SC_A], qb = -gg;
+    const double to_tr = Delta / sqrt(gg);
+    double ag = 0.0;
+    ag = fmin(ag, to_tr * (qa * to_tr + qb));
+    if (qa != 0.0) {
+        const double ext = -0.5 * qb / qa;
+        if (ext > 0.0 && ext < to_tr) ag = fmin(ag, ext * (qa * ext + qb));
+    }
+    scal[SC_REG] = -ag / (Delta * Delta);
+}
+
+// exact 2-D trust-region step in span{g_h, gn_h} (scipy trf.py:496-509) for the radius `delta_arg`
+// (< 0: the radius stored by k_control_reg)
+__global__ void k_control_tr2d(double* scal, double delta_arg)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double Delta = delta_arg < 0.0 ? scal[SC_DELTA] : delta_arg;
+    const double gg = scal[SC_GG], ww = scal[SC_WW], wg = scal[SC_WG];
+    const double t11 = scal[SC_T11], t12 = scal[SC_T12], t22 = scal[SC_T22];
+    const double b11 = scal[SC_B11], b12 = scal[SC_B12], b22 = scal[SC_B22];
+    // orthonormal basis s1 = g_h/|g_h|, s2 = w/|w| ; x-space images t1/|g_h|, t2/|w|
+    const double n1 = sqrt(gg);
+    const bool rank2 = ww > 0.0;
+    const double n2 = rank2 ? sqrt(ww) : 1.0;
+    const double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
+    const double gS0 = n1, gS1 = rank2 ? wg / n2 : 0.0;
+    double pS[2];
+    solve_trust_region_2d(B00, B01, B11, gS0, gS1, Delta, pS);
+    const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
+    scal[SC_C1] = c1;
+    scal[SC_C2] = c2;
+    scal[SC_PRED] = -(0.5 * (B00 * pS[0] * pS[0] + 2.0 * B01 * pS[0] * pS[1] + B11 * pS[1] * pS[1]) + gS0 * pS[0] + gS1 * pS[1]);
+    scal[SC_STEPH] = sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
+    scal[SC_STEPN] = sqrt(fmax(0.0, c1 * c1 * t11 + 2.0 * c1 * c2 * t12 + c2 * c2 * t22));
 }
 
 // per-observation Jacobian blocks for tests (weights applied, no robust rescale)
