@@ -303,7 +303,7 @@ def run_b200_arm(args):
            "h2d_bytes_per_step": int(h2d / max(1, info_e["iterations"])),
            "d2h_bytes_per_step": int(d2h / max(1, info_e["iterations"])),
            "wall_s": wall, "iterations": info_e["iterations"], "nfev": info_e["nfev"], "status": info_e["status"],
-           "cost": info_e["cost"], "device_ms": info_e["solve_ms"],
+           "cost": info_e["cost"], "device_ms": info_e["solve_ms"], "wall_breakdown_s": info_e.get("wall_s"),
            "call": "ba_core.run_ba_optimization(p, {'loss': 'soft_l1', 'f_scale': 1.0, 'max_iter': 300})"}
 
     if rank == 0:

@@ -101,14 +101,20 @@ def run_ba_optimization(p, ls_params=None, verbose=False, plots=True, return_inf
         print("\nRunning bundle adjustment...")
         for k, v in cfg.items():
             print("    {}: {}".format(k, v))
+    import time
     vars_init = initial_vars(p)
+    t0 = time.perf_counter()
     with DeviceProblem(p) as prob:
+        t1 = time.perf_counter()
         residuals_init, _ = prob.residuals(vars_init)
         if not np.all(np.isfinite(residuals_init)):
             raise ValueError("Residuals are not finite in the initial point.")
+        t2 = time.perf_counter()
         vars_ba, residuals_ba, info = prob.solve(
             vars_init, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"],
             max_nfev=cfg["max_iter"], verbose=2 if cfg["verbose"] >= 2 else 0)
+        t3 = time.perf_counter()
+    info["wall_s"] = {"create": t1 - t0, "fun": t2 - t1, "solve": t3 - t2, "destroy": time.perf_counter() - t3}
     if verbose:
         flush_print("Shape of Jacobian sparsity: {}x{}".format(2 * p.pts_ind.size, vars_init.size))
         flush_print("Optimization took {:.4f} seconds on the device ({} function evaluations)\n".format(

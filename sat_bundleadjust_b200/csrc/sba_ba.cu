@@ -638,7 +638,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     if (p->world > 1) SBA_TRY(dev_alloc(&p->camsys, ns * nc + ns));
     else p->camsys = p->camsys_local;
     SBA_TRY(dev_alloc(&p->S, ns * ns + ns));
-    if (ns > 160) SBA_TRY(dev_alloc(&p->chol_work, (ns + 1) * ns));
+    if (ns > 160) SBA_TRY(dev_alloc(&p->chol_work, (ns + 1) * (ns | 1) + ns));
     const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
     SBA_TRY(dev_alloc(&p->cam_partials, (size_t)p->chunks.n * nv_cam));
     SBA_TRY(dev_alloc(&p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));

@@ -2,12 +2,10 @@
 // (n = n_cam * n_params <= ~1800).  There is no reference counterpart: the reference never forms S,
 // it hands the full sparse Jacobian to LSMR (scipy/optimize/_lsq/trf.py:485-495).
 //
-// One CTA, right-looking.  The right-hand side rides along as an extra row of the matrix, so the forward
-// substitution L y = rhs falls out of the factorisation itself (row n of L is y^T) and only the backward
-// substitution remains.  Columns of the trailing update are dealt to warps, rows to lanes (coalesced /
-// conflict-free in the column-major layout).  S is staged in shared memory when it fits
-// (n <= 160: 161 x 160 doubles = 206 KB of the 227 KB a CTA may use), otherwise worked on in place in
-// global memory, where the whole matrix is L2-resident.
+// One CTA, left-looking, one barrier per column (see the kernel).  The right-hand side rides along as an extra
+// row of the matrix, so the forward substitution L y = rhs falls out of the factorisation itself and only the
+// backward substitution remains.  S is staged in shared memory when it fits (n <= 160: 161 x 161 doubles =
+// 207 KB of the 227 KB a CTA may use), otherwise worked on in a global scratch buffer, which is L2-resident.
 #include "sba_internal.cuh"
 
 namespace sba {
@@ -15,77 +13,81 @@ namespace sba {
 constexpr int CHOL_THREADS = 256;
 constexpr int CHOL_SMEM_MAX_N = 160;
 
-// A: n x n column-major, lower triangle used, overwritten by L (full n x n written back).
-// b: rhs (n).  x: solution (n).  fail: (k+1) when pivot k is not positive / finite, else 0.
+// Left-looking, one thread per row, ONE barrier per column: thread i forms
+//     L[i,k] = (A[i,k] - sum_{m<k} L[i,m] L[k,m]) * rsqrt(A[k,k] - sum_{m<k} L[k,m]^2)
+// from columns that are already final (every thread recomputes the pivot instead of waiting for it).
+// Rows are stored with an odd leading dimension, so a column access is bank-conflict free and the pivot row is
+// a broadcast.  The right-hand side is row n: after the factorisation it holds y = L^-1 rhs.
+// A: n x n column-major, lower triangle used, overwritten by L.  b: rhs (n).  x: solution (n).
+// fail: (k+1) when pivot k is not positive / finite, else 0.
 template <bool SMEM>
 __global__ void __launch_bounds__(CHOL_THREADS)
 k_cholesky_solve(double* Ag, double* b, double* x, int n, double* fail, double* work)
 {
     extern __shared__ double sh[];
-    // augmented storage: (n+1) rows x n columns, leading dimension ld = n+1, row n = rhs^T
-    const int ld = n + 1;
-    double* A = SMEM ? sh : work;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = CHOL_THREADS / 32;
-    __shared__ double s_ipiv;
+    const int ld = n | 1;                          // odd row stride
+    double* L = SMEM ? sh : work;                  // (n+1) rows x ld, then n diagonal entries of the factor
+    double* dg = L + (size_t)(n + 1) * ld;
+    const int tid = threadIdx.x;
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     for (int e = tid; e < n * n; e += CHOL_THREADS) {
-        const int j = e / n, i = e - j * n;
-        A[i + (size_t)j * ld] = Ag[e];
+        const int j = e / n, i = e - j * n;        // column-major source
+        if (i >= j) L[(size_t)i * ld + j] = Ag[e];
     }
-    for (int j = tid; j < n; j += CHOL_THREADS) A[n + (size_t)j * ld] = b[j];
+    for (int j = tid; j < n; j += CHOL_THREADS) L[(size_t)n * ld + j] = b[j];
     __syncthreads();
     for (int k = 0; k < n; ++k) {
+        const double* rk = L + (size_t)k * ld;
+        double dkk = rk[k];                        // A[k,k] is never overwritten: the factor's diagonal lives in dg[]
+        for (int m = 0; m < k; ++m) dkk -= rk[m] * rk[m];
+        const bool bad = !(dkk > 0.0) || !isfinite(dkk);
+        const double ipiv = bad ? 0.0 : rsqrt(dkk);
         if (tid == 0) {
-            const double d = A[k + (size_t)k * ld];
-            if (!(d > 0.0) || !isfinite(d)) { s_fail = k + 1; s_ipiv = 0.0; }
-            else { const double p = sqrt(d); A[k + (size_t)k * ld] = p; s_ipiv = 1.0 / p; }
+            dg[k] = dkk * ipiv;
+            if (bad && s_fail == 0) s_fail = k + 1;
+        }
+        for (int i = k + 1 + tid; i <= n; i += CHOL_THREADS) {
+            double* ri = L + (size_t)i * ld;
+            double v = ri[k];
+            for (int m = 0; m < k; ++m) v -= ri[m] * rk[m];
+            ri[k] = v * ipiv;                      // only thread i ever touches L[i,k] during this step
         }
         __syncthreads();
         if (s_fail) break;
-        const double ipiv = s_ipiv;
-        double* colk = A + (size_t)k * ld;
-        for (int i = k + 1 + tid; i <= n; i += CHOL_THREADS) colk[i] *= ipiv;
-        __syncthreads();
-        // trailing update: A[i,j] -= L[i,k] L[j,k] for k < j < n, j <= i <= n
-        for (int j = k + 1 + warp; j < n; j += NW) {
-            const double ljk = colk[j];
-            double* colj = A + (size_t)j * ld;
-            for (int i = j + lane; i <= n; i += 32) colj[i] -= colk[i] * ljk;
-        }
-        __syncthreads();
     }
     if (s_fail) {
         if (tid == 0) *fail = (double)s_fail;
         return;
     }
-    // backward substitution L^T x = y, y = row n of the factor; solution accumulates in row n
+    // backward substitution L^T x = y (y = row n); the solution overwrites row n
+    double* y = L + (size_t)n * ld;
     for (int k = n - 1; k >= 0; --k) {
-        if (tid == 0) A[n + (size_t)k * ld] /= A[k + (size_t)k * ld];
+        const double* rk = L + (size_t)k * ld;
+        if (tid == 0) y[k] = y[k] / dg[k];
         __syncthreads();
-        const double xk = A[n + (size_t)k * ld];
-        for (int i = tid; i < k; i += CHOL_THREADS) A[n + (size_t)i * ld] -= A[k + (size_t)i * ld] * xk;
+        const double xk = y[k];
+        for (int i = tid; i < k; i += CHOL_THREADS) y[i] -= rk[i] * xk;
         __syncthreads();
     }
-    for (int i = tid; i < n; i += CHOL_THREADS) x[i] = A[n + (size_t)i * ld];
+    for (int i = tid; i < n; i += CHOL_THREADS) x[i] = y[i];
     for (int e = tid; e < n * n; e += CHOL_THREADS) {
         const int j = e / n, i = e - j * n;
-        Ag[e] = A[i + (size_t)j * ld];
+        Ag[e] = (i > j) ? L[(size_t)i * ld + j] : (i == j ? dg[j] : 0.0);
     }
     if (tid == 0) *fail = 0.0;
 }
 
-// `work` must hold (n+1)*n doubles when n > CHOL_SMEM_MAX_N (ignored otherwise)
+// `work` must hold (n+1)*(n|1)+n doubles when n > CHOL_SMEM_MAX_N (ignored otherwise)
 int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
                           cudaStream_t stream)
 {
     if (n <= CHOL_SMEM_MAX_N) {
-        const size_t bytes = (size_t)(n + 1) * n * sizeof(double);
+        const size_t bytes = ((size_t)(n + 1) * (n | 1) + n) * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
             SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (CHOL_SMEM_MAX_N + 1) * CHOL_SMEM_MAX_N * (int)sizeof(double)));
+                                          ((CHOL_SMEM_MAX_N + 1) * (CHOL_SMEM_MAX_N | 1) + CHOL_SMEM_MAX_N) * (int)sizeof(double)));
             attr_set = true;
         }
         k_cholesky_solve<true><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev, nullptr);

@@ -668,30 +668,60 @@ k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, co
         const int* __restrict__ item_chunk, double* __restrict__ schur_partials)
 {
     constexpr int NV = NR * NC + NR, NVALL = NC * NC + NC;
+    constexpr int EPT = CHUNK / TPB;                       // entries per thread
+    // 16-byte vector loads of the Z records when every offset involved is even
+    constexpr bool VEC = ((NC * 3) % 2 == 0) && ((NR * 3) % 2 == 0) && ((ROW0 * 3) % 2 == 0);
     __shared__ double sm[NV * (TPB / 32)];
     const int item = blockIdx.x, ch = item_chunk[item];
     const int j = chunk_cam[ch], jp = j + (item - item_base[ch]);
     const bool diag = (jp == j);
+    const int beg = chunk_beg[ch], end = chunk_end[ch];
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    const int* row = obs_of + (size_t)jp * N;
-    for (int t = chunk_beg[ch] + threadIdx.x; t < chunk_end[ch]; t += TPB) {
-        const int a = cm_obs[t], i = cm_pts[t];
-        const int b = diag ? a : row[i];
-        if (b < 0) continue;
+    // stage 1: all indices of this thread's entries, then all (camera j', track) look-ups: independent loads in flight
+    int ea[EPT], eb[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int t = beg + threadIdx.x + e * TPB;
+        ea[e] = t < end ? cm_obs[t] : -1;
+        eb[e] = t < end ? cm_pts[t] : 0;                   // track index for now
+    }
+    if (!diag) {
+        const int* row = obs_of + (size_t)jp * N;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) eb[e] = ea[e] >= 0 ? row[eb[e]] : -1;
+    }
+    // stage 2: products
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int a = ea[e];
+        const int b = diag ? a : eb[e];
+        if (a < 0 || b < 0) continue;
+        double A[NR * 3], B[NC * 3];
         const double* za = Zin + (size_t)a * NC * 3 + ROW0 * 3;
         const double* zb = Zin + (size_t)b * NC * 3;
-        double A[NR * 3];
+        if (VEC) {
+            const double2* za2 = reinterpret_cast<const double2*>(za);
+            const double2* zb2 = reinterpret_cast<const double2*>(zb);
 #pragma unroll
-        for (int k = 0; k < NR * 3; ++k) A[k] = za[k];
+            for (int k = 0; k < NR * 3 / 2; ++k) { const double2 v = za2[k]; A[2 * k] = v.x; A[2 * k + 1] = v.y; }
+#pragma unroll
+            for (int k = 0; k < NC * 3 / 2; ++k) { const double2 v = zb2[k]; B[2 * k] = v.x; B[2 * k + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NR * 3; ++k) A[k] = za[k];
+#pragma unroll
+            for (int k = 0; k < NC * 3; ++k) B[k] = zb[k];
+        }
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
-            const double b0 = zb[3 * s], b1 = zb[3 * s + 1], b2 = zb[3 * s + 2];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r * NC + s] += A[3 * r] * b0 + A[3 * r + 1] * b1 + A[3 * r + 2] * b2;
+            for (int r = 0; r < NR; ++r)
+                acc[r * NC + s] += A[3 * r] * B[3 * s] + A[3 * r + 1] * B[3 * s + 1] + A[3 * r + 2] * B[3 * s + 2];
         }
         if (diag) {
+            const int i = eb[e];
             const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
 #pragma unroll
             for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;

@@ -292,7 +292,7 @@ extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info
     if (!A || !b || n < 1) { set_error("bad argument"); return SBA_E_INVALID; }
     SBA_TRY(require_device());
     DevBuf dA, db, dx, df, dw;
-    SBA_TRY(dw.alloc((size_t)(n + 1) * n * sizeof(double)));
+    SBA_TRY(dw.alloc(((size_t)(n + 1) * (n | 1) + n) * sizeof(double)));
     SBA_TRY(dA.alloc((size_t)n * n * sizeof(double))); SBA_TRY(db.alloc(n * sizeof(double)));
     SBA_TRY(dx.alloc(n * sizeof(double))); SBA_TRY(df.alloc(sizeof(double)));
     SBA_CUDA(cudaMemcpy(dA.p, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
