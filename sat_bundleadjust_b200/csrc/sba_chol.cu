@@ -39,8 +39,17 @@ k_cholesky_solve(double* Ag, double* b, double* x, int n, double* fail, double* 
     __syncthreads();
     for (int k = 0; k < n; ++k) {
         const double* rk = L + (size_t)k * ld;
-        double dkk = rk[k];                        // A[k,k] is never overwritten: the factor's diagonal lives in dg[]
-        for (int m = 0; m < k; ++m) dkk -= rk[m] * rk[m];
+        // A[k,k] is never overwritten: the factor's diagonal lives in dg[].  Four independent chains per dot product:
+        // a single dependent DFMA chain costs ~10 cycles per term on this part.
+        double d0 = rk[k], d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        {
+            int m = 0;
+            for (; m + 4 <= k; m += 4) {
+                d0 -= rk[m] * rk[m]; d1 -= rk[m + 1] * rk[m + 1]; d2 -= rk[m + 2] * rk[m + 2]; d3 -= rk[m + 3] * rk[m + 3];
+            }
+            for (; m < k; ++m) d0 -= rk[m] * rk[m];
+        }
+        const double dkk = (d0 + d1) + (d2 + d3);
         const bool bad = !(dkk > 0.0) || !isfinite(dkk);
         const double ipiv = bad ? 0.0 : rsqrt(dkk);
         if (tid == 0) {
@@ -49,9 +58,13 @@ k_cholesky_solve(double* Ag, double* b, double* x, int n, double* fail, double* 
         }
         for (int i = k + 1 + tid; i <= n; i += CHOL_THREADS) {
             double* ri = L + (size_t)i * ld;
-            double v = ri[k];
-            for (int m = 0; m < k; ++m) v -= ri[m] * rk[m];
-            ri[k] = v * ipiv;                      // only thread i ever touches L[i,k] during this step
+            double v0 = ri[k], v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            int m = 0;
+            for (; m + 4 <= k; m += 4) {
+                v0 -= ri[m] * rk[m]; v1 -= ri[m + 1] * rk[m + 1]; v2 -= ri[m + 2] * rk[m + 2]; v3 -= ri[m + 3] * rk[m + 3];
+            }
+            for (; m < k; ++m) v0 -= ri[m] * rk[m];
+            ri[k] = ((v0 + v1) + (v2 + v3)) * ipiv;   // only thread i ever touches L[i,k] during this step
         }
         __syncthreads();
         if (s_fail) break;

@@ -244,6 +244,7 @@ k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __re
                   double* scal)
 {
     __shared__ double sv[WPB][9][32];
+    __shared__ int strk[WPB][32];
     __shared__ double sm[1 * (TPB / 32)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ob, nobs;
@@ -277,19 +278,22 @@ k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __re
         }
 #pragma unroll
         for (int k = 0; k < 9; ++k) sv[warp][k][lane] = vals[k];
+        // tracks of the tile: bit l of `heads` is set when lane l holds the first observation of a track
+        const bool head = lane < nobs && a == o.track_ptr[i];
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int ntr = __popc(heads);
+        if (head) strk[warp][__popc(heads & ((1u << lane) - 1u))] = i;
         __syncwarp();
-        if (lane < nobs) {
-            const int beg = o.track_ptr[i];
-            if (a == beg) {
-                const int L = o.track_ptr[i + 1] - beg;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    double t = 0.0;
-                    for (int m = 0; m < L; ++m) t += sv[warp][k][lane + m];
-                    if (k < 6) V[6 * (size_t)i + k] = t;
-                    else gp_out[3 * (size_t)i + (k - 6)] = t;
-                }
-            }
+        // one lane per (track, value): 9 * ntr short sums instead of 9 long ones on the head lanes
+        for (int s = lane; s < 9 * ntr; s += 32) {
+            const int tr = s / 9, k = s - 9 * tr;
+            const int l0 = __fns(heads, 0, tr + 1);
+            const int l1 = (tr + 1 < ntr) ? __fns(heads, 0, tr + 2) : nobs;
+            double t = 0.0;
+            for (int m = l0; m < l1; ++m) t += sv[warp][k][m];
+            const int it = strk[warp][tr];
+            if (k < 6) V[6 * (size_t)it + k] = t;
+            else gp_out[3 * (size_t)it + (k - 6)] = t;
         }
     } else {
         // a single long track: the warp strides over its observations

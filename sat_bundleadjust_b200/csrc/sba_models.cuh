@@ -26,6 +26,24 @@
 
 namespace sba {
 
+// IEEE-rounded reciprocal and (1-2 ulp) reciprocal square root: single fast-path sequences on the device
+SBA_HD double fast_rcp(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+SBA_HD double fast_rsqrt(double x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 enum Model { MODEL_AFFINE = 0, MODEL_PERSPECTIVE = 1, MODEL_RPC = 2 };
 enum Loss { LOSS_LINEAR = 0, LOSS_HUBER = 1, LOSS_SOFT_L1 = 2, LOSS_CAUCHY = 3, LOSS_ARCTAN = 4 };
 
@@ -451,7 +469,7 @@ SBA_HD void point_side(const double* __restrict__ rec, const double* __restrict_
         const double pu = m[0] * X + m[1] * Y + m[2] * Z + rec[CR_KT];
         const double pv = m[3] * X + m[4] * Y + m[5] * Z + rec[CR_KT + 1];
         const double d = m[6] * X + m[7] * Y + m[8] * Z + rec[CR_KT + 2];
-        const double invd = 1.0 / d;
+        const double invd = fast_rcp(d);
         u = pu * invd; v = pv * invd;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -488,7 +506,7 @@ SBA_HD void full_side(const double* __restrict__ rec, const double* __restrict__
     if (MODEL == MODEL_PERSPECTIVE) {
         a = r.x3 + c.t0; b = r.y3 + c.t1;
         const double d = r.z2 + c.t2;
-        invd = 1.0 / d;
+        invd = fast_rcp(d);
         u = (c.k0 * a + c.k2 * b + c.k3 * d) * invd;
         v = (c.k1 * b + c.k4 * d) * invd;
         A[0] = c.k0 * invd; A[1] = c.k2 * invd; A[2] = (c.k3 - u) * invd;
@@ -570,6 +588,11 @@ SBA_HD void loss_rho(int loss, double z, double& r0, double& r1, double& r2)
 SBA_HD double loss_cost(int loss, double f, double f_scale)
 {
     if (loss == LOSS_LINEAR) return 0.5 * f * f;
+    if (loss == LOSS_SOFT_L1) {
+        const double q = f * fast_rcp(f_scale);
+        const double t = 1.0 + q * q;
+        return f_scale * f_scale * (t * fast_rsqrt(t) - 1.0);
+    }
     const double q = f / f_scale;
     double r0, r1, r2;
     loss_rho(loss, q * q, r0, r1, r2);
@@ -583,14 +606,15 @@ SBA_HD double loss_rescale(int loss, double f_scale, double& f, double& cost)
     if (loss == LOSS_SOFT_L1) {
         // rho' = t^-1/2, rho'' = -1/2 t^-3/2  =>  rho' + 2 rho'' z = t^-3/2 exactly (t = 1 + z):
         // scale = t^-3/4, f <- f t^1/4.  One sqrt and one reciprocal-sqrt instead of two sqrt + three divisions.
-        const double q = f / f_scale;
+        const double q = f * fast_rcp(f_scale);
         const double t = 1.0 + q * q;
         if (t < 1e10) {                        // beyond that scipy's EPS clamp of the scale applies: generic path
-            const double s = sqrt(t);          // t^1/2
-            const double s4 = sqrt(s);         // t^1/4
+            const double r2 = fast_rsqrt(t);   // t^-1/2
+            const double s = t * r2;           // t^1/2
+            const double r4 = fast_rsqrt(s);   // t^-1/4
             cost = f_scale * f_scale * (s - 1.0);
-            f = f * s4;
-            return 1.0 / (s * s4);             // t^-3/4
+            f = f * (s * r4);                  // f t^1/4
+            return r2 * r4;                    // t^-3/4
         }
     }
     const double q = f / f_scale;
