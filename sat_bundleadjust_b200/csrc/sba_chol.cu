@@ -91,11 +91,80 @@ k_cholesky_solve(double* Ag, double* b, double* x, int n, double* fail, double* 
     if (tid == 0) *fail = 0.0;
 }
 
+constexpr int CHOL_RL_MAX_N = 100;     // two (n+1) x (n|1) buffers must fit in shared memory
+
+// Small systems (n <= 100): right-looking with ONE barrier per column and no serial section.
+// W holds the running Schur complement (never scaled), Lf receives the factor.  In step k every thread reads the
+// pivot W[k,k] itself, forms 1/pivot, and applies W[i,j] -= W[i,k] W[j,k] / W[k,k] to its share of the trailing
+// triangle (16 x 16 thread tile, rows strided by 16 over ty, columns over tx); column k of W is only read in step k,
+// so nothing it needs is overwritten.  The threads with tx == 0 also emit L[i,k] = W[i,k] / sqrt(W[k,k]).
+// The right-hand side is row n of W, so row n of Lf ends up as y = L^-1 rhs.
+__global__ void __launch_bounds__(CHOL_THREADS)
+k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
+{
+    extern __shared__ double sh[];
+    const int ld = n | 1;
+    double* W = sh;
+    double* Lf = sh + (size_t)(n + 1) * ld;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int e = tid; e < n * n; e += CHOL_THREADS) {
+        const int j = e / n, i = e - j * n;
+        if (i >= j) W[(size_t)i * ld + j] = Ag[e];
+    }
+    for (int j = tid; j < n; j += CHOL_THREADS) W[(size_t)n * ld + j] = b[j];
+    __syncthreads();
+    int failed = 0;
+    for (int k = 0; k < n; ++k) {
+        const double dkk = W[(size_t)k * ld + k];
+        if (!(dkk > 0.0) || !isfinite(dkk)) { failed = k + 1; break; }      // uniform: every thread reads the same value
+        const double inv = fast_rcp(dkk);
+        if (tx == 0) {
+            const double ip = fast_rsqrt(dkk);
+            for (int i = k + ty; i <= n; i += 16) Lf[(size_t)i * ld + k] = W[(size_t)i * ld + k] * ip;
+        }
+        for (int i = k + 1 + ty; i <= n; i += 16) {
+            const double aik = W[(size_t)i * ld + k] * inv;
+            double* wi = W + (size_t)i * ld;
+            const int jmax = i < n ? i : n - 1;
+            for (int j = k + 1 + tx; j <= jmax; j += 16) wi[j] -= aik * W[(size_t)j * ld + k];
+        }
+        __syncthreads();
+    }
+    if (failed) {
+        if (tid == 0) *fail = (double)failed;
+        return;
+    }
+    double* y = Lf + (size_t)n * ld;
+    for (int k = n - 1; k >= 0; --k) {
+        const double* rk = Lf + (size_t)k * ld;
+        if (tid == 0) y[k] = y[k] / rk[k];
+        __syncthreads();
+        const double xk = y[k];
+        for (int i = tid; i < k; i += CHOL_THREADS) y[i] -= rk[i] * xk;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += CHOL_THREADS) x[i] = y[i];
+    for (int e = tid; e < n * n; e += CHOL_THREADS) {
+        const int j = e / n, i = e - j * n;
+        Ag[e] = (i >= j) ? Lf[(size_t)i * ld + j] : 0.0;
+    }
+    if (tid == 0) *fail = 0.0;
+}
+
 // `work` must hold (n+1)*(n|1)+n doubles when n > CHOL_SMEM_MAX_N (ignored otherwise)
 int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
                           cudaStream_t stream)
 {
-    if (n <= CHOL_SMEM_MAX_N) {
+    if (n <= CHOL_RL_MAX_N) {
+        const size_t bytes = 2 * (size_t)(n + 1) * (n | 1) * sizeof(double);
+        static bool attr_small = false;
+        if (!attr_small) {
+            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          2 * (CHOL_RL_MAX_N + 1) * (CHOL_RL_MAX_N | 1) * (int)sizeof(double)));
+            attr_small = true;
+        }
+        k_cholesky_solve_small<<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+    } else if (n <= CHOL_SMEM_MAX_N) {
         const size_t bytes = ((size_t)(n + 1) * (n | 1) + n) * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {

@@ -220,7 +220,7 @@ def test_cholesky_solve(built):
     from sat_bundleadjust_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(0)
-    for n in (1, 7, 60, 161, 300):
+    for n in (1, 7, 60, 100, 101, 130, 161, 300):
         A = rng.standard_normal((n, n + 5))
         S = A @ A.T + 0.1 * np.eye(n)
         b = rng.standard_normal(n)
