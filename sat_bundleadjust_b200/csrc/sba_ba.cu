@@ -165,10 +165,26 @@ static int run_residual(sba_problem* p, const double* x, const double* camrec, i
     return check_launch(p);
 }
 
-// fused residual + analytic Jacobian + robust weighting + block assembly at x (camrec must be prepared)
+// fused residual + analytic Jacobian + robust weighting + block assembly at x (camrec must be prepared).
+// The track-major half (V, g_p) runs on the solver's stream, the camera-major half (U, g_c) on a side stream.
 static int run_assemble(sba_problem* p, const double* x, const double* camrec, int loss, double f_scale)
 {
     const double* xp = x + (size_t)p->M * p->nc;
+    SBA_CUDA(cudaEventRecord(p->ev_fork, p->stream));
+    SBA_CUDA(cudaStreamWaitEvent(p->stream2, p->ev_fork, 0));
+    {
+#define L(MODEL, NC)                                                                                                   \
+    k_assemble_cameras<MODEL, NC><<<p->chunks.n, TPB, 0, p->stream2>>>(                                               \
+        p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_pts, (const double2*)p->cm_pts2d, p->cm_w, xp, camrec,      \
+        p->rpc_tab, p->n_cam_fix, loss, f_scale, p->cam_partials);                                                     \
+    SBA_TRY(check_launch(p));                                                                                          \
+    k_reduce_cameras<NC><<<p->M, 128, 0, p->stream2>>>(p->cam_partials, p->cam_ptr /* first chunk table */, p->M,      \
+                                                       p->camsys_local)
+        SBA_DISPATCH(p, L);
+#undef L
+        SBA_TRY(check_launch(p));
+    }
+    SBA_CUDA(cudaEventRecord(p->ev_join, p->stream2));
     {
         const int grid = (p->n_tiles + WPB - 1) / WPB;
 #define L(MODEL)                                                                                                      \
@@ -179,18 +195,7 @@ static int run_assemble(sba_problem* p, const double* x, const double* camrec, i
 #undef L
         SBA_TRY(check_launch(p));
     }
-    {
-#define L(MODEL, NC)                                                                                                   \
-    k_assemble_cameras<MODEL, NC><<<p->chunks.n, TPB, 0, p->stream>>>(                                                \
-        p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_pts, (const double2*)p->cm_pts2d, p->cm_w, xp, camrec,      \
-        p->rpc_tab, p->n_cam_fix, loss, f_scale, p->cam_partials);                                                     \
-    SBA_TRY(check_launch(p));                                                                                          \
-    k_reduce_cameras<NC><<<p->M, 128, 0, p->stream>>>(p->cam_partials, p->cam_ptr /* first chunk table */, p->M,       \
-                                                      p->camsys_local)
-        SBA_DISPATCH(p, L);
-#undef L
-        SBA_TRY(check_launch(p));
-    }
+    SBA_CUDA(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     if (p->world > 1) {
         const size_t cnt = (size_t)p->M * p->nc * p->nc + (size_t)p->M * p->nc;
         SBA_CUDA(cudaMemcpyAsync(p->camsys, p->camsys_local, cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
@@ -519,6 +524,9 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->flush_buf) cudaFree(p->flush_buf);
     delete p;
@@ -652,6 +660,9 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_alloc(&p->r_out, 2 * (size_t)K));
     SBA_CUDA(cudaEventCreate(&p->ev0));
     SBA_CUDA(cudaEventCreate(&p->ev1));
+    SBA_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    SBA_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    SBA_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     SBA_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope
     return SBA_OK;
 }

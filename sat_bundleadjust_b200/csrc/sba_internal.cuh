@@ -82,6 +82,8 @@ struct sba_problem {
     int rank = 0, world = 1;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // side stream: the camera-major half of the assembly overlaps the track-major half
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     sba_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
 

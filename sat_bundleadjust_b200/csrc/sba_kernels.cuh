@@ -665,7 +665,7 @@ k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restric
 // slower on B200 -- 227 us vs 163 us at 5e5 observations -- because it serialises the partners.)
 // ------------------------------------------------------------------------------------------------
 template <int NC, int ROW0, int NR>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 3)
 k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
         const int* __restrict__ cm_obs, const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N, int M,
         const double* __restrict__ Zin, const double* __restrict__ q, const int* __restrict__ item_base,
