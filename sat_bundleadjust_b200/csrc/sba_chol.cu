@@ -99,6 +99,7 @@ constexpr int CHOL_RL_MAX_N = 100;     // two (n+1) x (n|1) buffers must fit in 
 // triangle (16 x 16 thread tile, rows strided by 16 over ty, columns over tx); column k of W is only read in step k,
 // so nothing it needs is overwritten.  The threads with tx == 0 also emit L[i,k] = W[i,k] / sqrt(W[k,k]).
 // The right-hand side is row n of W, so row n of Lf ends up as y = L^-1 rhs.
+template <int NT>     // NT x NT register tile per thread: rows/columns k+1+t+16a, a < NT  (16*NT >= n+1)
 __global__ void __launch_bounds__(CHOL_THREADS)
 k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
 {
@@ -118,16 +119,39 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         const double dkk = W[(size_t)k * ld + k];
         if (!(dkk > 0.0) || !isfinite(dkk)) { failed = k + 1; break; }      // uniform: every thread reads the same value
         const double inv = fast_rcp(dkk);
-        if (tx == 0) {
+        // column k of the running complement for this thread's rows and columns (read-only during this step)
+        double ci[NT], cj[NT];
+#pragma unroll
+        for (int a = 0; a < NT; ++a) {
+            const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * a;
+            ci[a] = i <= n ? W[(size_t)i * ld + k] * inv : 0.0;
+            cj[a] = j < n ? W[(size_t)j * ld + k] : 0.0;
+        }
+        if (tx == 0) {      // factor column k (rows k..n) from the same, still unmodified, column
             const double ip = fast_rsqrt(dkk);
             for (int i = k + ty; i <= n; i += 16) Lf[(size_t)i * ld + k] = W[(size_t)i * ld + k] * ip;
         }
-        for (int i = k + 1 + ty; i <= n; i += 16) {
-            const double aik = W[(size_t)i * ld + k] * inv;
-            double* wi = W + (size_t)i * ld;
-            const int jmax = i < n ? i : n - 1;
-            for (int j = k + 1 + tx; j <= jmax; j += 16) wi[j] -= aik * W[(size_t)j * ld + k];
-        }
+        // all loads of the tile, then all FMAs, then all stores: shared-memory stores would otherwise serialise
+        // the loop (the compiler must assume they alias the next loads)
+        double w[NT][NT];
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * c;
+                w[a][c] = (i <= n && j <= i && j < n) ? W[(size_t)i * ld + j] : 0.0;
+            }
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int c = 0; c < NT; ++c) w[a][c] -= ci[a] * cj[c];
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * c;
+                if (i <= n && j <= i && j < n) W[(size_t)i * ld + j] = w[a][c];
+            }
         __syncthreads();
     }
     if (failed) {
@@ -158,12 +182,16 @@ int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, do
     if (n <= CHOL_RL_MAX_N) {
         const size_t bytes = 2 * (size_t)(n + 1) * (n | 1) * sizeof(double);
         static bool attr_small = false;
+        const int max_bytes = 2 * (CHOL_RL_MAX_N + 1) * (CHOL_RL_MAX_N | 1) * (int)sizeof(double);
         if (!attr_small) {
-            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          2 * (CHOL_RL_MAX_N + 1) * (CHOL_RL_MAX_N | 1) * (int)sizeof(double)));
+            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
+            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
             attr_small = true;
         }
-        k_cholesky_solve_small<<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        if (n + 1 <= 32) k_cholesky_solve_small<2><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        else if (n + 1 <= 64) k_cholesky_solve_small<4><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        else k_cholesky_solve_small<7><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
     } else if (n <= CHOL_SMEM_MAX_N) {
         const size_t bytes = ((size_t)(n + 1) * (n | 1) + n) * sizeof(double);
         static bool attr_set = false;

@@ -121,6 +121,9 @@ struct sba_problem {
     // measurement: event ring for per-phase timing, scratch for L2 flushes
     std::vector<cudaEvent_t> ev_pool;
     int ev_used = 0;
+    std::vector<void*> arena_chunks;         // device slabs owned by this problem
+    char* arena_ptr = nullptr;
+    size_t arena_left = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
 };
