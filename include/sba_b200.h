@@ -158,6 +158,13 @@ void stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, float *kp_a, flo
 int sba_stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, const float *kp_a, const float *kp_b, int64_t n_kp,
                                     const void *rpc_a, const void *rpc_b);
 
+/* Batched RPC refit, replaces ba_rpcfit.weighted_lsq (bundle_adjust/ba_rpcfit.py:88-153) for n_cam cameras at once:
+ * target (n_cam, n_samples, 2) = (col,row), input_locs (n_cam, n_samples, 3) = (lon,lat,alt) -> rpc_out (n_cam, 90)
+ * in the table layout above; h = ridge (1e-3), tol = RMSE change that stops the re-weighting (1e-2 px), max_iter (20).
+ * n_iter_out (n_cam) / rmse_out (n_cam) may be NULL. */
+int sba_rpcfit_weighted_lsq(const double *target, const double *input_locs, int32_t n_cam, int32_t n_samples, double h,
+                            double tol, int32_t max_iter, double *rpc_out, int32_t *n_iter_out, double *rmse_out);
+
 /* FP64 dense Cholesky solve of an n x n SPD system on the device (host buffers in/out), exposed for
  * tests of the reduced-camera-system factorisation.  A is column-major, overwritten by L. */
 int sba_cholesky_solve(double *A, double *b, int32_t n, int32_t *info);

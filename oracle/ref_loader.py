@@ -49,12 +49,16 @@ def load_reference():
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "bundle_adjust")]
         pkg._sba_stub = True
         sys.modules["bundle_adjust"] = pkg
+    # the reference's ba_rpcfit builds its output model with `rpcm.RPCModel(dict)`; rpcm is not installed, so the
+    # stub module hands out the oracle's look-alike (validated against the reference's compiled C, see rpc_oracle.py)
+    from . import rpc_oracle
+    sys.modules["rpcm"].RPCModel = rpc_oracle.RPCModel
     old = sys.dont_write_bytecode
     sys.dont_write_bytecode = True  # the reference tree is read-only
     try:
-        from bundle_adjust import ba_core, ba_params, ba_rotate, cam_utils, geo_utils
+        from bundle_adjust import ba_core, ba_params, ba_rotate, ba_rpcfit, cam_utils, geo_utils
     finally:
         sys.dont_write_bytecode = old
-    ns = types.SimpleNamespace(ba_core=ba_core, ba_params=ba_params, ba_rotate=ba_rotate,
+    ns = types.SimpleNamespace(ba_core=ba_core, ba_params=ba_params, ba_rotate=ba_rotate, ba_rpcfit=ba_rpcfit,
                                cam_utils=cam_utils, geo_utils=geo_utils)
     return ns

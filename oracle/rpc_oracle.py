@@ -85,7 +85,10 @@ class RPCModel:
             for attr, key, _ in _KEYS:
                 setattr(self, attr, float(d[key]))
             for attr, key in _POLYS:
-                setattr(self, attr, [float(d["%s_%d" % (key, i + 1)]) for i in range(20)])
+                if key in d:      # GeoTIFF-tag style: one string with the coefficients (what ba_rpcfit.initialize_rpc passes)
+                    setattr(self, attr, [float(v) for v in str(d[key]).split()])
+                else:
+                    setattr(self, attr, [float(d["%s_%d" % (key, i + 1)]) for i in range(20)])
 
     @classmethod
     def from_file(cls, path):

@@ -64,6 +64,7 @@ EXPORTED_SYMBOLS = [
     "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_solve",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
+    "sba_rpcfit_weighted_lsq",
 ]
 
 _lib = None
@@ -99,6 +100,9 @@ def load():
     lib.stereo_corresp_to_lonlatalt.argtypes = [c_double_p, c_float_p, c_float_p, c_float_p, ctypes.c_int, vp, vp]
     lib.stereo_corresp_to_lonlatalt.restype = None
     lib.sba_cholesky_solve.argtypes = [c_double_p, c_double_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.sba_rpcfit_weighted_lsq.argtypes = [c_double_p, c_double_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                            ctypes.c_double, ctypes.c_int32, c_double_p, ctypes.POINTER(ctypes.c_int32),
+                                            c_double_p]
     _lib = lib
     return lib
 

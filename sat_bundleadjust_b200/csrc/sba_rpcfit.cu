@@ -1,0 +1,292 @@
+// Batched RPC refit: regularised, iteratively re-weighted least squares of the 78 free RPC coefficients from
+// N (lon, lat, alt) -> (col, row) correspondences, one CTA per camera.
+//
+// Replaces bundle_adjust/ba_rpcfit.py:88-153 (`weighted_lsq`), :156-198 (`scaling_params`, `initialize_rpc`) and
+// :77-85 (`calculate_RMSE_row_col`).  The algorithm is the reference's: normalise by (max-min)/2 and min+scale,
+// design rows m = [1, p(lon,lat,alt), -t p(lon,lat,alt)] (p = the 19 non-constant RPC00B monomials, :17-44),
+// one unregularised solve, then up to max_iter passes with weights 1/den^2 and ridge h^2, stopping when the
+// pixel RMSE changes by less than tol.  What differs is the execution: the reference builds N x N diagonal weight
+// matrices with np.diagflat and inverts 39 x 39 matrices per camera in Python; here the two 39 x 39 normal systems
+// of a camera are accumulated by 256 threads from shared-memory samples and solved by one warp each
+// (Gaussian elimination with partial pivoting), all cameras at once.
+#include "sba_internal.cuh"
+
+namespace sba {
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_NC = 39;                 // unknowns per system
+constexpr int RF_LD = 41;                 // row stride of the augmented 39 x 40 systems (odd: no bank conflicts)
+constexpr int RF_NE = RF_NC * (RF_NC + 1) / 2 + RF_NC;     // upper triangle + rhs = 819 accumulators per system
+constexpr int RF_EPT = (2 * RF_NE + RF_THREADS - 1) / RF_THREADS;   // accumulators per thread (both systems) = 7
+constexpr int RF_CH = 64;                 // samples whose design vectors are staged at a time
+
+__device__ __forceinline__ void rf_monomials19(double lon, double lat, double alt, double* pv)
+{
+    pv[0] = lon; pv[1] = lat; pv[2] = alt; pv[3] = lon * lat; pv[4] = lon * alt; pv[5] = lat * alt;
+    pv[6] = lon * lon; pv[7] = lat * lat; pv[8] = alt * alt; pv[9] = lat * lon * alt; pv[10] = lon * lon * lon;
+    pv[11] = lon * lat * lat; pv[12] = lon * alt * alt; pv[13] = lon * lon * lat; pv[14] = lat * lat * lat;
+    pv[15] = lat * alt * alt; pv[16] = lon * lon * alt; pv[17] = lat * lat * alt; pv[18] = alt * alt * alt;
+}
+
+// design-row entry p of a sample with monomials pv and normalised target t
+__device__ __forceinline__ double rf_design(int p, const double* pv, double t)
+{
+    return p == 0 ? 1.0 : (p < 20 ? pv[p - 1] : -t * pv[p - 20]);
+}
+
+template <int NV>
+__device__ __forceinline__ void rf_block_reduce(double (&v)[NV], double* sm, bool is_max)
+{
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = is_max ? fmax(x, y) : x + y;
+        }
+        v[k] = x;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = sm[k];
+        for (int w = 1; w < RF_THREADS / 32; ++w) x = is_max ? fmax(x, sm[w * NV + k]) : x + sm[w * NV + k];
+        v[k] = x;
+    }
+}
+
+// Gaussian elimination with partial pivoting of the 39 x 40 augmented system A (row stride RF_LD) by one warp;
+// the solution ends up in sol[0..38].
+__device__ void rf_solve39(double* A, double* sol, int lane)
+{
+    for (int k = 0; k < RF_NC; ++k) {
+        // pivot search in column k, rows k..38
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + lane; i < RF_NC; i += 32) {
+            const double a = fabs(A[i * RF_LD + k]);
+            if (a > best) { best = a; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi != k)
+            for (int j = lane; j <= RF_NC; j += 32) {
+                const double t = A[k * RF_LD + j];
+                A[k * RF_LD + j] = A[bi * RF_LD + j];
+                A[bi * RF_LD + j] = t;
+            }
+        __syncwarp();
+        const double ipiv = 1.0 / A[k * RF_LD + k];
+        for (int i = k + 1 + lane; i < RF_NC; i += 32) {
+            const double f = A[i * RF_LD + k] * ipiv;
+            for (int j = k + 1; j <= RF_NC; ++j) A[i * RF_LD + j] -= f * A[k * RF_LD + j];
+        }
+        __syncwarp();
+    }
+    for (int k = RF_NC - 1; k >= 0; --k) {
+        double s = 0.0;
+        for (int j = k + 1 + lane; j < RF_NC; j += 32) s += A[k * RF_LD + j] * sol[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sol[k] = (A[k * RF_LD + RF_NC] - s) / A[k * RF_LD + k];
+        __syncwarp();
+    }
+}
+
+// target: (B, N, 2) col,row ; locs: (B, N, 3) lon,lat,alt ; rpc_out: (B, 90) tables of include/sba_b200.h
+__global__ void __launch_bounds__(RF_THREADS)
+k_rpcfit(const double* __restrict__ target, const double* __restrict__ locs, int N, double h2, double tol, int max_iter,
+         double* __restrict__ rpc_out, int* __restrict__ iters_out, double* __restrict__ rmse_out)
+{
+    extern __shared__ double dyn[];
+    double* s_lon = dyn;             // normalised samples, N each
+    double* s_lat = s_lon + N;
+    double* s_alt = s_lat + N;
+    double* s_c = s_alt + N;
+    double* s_r = s_c + N;
+    double* s_w = s_r + N;           // weights of the row system, then of the column system (2N)
+    __shared__ double A[2][RF_NC * RF_LD];
+    __shared__ double sol[2][RF_NC + 1];
+    __shared__ double red[10 * (RF_THREADS / 32)];
+    __shared__ double coef[80];      // row_num, row_den, col_num, col_den
+    __shared__ double spv[RF_CH][21];   // [1, 19 monomials] of the staged samples (odd stride)
+    const int cam = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* tg = target + (size_t)cam * N * 2;
+    const double* lc = locs + (size_t)cam * N * 3;
+
+    // 1. normalisation constants: scale = (max - min)/2, offset = min + scale  (ba_rpcfit.py:156-164)
+    double mx[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) mx[k] = -1.7976931348623157e308;
+    for (int s = tid; s < N; s += RF_THREADS) {
+        const double v[5] = {lc[3 * s], lc[3 * s + 1], lc[3 * s + 2], tg[2 * s], tg[2 * s + 1]};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { mx[k] = fmax(mx[k], v[k]); mx[5 + k] = fmax(mx[5 + k], -v[k]); }
+    }
+    rf_block_reduce<10>(mx, red, true);
+    double scale[5], offset[5];      // lon, lat, alt, col, row
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double hi = mx[k], lo = -mx[5 + k];
+        scale[k] = (hi - lo) / 2;
+        offset[k] = lo + scale[k];
+    }
+    for (int s = tid; s < N; s += RF_THREADS) {
+        s_lon[s] = (lc[3 * s] - offset[0]) / scale[0];
+        s_lat[s] = (lc[3 * s + 1] - offset[1]) / scale[1];
+        s_alt[s] = (lc[3 * s + 2] - offset[2]) / scale[2];
+        s_c[s] = (tg[2 * s] - offset[3]) / scale[3];
+        s_r[s] = (tg[2 * s + 1] - offset[4]) / scale[4];
+        s_w[s] = 1.0;
+        s_w[N + s] = 1.0;
+    }
+    // this thread's accumulators: entry e of system sys is (p, q) of the upper triangle, or (p, rhs)
+    int ep[RF_EPT], eq[RF_EPT], es[RF_EPT];
+#pragma unroll
+    for (int t = 0; t < RF_EPT; ++t) {
+        int e = tid + t * RF_THREADS;
+        es[t] = -1; ep[t] = 0; eq[t] = 0;
+        if (e < 2 * RF_NE) {
+            es[t] = e / RF_NE;
+            e -= es[t] * RF_NE;
+            if (e >= RF_NC * (RF_NC + 1) / 2) { ep[t] = e - RF_NC * (RF_NC + 1) / 2; eq[t] = RF_NC; }   // rhs
+            else {
+                int p = 0;
+                while (e >= RF_NC - p) { e -= RF_NC - p; ++p; }
+                ep[t] = p; eq[t] = p + e;
+            }
+        }
+    }
+    __syncthreads();
+
+    double rmse = 0.0, rmse_prev = 0.0;
+    int n_iter = 0;
+    for (int pass = 0; pass <= max_iter; ++pass) {
+        // 2. normal equations of both systems: sum_s w_s m_p m_q ( + h^2 on the diagonal after the first pass)
+        double acc[RF_EPT];
+#pragma unroll
+        for (int t = 0; t < RF_EPT; ++t) acc[t] = 0.0;
+        for (int s0 = 0; s0 < N; s0 += RF_CH) {
+            // the chunk's design vectors go through shared memory: the entries (p, q) differ per thread, so the
+            // monomials must be addressable
+            __syncthreads();
+            if (tid < RF_CH && s0 + tid < N) {
+                double pv[19];
+                rf_monomials19(s_lon[s0 + tid], s_lat[s0 + tid], s_alt[s0 + tid], pv);
+                spv[tid][0] = 1.0;
+#pragma unroll
+                for (int k = 0; k < 19; ++k) spv[tid][1 + k] = pv[k];
+            }
+            __syncthreads();
+            const int cnt = min(RF_CH, N - s0);
+            for (int c = 0; c < cnt; ++c) {
+                const int s = s0 + c;
+                const double tr = s_r[s], tc = s_c[s], wr = s_w[s], wc = s_w[N + s];
+#pragma unroll
+                for (int t = 0; t < RF_EPT; ++t) {
+                    if (es[t] < 0) continue;
+                    const double tt = es[t] == 0 ? tr : tc, ww = es[t] == 0 ? wr : wc;
+                    const double mp = ep[t] < 20 ? spv[c][ep[t]] : -tt * spv[c][ep[t] - 19];
+                    const double mq = eq[t] == RF_NC ? tt : (eq[t] < 20 ? spv[c][eq[t]] : -tt * spv[c][eq[t] - 19]);
+                    acc[t] += ww * mp * mq;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < RF_EPT; ++t) {
+            if (es[t] < 0) continue;
+            double v = acc[t];
+            if (pass > 0 && ep[t] == eq[t]) v += h2;
+            A[es[t]][ep[t] * RF_LD + eq[t]] = v;
+            if (eq[t] < RF_NC) A[es[t]][eq[t] * RF_LD + ep[t]] = v;
+        }
+        __syncthreads();
+        // 3. solve: warp 0 the row system, warp 1 the column system
+        if (warp < 2) rf_solve39(A[warp], sol[warp], lane);
+        __syncthreads();
+        if (tid < 80) {
+            const int sys = tid / 40, k = tid % 40;      // coef = [num(20), den(20)] per system, den[0] = 1
+            coef[tid] = k < 20 ? sol[sys][k] : (k == 20 ? 1.0 : sol[sys][k - 1]);
+        }
+        __syncthreads();
+        // 4. denominators -> weights of the next pass, and the pixel RMSE of this fit
+        double sq[2] = {0.0, 0.0};
+        for (int s = tid; s < N; s += RF_THREADS) {
+            double pv[19];
+            rf_monomials19(s_lon[s], s_lat[s], s_alt[s], pv);
+            double num_r = coef[0], den_r = coef[20], num_c = coef[40], den_c = coef[60];
+#pragma unroll
+            for (int k = 0; k < 19; ++k) {
+                num_r += coef[1 + k] * pv[k]; den_r += coef[21 + k] * pv[k];
+                num_c += coef[41 + k] * pv[k]; den_c += coef[61 + k] * pv[k];
+            }
+            s_w[s] = 1.0 / (den_r * den_r);
+            s_w[N + s] = 1.0 / (den_c * den_c);
+            const double er = (num_r / den_r - s_r[s]) * scale[4], ec = (num_c / den_c - s_c[s]) * scale[3];
+            sq[0] += ec * ec; sq[1] += er * er;
+        }
+        rf_block_reduce<2>(sq, red, false);
+        rmse_prev = rmse;
+        rmse = sqrt(0.5 * (sq[0] / N + sq[1] / N));
+        n_iter = pass;
+        if (pass > 0 && fabs(rmse_prev - rmse) < tol) break;
+    }
+    if (tid < 90) {
+        double v;
+        if (tid < 10) {
+            // row_off col_off lat_off lon_off alt_off row_scl col_scl lat_scl lon_scl alt_scl
+            const int map[5] = {4, 3, 1, 0, 2};
+            v = tid < 5 ? offset[map[tid]] : scale[map[tid - 5]];
+        } else v = coef[tid - 10];
+        rpc_out[(size_t)cam * 90 + tid] = v;
+    }
+    if (tid == 0) { iters_out[cam] = n_iter; rmse_out[cam] = rmse; }
+}
+
+}  // namespace sba
+
+using namespace sba;
+
+extern "C" int sba_rpcfit_weighted_lsq(const double* target, const double* input_locs, int32_t n_cam, int32_t n_samples,
+                                       double h, double tol, int32_t max_iter, double* rpc_out, int32_t* n_iter_out,
+                                       double* rmse_out)
+{
+    if (!target || !input_locs || !rpc_out || n_cam < 1 || n_samples < RF_NC || max_iter < 0) {
+        set_error("rpcfit: bad argument (need at least 39 samples per camera)");
+        return SBA_E_INVALID;
+    }
+    const size_t smem = (size_t)7 * n_samples * sizeof(double);
+    if (smem > 160 * 1024) { set_error("rpcfit: at most 2900 samples per camera"); return SBA_E_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: sat_bundleadjust_b200 has no CPU fallback");
+        return SBA_E_CUDA;
+    }
+    double *d_t = nullptr, *d_l = nullptr, *d_o = nullptr, *d_r = nullptr;
+    int* d_i = nullptr;
+    const size_t B = n_cam, N = n_samples;
+    SBA_CUDA(cudaMalloc(&d_t, B * N * 2 * sizeof(double)));
+    SBA_CUDA(cudaMalloc(&d_l, B * N * 3 * sizeof(double)));
+    SBA_CUDA(cudaMalloc(&d_o, B * 90 * sizeof(double)));
+    SBA_CUDA(cudaMalloc(&d_r, B * sizeof(double)));
+    SBA_CUDA(cudaMalloc(&d_i, B * sizeof(int)));
+    SBA_CUDA(cudaMemcpy(d_t, target, B * N * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(d_l, input_locs, B * N * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaFuncSetAttribute(k_rpcfit, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k_rpcfit<<<n_cam, RF_THREADS, smem>>>(d_t, d_l, n_samples, h * h, tol, max_iter, d_o, d_i, d_r);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(rpc_out, d_o, B * 90 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n_iter_out) SBA_CUDA(cudaMemcpy(n_iter_out, d_i, B * sizeof(int), cudaMemcpyDeviceToHost));
+    if (rmse_out) SBA_CUDA(cudaMemcpy(rmse_out, d_r, B * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_t); cudaFree(d_l); cudaFree(d_o); cudaFree(d_r); cudaFree(d_i);
+    return SBA_OK;
+}

@@ -10,6 +10,7 @@ Fixtures (all inputs are stored next to the outputs, so the tests never need the
                     reference `fun` at the initial point and at a perturbed point, the sparsity pattern,
                     the reference `run_ba_optimization` result (x, err, nfev, cost), and the reference's cost
                     function at a true local minimum (`conv_*`, oracle.ba_oracle.solve_converged)
+  rpcfit_golden.npz ba_rpcfit.weighted_lsq of the reference on 12 Rt-corrected 10x10x10 samplings (targets, inputs, fitted RPC, errors)
   rpc_golden.npz    the two SkySat RPCs of the reference's tests/data/images (coefficients as arrays),
                     projections / localisations / two-view triangulations computed by the compiled reference C,
                     and the reference `fun` for cam_model='rpc' driven through oracle.rpc_oracle.RPCModel
@@ -175,9 +176,47 @@ def make_rpc_golden(ref):
     np.savez_compressed(os.path.join(HERE, "rpc_golden.npz"), **out)
 
 
+def make_rpcfit_golden(ref):
+    """ba_rpcfit.weighted_lsq of the UNMODIFIED reference (its `rpcm.RPCModel` is the oracle's look-alike, see
+    oracle/ref_loader.py) on the Rt-corrected sampling of the two SkySat RPCs."""
+    from oracle import rpcfit_oracle
+    R = np.load(os.path.join(HERE, "rpc_golden.npz"))
+    out = {}
+    crop = {"col0": 0.0, "row0": 0.0, "width": 3199.0, "height": 1349.0}
+    rts = [np.array([3e-6, -2e-6, 4e-6, 0.8, -0.5, 0.3]), np.array([-5e-6, 1e-6, 2e-6, -1.0, 0.4, 0.7]),
+           np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0])]
+    k = 0
+    for key in ("rpc_a", "rpc_b"):
+        a = R[key]
+        rpc = rpc_oracle.RPCModel()
+        (rpc.row_offset, rpc.col_offset, rpc.lat_offset, rpc.lon_offset, rpc.alt_offset,
+         rpc.row_scale, rpc.col_scale, rpc.lat_scale, rpc.lon_scale, rpc.alt_scale) = [float(v) for v in a[:10]]
+        rpc.row_num, rpc.row_den, rpc.col_num, rpc.col_den = [list(a[10 + 20 * i: 30 + 20 * i]) for i in range(4)]
+        center = approx_center(rpc)
+        for rt in rts:
+            for margin in (10, 160):
+                Rt = np.concatenate([rt, center])
+                target, locs, _ = rpcfit_oracle.rt_corrected_samples(Rt, rpc, crop, margin=margin)
+                fit = ref.ba_rpcfit.weighted_lsq(target, locs)
+                err = ref.ba_rpcfit.check_errors(fit, locs, target)
+                pre = "case%d/" % k
+                out[pre + "Rt"], out[pre + "src"], out[pre + "margin"] = Rt, np.array(key), np.array(margin)
+                out[pre + "target"], out[pre + "input_locs"] = target, locs
+                out[pre + "ref_rpc"] = rpc_arrays(fit)
+                out[pre + "ref_err"] = err
+                k += 1
+    out["n_cases"] = np.array(k)
+    np.savez_compressed(os.path.join(HERE, "rpcfit_golden.npz"), **out)
+    print("rpcfit cases", k)
+
+
 if __name__ == "__main__":
     ref = load_reference()
+    if "--only-rpcfit" in sys.argv:
+        make_rpcfit_golden(ref)
+        sys.exit(0)
     make_ba_golden(ref)
     make_rpc_golden(ref)
-    for f in ("ba_golden.npz", "rpc_golden.npz"):
+    make_rpcfit_golden(ref)
+    for f in ("ba_golden.npz", "rpc_golden.npz", "rpcfit_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
