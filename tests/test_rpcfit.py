@@ -9,8 +9,8 @@ determines.  Replacing np.linalg.inv(A) @ b by np.linalg.solve(A, b) inside the 
 changes the pass count (1 instead of 3), the coefficients by 3e-4 and the projections on the samples by 1e-3 px
 (test_reference_fit_is_ill_conditioned below documents this).  What IS well-posed, and what we require:
   * normalisation constants: 1e-12 relative (same min/max arithmetic)
-  * the fitted function on the samples: within 5e-3 px of the reference fit's projections (both fits reproduce the
-    targets to ~1e-3 px) and a fit error (check_errors) no worse than 3x the reference's
+  * the fitted function on the samples: a fit error against the targets (check_errors) no worse than 3x the
+    reference's (or 2e-3 px); in the wide-margin cases the reference's own fit is off by 1e-2 px while ours is at 1e-4
 """
 import numpy as np
 import pytest
@@ -75,10 +75,6 @@ def test_gpu_weighted_lsq_batch_vs_reference_golden(built):
             r, g = ref[10 + 20 * a: 14 + 20 * a], got[10 + 20 * a: 14 + 20 * a]
             assert np.abs(g - r).max() <= 1e-3 * np.abs(ref[10 + 20 * a: 30 + 20 * a]).max()
         x = locs[k]
-        ref_model = util.rpc_from_array(ref)
-        pr = np.stack(ref_model.projection(x[:, 0], x[:, 1], x[:, 2]), axis=1)
-        pg = np.stack(m.projection(x[:, 0], x[:, 1], x[:, 2]), axis=1)
-        assert np.abs(pr - pg).max() < 5e-3
         err = ba_rpcfit.check_errors(m, x, targets[k])
         ref_err = F["case%d/ref_err" % k]
         assert err.max() <= max(3 * ref_err.max(), 2e-3) and np.sqrt(np.mean(err ** 2)) <= max(3 * np.sqrt(np.mean(ref_err ** 2)), 1e-3)
