@@ -237,7 +237,7 @@ k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict_
 // of each track are formed by the lane of its first observation from the warp's shared-memory slice.
 // ------------------------------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, MODEL == MODEL_RPC ? 3 : 6)
 k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
                   const double* __restrict__ rpc_tab, int n_pts_fix, int loss, double f_scale,
                   double* __restrict__ V, double* __restrict__ gp_out, double* partials, unsigned* counter,
@@ -245,6 +245,7 @@ k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __re
 {
     __shared__ double sv[WPB][9][32];
     __shared__ int strk[WPB][32];
+    __shared__ int sseg[WPB][32];
     __shared__ double sm[1 * (TPB / 32)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ob, nobs;
@@ -278,17 +279,20 @@ k_assemble_points(ObsArrays o, const double* __restrict__ xp, const double* __re
         }
 #pragma unroll
         for (int k = 0; k < 9; ++k) sv[warp][k][lane] = vals[k];
-        // tracks of the tile: bit l of `heads` is set when lane l holds the first observation of a track
+        // tracks of the tile: the lane holding a track's first observation publishes (track, first lane, length)
         const bool head = lane < nobs && a == o.track_ptr[i];
         const unsigned heads = __ballot_sync(0xffffffffu, head);
         const int ntr = __popc(heads);
-        if (head) strk[warp][__popc(heads & ((1u << lane) - 1u))] = i;
+        if (head) {
+            const int rank = __popc(heads & ((1u << lane) - 1u));
+            strk[warp][rank] = i;
+            sseg[warp][rank] = lane | ((o.track_ptr[i + 1] - a) << 8);
+        }
         __syncwarp();
         // one lane per (track, value): 9 * ntr short sums instead of 9 long ones on the head lanes
         for (int s = lane; s < 9 * ntr; s += 32) {
             const int tr = s / 9, k = s - 9 * tr;
-            const int l0 = __fns(heads, 0, tr + 1);
-            const int l1 = (tr + 1 < ntr) ? __fns(heads, 0, tr + 2) : nobs;
+            const int seg = sseg[warp][tr], l0 = seg & 0xff, l1 = l0 + (seg >> 8);
             double t = 0.0;
             for (int m = l0; m < l1; ++m) t += sv[warp][k][m];
             const int it = strk[warp][tr];
@@ -480,7 +484,7 @@ k_scale_dots(const double* __restrict__ camsys, const double* __restrict__ V, co
 // J * [v1 v2] over all observations; sums |Jv1|^2 (, Jv1.Jv2, |Jv2|^2)
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int NC, int NVEC>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, (MODEL == MODEL_RPC || NC > 6) ? 3 : 6)
 k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
       const double* __restrict__ rpc_tab, long long K, int ns, int n_cam_fix, int n_pts_fix, int loss, double f_scale,
       const double* __restrict__ v1, const double* __restrict__ v2, double* partials, unsigned* counter, double* scal,
@@ -591,7 +595,7 @@ __device__ __forceinline__ void obs_Z(const ObsEval<MODEL, NC>& e, const double 
 }
 
 template <int MODEL, int NC>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, (MODEL == MODEL_RPC || NC > 6) ? 3 : 6)
 k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
              const double* __restrict__ rpc_tab, int ns, int n_cam_fix, int n_pts_fix, int loss,
              double f_scale, const double* __restrict__ V, const double* __restrict__ g,
