@@ -10,7 +10,8 @@ changes the pass count (1 instead of 3), the coefficients by 3e-4 and the projec
 (test_reference_fit_is_ill_conditioned below documents this).  What IS well-posed, and what we require:
   * normalisation constants: 1e-12 relative (same min/max arithmetic)
   * the fitted function on the samples: a fit error against the targets (check_errors) no worse than 3x the
-    reference's (or 2e-3 px); in the wide-margin cases the reference's own fit is off by 1e-2 px while ours is at 1e-4
+    reference's or 2.5e-2 px (max) / 1e-2 px (rms), i.e. the stopping threshold itself; tightening `tol` gives the
+    converged fit (test below)
 """
 import numpy as np
 import pytest
@@ -77,8 +78,15 @@ def test_gpu_weighted_lsq_batch_vs_reference_golden(built):
         x = locs[k]
         err = ba_rpcfit.check_errors(m, x, targets[k])
         ref_err = F["case%d/ref_err" % k]
-        assert err.max() <= max(3 * ref_err.max(), 2e-3) and np.sqrt(np.mean(err ** 2)) <= max(3 * np.sqrt(np.mean(ref_err ** 2)), 1e-3)
+        # the pass count hangs on |dRMSE| < 1e-2 px: with an accurate first solve the loop may stop after one pass where the
+        # reference's inaccurate inverse makes it run three, leaving up to ~2e-2 px at the corners of the widest samplings
+        assert err.max() <= max(3 * ref_err.max(), 2.5e-2) and np.sqrt(np.mean(err ** 2)) <= max(3 * np.sqrt(np.mean(ref_err ** 2)), 1e-2)
         assert 1 <= iters[k] <= 20 and rmse[k] < 0.01
+    # a tighter stopping threshold reaches the reference's fit quality everywhere
+    tight, _, _ = ba_rpcfit.weighted_lsq_batch(targets, locs, tol=1e-5)
+    for k, m in enumerate(tight):
+        err = ba_rpcfit.check_errors(m, locs[k], targets[k])
+        assert err.max() <= max(3 * F["case%d/ref_err" % k].max(), 2e-3)
     # single-camera entry point, same arguments as the reference
     one = ba_rpcfit.weighted_lsq(targets[3], locs[3])
     assert np.array_equal(one.table(), models[3].table())
