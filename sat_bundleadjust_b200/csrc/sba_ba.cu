@@ -293,8 +293,8 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
     tm.begin(SBA_PH_SCHUR);
     {
 #define SCHUR_ARGS                                                                                                     \
-    p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->obs_of, p->N, p->M, p->Z, p->q, p->item_base, \
-        p->item_chunk, p->schur_partials
+    p->slice_block, p->slice_p0, p->slice_p1, p->sb_j, p->sb_jp, (const int2*)p->pairs, p->pts_ind, p->Z, p->q,          \
+        p->schur_partials
         switch (p->nc) {
         case 3: k_schur<3, 0, 3><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 5: k_schur<5, 0, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
@@ -310,8 +310,8 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
         SBA_TRY(check_launch(p));
 #undef SCHUR_ARGS
 #define FIN_ARGS                                                                                                       \
-    p->schur_partials, p->cam_ptr, p->item_base, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv,       \
-        p->scal, p->rank == 0, p->S
+    p->schur_partials, p->sb_first, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, p->scal,           \
+        p->rank == 0, p->S
         switch (p->nc) {
         case 3: k_schur_finalize<3><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
         case 5: k_schur_finalize<5><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
@@ -641,6 +641,50 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_CUDA(cudaMemsetAsync(p->obs_of, 0xFF, (size_t)M * N * sizeof(int), s));
     k_fill_obs_of<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cam_ind, p->pts_ind, K, N, p->obs_of);
     SBA_CUDA(cudaGetLastError());
+    // --- static pair lists of the Schur complement: count, scan on the host, fill ---
+    {
+        const int n_items = item_base.back();
+        int *d_counts = nullptr, *d_off = nullptr;
+        SBA_TRY(dev_alloc(p, &d_counts, (size_t)n_items));
+        SBA_TRY(dev_alloc(p, &d_off, (size_t)n_items));
+        k_pair_count<<<(n_items + 3) / 4, 128, 0, s>>>(p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_pts, p->obs_of, N,
+                                                      p->item_base, p->item_chunk, n_items, d_counts);
+        SBA_CUDA(cudaGetLastError());
+        std::vector<int> counts(n_items), off(n_items);
+        SBA_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (size_t)n_items * sizeof(int), cudaMemcpyDeviceToHost, s));
+        SBA_CUDA(cudaStreamSynchronize(s));
+        // pair list order: block (j, j'), then the chunks of camera j
+        std::vector<int> slice_block, slice_p0, slice_p1, sb_first;
+        long long total = 0;
+        for (size_t blk = 0; blk < sb_j.size(); ++blk) {
+            const int j = sb_j[blk], jp = sb_jp[blk];
+            const long long blk_begin = total;
+            for (int c = first_chunk[j]; c < first_chunk[j + 1]; ++c) {
+                const int item = item_base[c] + (jp - j);
+                off[item] = (int)total;
+                total += counts[item];
+            }
+            sb_first.push_back((int)slice_block.size());
+            for (long long q0 = blk_begin; q0 < total; q0 += SLICE) {
+                slice_block.push_back((int)blk); slice_p0.push_back((int)q0); slice_p1.push_back((int)std::min(q0 + SLICE, total));
+            }
+        }
+        sb_first.push_back((int)slice_block.size());
+        if (total > 2000000000LL) { set_error("pair list too large: use the matrix-free path"); return SBA_E_INVALID; }
+        p->n_pairs = total;
+        p->n_schur_items = (int)slice_block.size();
+        SBA_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, s));
+        SBA_TRY(dev_alloc(p, &p->pairs, (size_t)std::max<long long>(total, 1) * 2));
+        k_pair_fill<<<(n_items + 3) / 4, 128, 0, s>>>(p->chunks.cam, p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts,
+                                                     p->obs_of, N, p->item_base, p->item_chunk, n_items, d_off,
+                                                     (int2*)p->pairs);
+        SBA_CUDA(cudaGetLastError());
+        SBA_TRY(dev_upload(p, &p->slice_block, slice_block, s));
+        SBA_TRY(dev_upload(p, &p->slice_p0, slice_p0, s));
+        SBA_TRY(dev_upload(p, &p->slice_p1, slice_p1, s));
+        SBA_TRY(dev_upload(p, &p->sb_first, sb_first, s));
+        SBA_CUDA(cudaStreamSynchronize(s));   // `off` and the slice vectors go out of scope
+    }
 
     // --- iteration state ---
     const size_t n = (size_t)p->n, ns = (size_t)M * nc;

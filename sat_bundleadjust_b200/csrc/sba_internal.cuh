@@ -97,7 +97,10 @@ struct sba_problem {
     int n_schur_items = 0;   // (chunk, partner camera) partial slots
     int *item_base = nullptr;                                  // device: first slot of every chunk (n_chunks + 1)
     int *item_chunk = nullptr;                                 // device: slot -> chunk
-    int *sb_j = nullptr, *sb_jp = nullptr;                     // device: (j,j') blocks
+    int *sb_j = nullptr, *sb_jp = nullptr, *sb_first = nullptr; // device: (j,j') blocks and their first slice
+    int *pairs = nullptr;                                      // device: int2 (a, b) observation pairs, block-major
+    int *slice_block = nullptr, *slice_p0 = nullptr, *slice_p1 = nullptr;   // device: <= SLICE pairs of one block each
+    long long n_pairs = 0;
     int *tile_obs = nullptr;                                   // device: warp-tile observation offsets (n_tiles + 1)
     int n_tiles = 0;
     int n_schur_blocks = 0;

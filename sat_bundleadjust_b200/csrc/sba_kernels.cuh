@@ -661,51 +661,90 @@ k_point_prep(ObsArrays o, const double* __restrict__ xp, const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// G3b: Schur complement blocks.  Work item = (camera j, camera j' >= j, chunk of camera j's
-// observations); for every track of the chunk also seen by j', acc += Z_a Z_b^T in registers
-// (rows ROW0..ROW0+NR-1); the diagonal items also accumulate Z_a q_i for the right-hand side.
-// No atomics: one partial per work item, summed in a fixed order by k_schur_finalize.
-// (A variant that walks over the partners j' inside the block to keep Z_a L1-resident was measured
-// slower on B200 -- 227 us vs 163 us at 5e5 observations -- because it serialises the partners.)
+// G3b: Schur complement blocks from explicit pair lists.
+// The structure of S is static over a solve, so the list of (observation a of camera j, observation b of camera j')
+// pairs that share a track is built once per problem (k_pair_count / k_pair_fill, ordered by block, then by camera
+// j's camera-major order: deterministic).  Work item = a slice of <= SLICE pairs of ONE block (j, j'): every lane
+// has a valid pair (no failed look-ups, no divergence), acc += Z_a Z_b^T stays in registers (rows
+// ROW0..ROW0+NR-1), diagonal blocks also accumulate Z_a q_i.  No atomics: one partial per slice, summed in a fixed
+// order by k_schur_finalize.
 // ------------------------------------------------------------------------------------------------
+constexpr int SLICE = 1024;
+
+// one warp per (chunk of camera j, partner j') item: number of tracks of the chunk that j' also sees
+__global__ void k_pair_count(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg,
+                             const int* __restrict__ chunk_end, const int* __restrict__ cm_pts,
+                             const int* __restrict__ obs_of, int N, const int* __restrict__ item_base,
+                             const int* __restrict__ item_chunk, int n_items, int* __restrict__ counts)
+{
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const int ch = item_chunk[item], j = chunk_cam[ch], jp = j + (item - item_base[ch]);
+    int cnt = 0;
+    if (jp == j) cnt = chunk_end[ch] - chunk_beg[ch];
+    else {
+        const int* row = obs_of + (size_t)jp * N;
+        for (int t = chunk_beg[ch] + lane; t < chunk_end[ch]; t += 32) cnt += row[cm_pts[t]] >= 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) counts[item] = cnt;
+}
+
+// same traversal, writes the pairs of the item at pairs[item_off[item] ...] in camera-major order
+__global__ void k_pair_fill(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg,
+                            const int* __restrict__ chunk_end, const int* __restrict__ cm_obs,
+                            const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N,
+                            const int* __restrict__ item_base, const int* __restrict__ item_chunk, int n_items,
+                            const int* __restrict__ item_off, int2* __restrict__ pairs)
+{
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const int ch = item_chunk[item], j = chunk_cam[ch], jp = j + (item - item_base[ch]);
+    const int* row = obs_of + (size_t)jp * N;
+    int out = item_off[item];
+    const int beg = chunk_beg[ch], end = chunk_end[ch];
+    for (int t0 = beg; t0 < end; t0 += 32) {
+        const int t = t0 + lane;
+        int a = -1, b = -1;
+        if (t < end) {
+            a = cm_obs[t];
+            b = (jp == j) ? a : row[cm_pts[t]];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, b >= 0);
+        if (b >= 0) pairs[out + __popc(m & ((1u << lane) - 1u))] = make_int2(a, b);
+        out += __popc(m);
+    }
+}
+
 template <int NC, int ROW0, int NR>
 __global__ void __launch_bounds__(TPB, 3)
-k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
-        const int* __restrict__ cm_obs, const int* __restrict__ cm_pts, const int* __restrict__ obs_of, int N, int M,
-        const double* __restrict__ Zin, const double* __restrict__ q, const int* __restrict__ item_base,
-        const int* __restrict__ item_chunk, double* __restrict__ schur_partials)
+k_schur(const int* __restrict__ slice_block, const int* __restrict__ slice_p0, const int* __restrict__ slice_p1,
+        const int* __restrict__ sb_j, const int* __restrict__ sb_jp, const int2* __restrict__ pairs,
+        const int* __restrict__ pts_ind, const double* __restrict__ Zin, const double* __restrict__ q,
+        double* __restrict__ schur_partials)
 {
     constexpr int NV = NR * NC + NR, NVALL = NC * NC + NC;
-    constexpr int EPT = CHUNK / TPB;                       // entries per thread
+    constexpr int EPT = SLICE / TPB;                       // pairs per thread
     // 16-byte vector loads of the Z records when every offset involved is even
     constexpr bool VEC = ((NC * 3) % 2 == 0) && ((NR * 3) % 2 == 0) && ((ROW0 * 3) % 2 == 0);
     __shared__ double sm[NV * (TPB / 32)];
-    const int item = blockIdx.x, ch = item_chunk[item];
-    const int j = chunk_cam[ch], jp = j + (item - item_base[ch]);
-    const bool diag = (jp == j);
-    const int beg = chunk_beg[ch], end = chunk_end[ch];
+    const int sl = blockIdx.x, blk = slice_block[sl];
+    const bool diag = sb_j[blk] == sb_jp[blk];
+    const int p0 = slice_p0[sl], p1 = slice_p1[sl];
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    // stage 1: all indices of this thread's entries, then all (camera j', track) look-ups: independent loads in flight
-    int ea[EPT], eb[EPT];
+    int2 pr[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int t = beg + threadIdx.x + e * TPB;
-        ea[e] = t < end ? cm_obs[t] : -1;
-        eb[e] = t < end ? cm_pts[t] : 0;                   // track index for now
+        const int p = p0 + threadIdx.x + e * TPB;
+        pr[e] = p < p1 ? pairs[p] : make_int2(-1, -1);
     }
-    if (!diag) {
-        const int* row = obs_of + (size_t)jp * N;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) eb[e] = ea[e] >= 0 ? row[eb[e]] : -1;
-    }
-    // stage 2: products
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int a = ea[e];
-        const int b = diag ? a : eb[e];
-        if (a < 0 || b < 0) continue;
+        const int a = pr[e].x, b = pr[e].y;
+        if (a < 0) continue;
         double A[NR * 3], B[NC * 3];
         const double* za = Zin + (size_t)a * NC * 3 + ROW0 * 3;
         const double* zb = Zin + (size_t)b * NC * 3;
@@ -729,7 +768,7 @@ k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, co
                 acc[r * NC + s] += A[3 * r] * B[3 * s] + A[3 * r + 1] * B[3 * s + 1] + A[3 * r + 2] * B[3 * s + 2];
         }
         if (diag) {
-            const int i = eb[e];
+            const int i = pts_ind[a];
             const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
 #pragma unroll
             for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;
@@ -739,18 +778,17 @@ k_schur(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, co
     if (threadIdx.x < NV) {
         const int k = threadIdx.x;
         const int pos = (k < NR * NC) ? (ROW0 * NC + k) : (NC * NC + ROW0 + (k - NR * NC));
-        schur_partials[(size_t)item * NVALL + pos] = tot;
+        schur_partials[(size_t)sl * NVALL + pos] = tot;
     }
 }
 
-// one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum over the chunks of camera j ;
-// rhs_j = -g_j + sum.  The partial of (chunk ch, partner j') lives at item_base[ch] + (j' - j).
-// One warp per value: lanes stride over the chunks, fixed-shape shuffle tree -> deterministic.
+// one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum over the block's slices ;
+// rhs_j = -g_j + sum.  One warp per value: lanes stride over the slices, fixed-shape shuffle tree -> deterministic.
 template <int NC>
 __global__ void __launch_bounds__(128)
-k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ first_chunk,
-                 const int* __restrict__ item_base, const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M,
-                 int n_cam_fix, const double* __restrict__ camsys_local, const double* __restrict__ sinv,
+k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ sb_first,
+                 const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M, int n_cam_fix,
+                 const double* __restrict__ camsys_local, const double* __restrict__ sinv,
                  const double* __restrict__ scal, int add_diag, double* __restrict__ S)
 {
     constexpr int NVALL = NC * NC + NC;
@@ -758,10 +796,10 @@ k_schur_finalize(const double* __restrict__ schur_partials, const int* __restric
     const int blk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = sb_j[blk], jp = sb_jp[blk];
     const int ns = M * NC;
-    const int c0 = first_chunk[j], c1 = first_chunk[j + 1];
+    const int s0 = sb_first[blk], s1 = sb_first[blk + 1];
     for (int k = warp; k < NVALL; k += 4) {
         double s = 0.0;
-        for (int ch = c0 + lane; ch < c1; ch += 32) s += schur_partials[(size_t)(item_base[ch] + (jp - j)) * NVALL + k];
+        for (int sl = s0 + lane; sl < s1; sl += 32) s += schur_partials[(size_t)sl * NVALL + k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane != 0) continue;
