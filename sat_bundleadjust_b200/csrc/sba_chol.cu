@@ -105,13 +105,12 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
 {
     extern __shared__ double sh[];
     const int ld = n | 1;
-    double* W = sh;
-    double* Lf = sh + (size_t)(n + 1) * ld;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    for (int e = tid; e < n * n; e += CHOL_THREADS) {
-        const int j = e / n, i = e - j * n;
-        if (i >= j) W[(size_t)i * ld + j] = Ag[e];
-    }
+    double* W = sh;                                  // running Schur complement, (n+1) x ld, row n = rhs
+    double* Lf = sh + (size_t)(n + 1) * ld;          // factor, same shape; row n = y = L^-1 rhs
+    __shared__ double s_ip[CHOL_RL_MAX_N + 1];       // 1 / L[k,k]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    for (int j = warp; j < n; j += CHOL_THREADS / 32)
+        for (int i = j + lane; i < n; i += 32) W[(size_t)i * ld + j] = Ag[(size_t)j * n + i];     // column-major source
     for (int j = tid; j < n; j += CHOL_THREADS) W[(size_t)n * ld + j] = b[j];
     __syncthreads();
     int failed = 0;
@@ -119,6 +118,7 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         const double dkk = W[(size_t)k * ld + k];
         if (!(dkk > 0.0) || !isfinite(dkk)) { failed = k + 1; break; }      // uniform: every thread reads the same value
         const double inv = fast_rcp(dkk);
+        const double ip = fast_rsqrt(dkk);
         // column k of the running complement for this thread's rows and columns (read-only during this step)
         double ci[NT], cj[NT];
 #pragma unroll
@@ -127,10 +127,9 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
             ci[a] = i <= n ? W[(size_t)i * ld + k] * inv : 0.0;
             cj[a] = j < n ? W[(size_t)j * ld + k] : 0.0;
         }
-        if (tx == 0) {      // factor column k (rows k..n) from the same, still unmodified, column
-            const double ip = fast_rsqrt(dkk);
-            for (int i = k + ty; i <= n; i += 16) Lf[(size_t)i * ld + k] = W[(size_t)i * ld + k] * ip;
-        }
+        // factor column k (rows k..n), one element per thread, from the same still unmodified column
+        if (k + tid <= n) Lf[(size_t)(k + tid) * ld + k] = W[(size_t)(k + tid) * ld + k] * ip;
+        if (tid == 0) s_ip[k] = ip;
         // all loads of the tile, then all FMAs, then all stores: shared-memory stores would otherwise serialise
         // the loop (the compiler must assume they alias the next loads)
         double w[NT][NT];
@@ -158,20 +157,32 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         if (tid == 0) *fail = (double)failed;
         return;
     }
-    double* y = Lf + (size_t)n * ld;
-    for (int k = n - 1; k >= 0; --k) {
-        const double* rk = Lf + (size_t)k * ld;
-        if (tid == 0) y[k] = y[k] / rk[k];
-        __syncthreads();
-        const double xk = y[k];
-        for (int i = tid; i < k; i += CHOL_THREADS) y[i] -= rk[i] * xk;
-        __syncthreads();
+    // backward substitution L^T x = y by ONE warp, y in registers (lane l holds y[l + 32 m]), no block barriers
+    if (warp == 0) {
+        constexpr int NY = (CHOL_RL_MAX_N + 31) / 32;
+        double y[NY];
+#pragma unroll
+        for (int m = 0; m < NY; ++m) y[m] = (lane + 32 * m < n) ? Lf[(size_t)n * ld + lane + 32 * m] : 0.0;
+        for (int k = n - 1; k >= 0; --k) {
+            double yk = 0.0;
+#pragma unroll
+            for (int m = 0; m < NY; ++m)
+                if ((k >> 5) == m) yk = y[m];
+            const double xk = __shfl_sync(0xffffffffu, yk, k & 31) * s_ip[k];
+            const double* rk = Lf + (size_t)k * ld;
+#pragma unroll
+            for (int m = 0; m < NY; ++m) {
+                const int i = lane + 32 * m;
+                if (i < k) y[m] -= rk[i] * xk;
+                else if (i == k) y[m] = xk;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NY; ++m)
+            if (lane + 32 * m < n) x[lane + 32 * m] = y[m];
     }
-    for (int i = tid; i < n; i += CHOL_THREADS) x[i] = y[i];
-    for (int e = tid; e < n * n; e += CHOL_THREADS) {
-        const int j = e / n, i = e - j * n;
-        Ag[e] = (i >= j) ? Lf[(size_t)i * ld + j] : 0.0;
-    }
+    for (int j = warp; j < n; j += CHOL_THREADS / 32)
+        for (int i = lane; i < n; i += 32) Ag[(size_t)j * n + i] = (i >= j) ? Lf[(size_t)i * ld + j] : 0.0;
     if (tid == 0) *fail = 0.0;
 }
 
