@@ -99,37 +99,41 @@ constexpr int CHOL_RL_MAX_N = 100;     // two (n+1) x (n|1) buffers must fit in 
 // triangle (16 x 16 thread tile, rows strided by 16 over ty, columns over tx); column k of W is only read in step k,
 // so nothing it needs is overwritten.  The threads with tx == 0 also emit L[i,k] = W[i,k] / sqrt(W[k,k]).
 // The right-hand side is row n of W, so row n of Lf ends up as y = L^-1 rhs.
-template <int NT>     // NT x NT register tile per thread: rows/columns k+1+t+16a, a < NT  (16*NT >= n+1)
-__global__ void __launch_bounds__(CHOL_THREADS)
+constexpr int CHOL_SMALL_THREADS = 1024;     // 32 x 32 thread tile: 8 warps per scheduler hide the FP64 / LDS latencies
+
+template <int NT>     // NT x NT register tile per thread: rows/columns k+1+t+32a, a < NT  (32*NT >= n+1)
+__global__ void __launch_bounds__(CHOL_SMALL_THREADS)
 k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
 {
     extern __shared__ double sh[];
     const int ld = n | 1;
     double* W = sh;                                  // running Schur complement, (n+1) x ld, row n = rhs
-    double* Lf = sh + (size_t)(n + 1) * ld;          // factor, same shape; row n = y = L^-1 rhs
+    double* Lf = sh + (n + 1) * ld;                  // factor, same shape; row n = y = L^-1 rhs
     __shared__ double s_ip[CHOL_RL_MAX_N + 1];       // 1 / L[k,k]
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
-    for (int j = warp; j < n; j += CHOL_THREADS / 32)
-        for (int i = j + lane; i < n; i += 32) W[(size_t)i * ld + j] = Ag[(size_t)j * n + i];     // column-major source
-    for (int j = tid; j < n; j += CHOL_THREADS) W[(size_t)n * ld + j] = b[j];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    for (int j = ty; j < n; j += 32)
+        for (int i = j + tx; i < n; i += 32) W[i * ld + j] = Ag[(size_t)j * n + i];     // column-major source
+    for (int j = tid; j < n; j += CHOL_SMALL_THREADS) W[n * ld + j] = b[j];
     __syncthreads();
     int failed = 0;
     for (int k = 0; k < n; ++k) {
-        const double dkk = W[(size_t)k * ld + k];
+        const double dkk = W[k * ld + k];
         if (!(dkk > 0.0) || !isfinite(dkk)) { failed = k + 1; break; }      // uniform: every thread reads the same value
         const double inv = fast_rcp(dkk);
-        const double ip = fast_rsqrt(dkk);
         // column k of the running complement for this thread's rows and columns (read-only during this step)
         double ci[NT], cj[NT];
 #pragma unroll
         for (int a = 0; a < NT; ++a) {
-            const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * a;
-            ci[a] = i <= n ? W[(size_t)i * ld + k] * inv : 0.0;
-            cj[a] = j < n ? W[(size_t)j * ld + k] : 0.0;
+            const int i = k + 1 + ty + 32 * a, j = k + 1 + tx + 32 * a;
+            ci[a] = i <= n ? W[i * ld + k] * inv : 0.0;
+            cj[a] = j < n ? W[j * ld + k] : 0.0;
         }
-        // factor column k (rows k..n), one element per thread, from the same still unmodified column
-        if (k + tid <= n) Lf[(size_t)(k + tid) * ld + k] = W[(size_t)(k + tid) * ld + k] * ip;
-        if (tid == 0) s_ip[k] = ip;
+        // factor column k (rows k..n), one element per thread of the first warps, from the same unmodified column
+        if (k + tid <= n) {
+            const double ip = fast_rsqrt(dkk);
+            Lf[(k + tid) * ld + k] = W[(k + tid) * ld + k] * ip;
+            if (tid == 0) s_ip[k] = ip;
+        }
         // all loads of the tile, then all FMAs, then all stores: shared-memory stores would otherwise serialise
         // the loop (the compiler must assume they alias the next loads)
         double w[NT][NT];
@@ -137,8 +141,8 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         for (int a = 0; a < NT; ++a)
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
-                const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * c;
-                w[a][c] = (i <= n && j <= i && j < n) ? W[(size_t)i * ld + j] : 0.0;
+                const int i = k + 1 + ty + 32 * a, j = k + 1 + tx + 32 * c;
+                w[a][c] = (i <= n && j <= i && j < n) ? W[i * ld + j] : 0.0;
             }
 #pragma unroll
         for (int a = 0; a < NT; ++a)
@@ -148,8 +152,8 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         for (int a = 0; a < NT; ++a)
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
-                const int i = k + 1 + ty + 16 * a, j = k + 1 + tx + 16 * c;
-                if (i <= n && j <= i && j < n) W[(size_t)i * ld + j] = w[a][c];
+                const int i = k + 1 + ty + 32 * a, j = k + 1 + tx + 32 * c;
+                if (i <= n && j <= i && j < n) W[i * ld + j] = w[a][c];
             }
         __syncthreads();
     }
@@ -158,31 +162,28 @@ k_cholesky_solve_small(double* Ag, double* b, double* x, int n, double* fail)
         return;
     }
     // backward substitution L^T x = y by ONE warp, y in registers (lane l holds y[l + 32 m]), no block barriers
-    if (warp == 0) {
-        constexpr int NY = (CHOL_RL_MAX_N + 31) / 32;
-        double y[NY];
-#pragma unroll
-        for (int m = 0; m < NY; ++m) y[m] = (lane + 32 * m < n) ? Lf[(size_t)n * ld + lane + 32 * m] : 0.0;
+    if (ty == 0) {
+        double y0 = tx < n ? Lf[n * ld + tx] : 0.0;
+        double y1 = tx + 32 < n ? Lf[n * ld + tx + 32] : 0.0;
+        double y2 = tx + 64 < n ? Lf[n * ld + tx + 64] : 0.0;
+        double y3 = tx + 96 < n ? Lf[n * ld + tx + 96] : 0.0;
         for (int k = n - 1; k >= 0; --k) {
-            double yk = 0.0;
-#pragma unroll
-            for (int m = 0; m < NY; ++m)
-                if ((k >> 5) == m) yk = y[m];
+            const int m = k >> 5;
+            const double yk = m == 0 ? y0 : (m == 1 ? y1 : (m == 2 ? y2 : y3));
             const double xk = __shfl_sync(0xffffffffu, yk, k & 31) * s_ip[k];
-            const double* rk = Lf + (size_t)k * ld;
-#pragma unroll
-            for (int m = 0; m < NY; ++m) {
-                const int i = lane + 32 * m;
-                if (i < k) y[m] -= rk[i] * xk;
-                else if (i == k) y[m] = xk;
-            }
+            const double* rk = Lf + k * ld;
+            if (tx < k) y0 -= rk[tx] * xk; else if (tx == k) y0 = xk;
+            if (k >= 32) { if (tx + 32 < k) y1 -= rk[tx + 32] * xk; else if (tx + 32 == k) y1 = xk; }
+            if (k >= 64) { if (tx + 64 < k) y2 -= rk[tx + 64] * xk; else if (tx + 64 == k) y2 = xk; }
+            if (k >= 96) { if (tx + 96 < k) y3 -= rk[tx + 96] * xk; else if (tx + 96 == k) y3 = xk; }
         }
-#pragma unroll
-        for (int m = 0; m < NY; ++m)
-            if (lane + 32 * m < n) x[lane + 32 * m] = y[m];
+        if (tx < n) x[tx] = y0;
+        if (tx + 32 < n) x[tx + 32] = y1;
+        if (tx + 64 < n) x[tx + 64] = y2;
+        if (tx + 96 < n) x[tx + 96] = y3;
     }
-    for (int j = warp; j < n; j += CHOL_THREADS / 32)
-        for (int i = lane; i < n; i += 32) Ag[(size_t)j * n + i] = (i >= j) ? Lf[(size_t)i * ld + j] : 0.0;
+    for (int j = ty; j < n; j += 32)
+        for (int i = tx; i < n; i += 32) Ag[(size_t)j * n + i] = (i >= j) ? Lf[i * ld + j] : 0.0;
     if (tid == 0) *fail = 0.0;
 }
 
@@ -195,14 +196,14 @@ int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, do
         static bool attr_small = false;
         const int max_bytes = 2 * (CHOL_RL_MAX_N + 1) * (CHOL_RL_MAX_N | 1) * (int)sizeof(double);
         if (!attr_small) {
+            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
             SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
             SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
-            SBA_CUDA(cudaFuncSetAttribute(k_cholesky_solve_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes));
             attr_small = true;
         }
-        if (n + 1 <= 32) k_cholesky_solve_small<2><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
-        else if (n + 1 <= 64) k_cholesky_solve_small<4><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
-        else k_cholesky_solve_small<7><<<1, CHOL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        if (n + 1 <= 32) k_cholesky_solve_small<1><<<1, CHOL_SMALL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        else if (n + 1 <= 64) k_cholesky_solve_small<2><<<1, CHOL_SMALL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
+        else k_cholesky_solve_small<4><<<1, CHOL_SMALL_THREADS, bytes, stream>>>(A_dev, b_dev, x_dev, n, fail_dev);
     } else if (n <= CHOL_SMEM_MAX_N) {
         const size_t bytes = ((size_t)(n + 1) * (n | 1) + n) * sizeof(double);
         static bool attr_set = false;
