@@ -229,6 +229,12 @@ def run_b200_arm(args):
             t = torch.as_tensor(sdist._CudaView(ptr, count), device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         prob.set_allreduce(hook)
+        if os.environ.get("SBA_COMM", "peer") == "peer":
+            def gather_obj(obj):
+                out = [None] * world
+                dist.all_gather_object(out, obj)
+                return out
+            prob.connect_peers(gather_obj)
     xl0 = sdist.local_vars(x0, ncv, ranges[rank]) if world > 1 else x0
     x_dev = torch.from_numpy(xl0).cuda()
     out_dev = torch.empty_like(x_dev)
@@ -324,6 +330,7 @@ def run_b200_arm(args):
             "config": {"workload": WORKLOADS[args.workload][5], "n_obs": Kobs, "n_tracks": int(p.n_pts), "n_cam": int(M),
                        "n_params_per_cam": int(c), "loss": LS["loss"], "tracks_per_gpu": int(N_loc),
                        "parallelism": "tracks sharded over %d GPU(s), cameras replicated" % world,
+                       "exchange": ("none" if world == 1 else os.environ.get("SBA_COMM", "peer") + " (per iteration: [U|g_c], [S|rhs], 5 scalar groups)"),
                        "l2": "256 MiB scratch overwritten between timed iterations (outside the event pairs)"},
             "lm_iters_per_s": K / (iter_ms * 1e-3),
             "jacobian_obs_per_s": Kobs / (jac_ms_mean * 1e-3),
@@ -344,6 +351,8 @@ def run_b200_arm(args):
                                               "on the full workload, 1 of %d host cores (the path is single-threaded)"
                                               % (os.cpu_count() or 1)}
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()      # peers may still be reading this rank's exchange buffer
     prob.close()
     if world > 1:
         dist.barrier()

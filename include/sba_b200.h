@@ -106,6 +106,12 @@ int sba_version(void);
 int sba_problem_create(sba_problem **out, const sba_problem_desc *desc, void *stream);
 int sba_problem_destroy(sba_problem *p);
 int sba_problem_set_allreduce(sba_problem *p, sba_allreduce_fn fn, void *user);
+/* Multi-GPU exchange without the hook: a device-side one-shot all-reduce over NVLink peer memory.  Every rank calls
+ * sba_comm_export (writes the 64-byte CUDA IPC handle of its symmetric buffer), the handles are gathered by any means
+ * (e.g. torch.distributed.all_gather_object), and every rank calls sba_comm_import with all of them in rank order.
+ * When imported, the solver uses it instead of the hook.  The problems of all ranks must be destroyed collectively. */
+int sba_comm_export(sba_problem *p, void *handle_out_64_bytes);
+int sba_comm_import(sba_problem *p, const void *handles_world_x_64_bytes);
 /* number of variables n = n_cam * n_params + 3 * n_pts */
 int64_t sba_problem_num_vars(const sba_problem *p);
 

@@ -64,7 +64,7 @@ EXPORTED_SYMBOLS = [
     "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_solve",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
-    "sba_rpcfit_weighted_lsq",
+    "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import",
 ]
 
 _lib = None
@@ -84,6 +84,8 @@ def load():
     lib.sba_problem_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ProblemDesc), vp]
     lib.sba_problem_destroy.argtypes = [vp]
     lib.sba_problem_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    lib.sba_comm_export.argtypes = [vp, ctypes.c_char_p]
+    lib.sba_comm_import.argtypes = [vp, ctypes.c_char_p]
     lib.sba_problem_num_vars.argtypes = [vp]
     lib.sba_problem_num_vars.restype = ctypes.c_int64
     lib.sba_residuals.argtypes = [vp, c_double_p, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p]

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "sba_comm.cuh"
 #include "sba_kernels.cuh"
 #include "sba_tr2d.h"
 
@@ -185,6 +186,8 @@ static int run_residual(sba_problem* p, const double* x, const double* camrec, i
     return check_launch(p);
 }
 
+static int allreduce_any(sba_problem* p, double* buf, long long count);
+
 // fused residual + analytic Jacobian + robust weighting + block assembly at x (camrec must be prepared).
 // The track-major half (V, g_p) runs on the solver's stream, the camera-major half (U, g_c) on a side stream.
 static int run_assemble(sba_problem* p, const double* x, const double* camrec, int loss, double f_scale)
@@ -219,23 +222,39 @@ static int run_assemble(sba_problem* p, const double* x, const double* camrec, i
     if (p->world > 1) {
         const size_t cnt = (size_t)p->M * p->nc * p->nc + (size_t)p->M * p->nc;
         SBA_CUDA(cudaMemcpyAsync(p->camsys, p->camsys_local, cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-        if (p->allreduce(p->allreduce_user, p->camsys, (int64_t)cnt) != 0) {
-            set_error("allreduce callback failed");
-            return SBA_E_INVALID;
-        }
+        SBA_TRY(allreduce_any(p, p->camsys, (long long)cnt));
     }
     return SBA_OK;
 }
 
-static int allreduce_scal(sba_problem* p, int first, int count)
+// SUM all-reduce of `count` doubles at device pointer `buf`, in place, on the solver's stream: peer memory when the
+// symmetric buffers are mapped (sba_comm_import), else the caller's hook (NCCL through torch.distributed)
+static int allreduce_any(sba_problem* p, double* buf, long long count)
 {
     if (p->world <= 1) return SBA_OK;
-    if (p->allreduce(p->allreduce_user, p->scal + first, count) != 0) {
+    if (p->comm_ready && count <= p->comm_cap) {
+        CommView c;
+        for (int r = 0; r < COMM_MAX_RANKS; ++r) { c.data[r] = nullptr; c.flag[r] = nullptr; }
+        for (int r = 0; r < p->world; ++r) {
+            c.data[r] = (double*)p->comm_peer[r];
+            c.flag[r] = (unsigned long long*)((double*)p->comm_peer[r] + 2 * p->comm_cap);
+        }
+        c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
+        const unsigned long long seq = ++p->comm_seq;
+        const int grid = grid_for(count, 256, 16);
+        k_comm_push<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->counters + 8);
+        SBA_TRY(check_launch(p));
+        k_comm_pull<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->scal);
+        return check_launch(p);
+    }
+    if (!p->allreduce || p->allreduce(p->allreduce_user, buf, count) != 0) {
         set_error("allreduce callback failed");
         return SBA_E_INVALID;
     }
     return SBA_OK;
 }
+
+static int allreduce_scal(sba_problem* p, int first, int count) { return allreduce_any(p, p->scal + first, count); }
 
 static int fetch_scal(sba_problem* p)
 {
@@ -322,12 +341,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
         SBA_TRY(check_launch(p));
 #undef FIN_ARGS
     }
-    if (p->world > 1) {
-        if (p->allreduce(p->allreduce_user, p->S, (int64_t)ns * ns + ns) != 0) {
-            set_error("allreduce callback failed");
-            return SBA_E_INVALID;
-        }
-    }
+    SBA_TRY(allreduce_any(p, p->S, (long long)ns * ns + ns));
     tm.end();
     tm.begin(SBA_PH_CHOLESKY);
     SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->chol_work,
@@ -441,6 +455,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         SBA_TRY(enqueue_iteration(-1.0));
         SBA_TRY(fetch_scal(p));
         const double* h = p->h_scal;
+        if (h[SC_COMM_FAIL] != 0.0) { set_error("peer-memory all-reduce timed out (a rank is missing)"); return SBA_E_CUDA; }
         for (int attempt = 0; h[SC_CHOL_FAIL] != 0.0 || !std::isfinite(h[SC_GGN]) || !std::isfinite(h[SC_B22]); ++attempt) {
             if (attempt >= 30) { set_error("reduced camera system could not be factorised"); return SBA_E_NUMERIC; }
             // re-damp: J_h has unit column norms, so reg is relative to 1
@@ -534,6 +549,9 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     if (!p) return SBA_OK;
     cudaSetDevice(p->device);
     for (void* c : p->arena_chunks) cudaFree(c);
+    for (int r = 0; r < p->world; ++r)
+        if (p->comm_ready && r != p->rank && p->comm_peer[r]) cudaIpcCloseMemHandle(p->comm_peer[r]);
+    if (p->comm_buf) cudaFree(p->comm_buf);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -766,6 +784,40 @@ extern "C" int sba_problem_set_allreduce(sba_problem* p, sba_allreduce_fn fn, vo
 
 extern "C" int64_t sba_problem_num_vars(const sba_problem* p) { return p ? p->n : -1; }
 
+// Multi-GPU exchange over peer memory: every rank exports the IPC handle of its symmetric buffer ...
+extern "C" int sba_comm_export(sba_problem* p, void* handle_out)
+{
+    if (!p || !handle_out) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    if (!p->comm_buf) {
+        const long long ns = (long long)p->M * p->nc;
+        p->comm_cap = std::max<long long>(ns * ns + ns, std::max<long long>(ns * p->nc + ns, SC_COUNT));
+        const size_t bytes = (size_t)(2 * p->comm_cap) * sizeof(double) + 2 * COMM_MAX_RANKS * sizeof(unsigned long long);
+        SBA_CUDA(cudaMalloc(&p->comm_buf, bytes));
+        SBA_CUDA(cudaMemset(p->comm_buf, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    SBA_CUDA(cudaIpcGetMemHandle(&h, p->comm_buf));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return SBA_OK;
+}
+
+// ... and maps the buffers of all ranks (handles: world x 64 bytes, in rank order; its own entry is skipped)
+extern "C" int sba_comm_import(sba_problem* p, const void* handles)
+{
+    if (!p || !handles || !p->comm_buf) { set_error("sba_comm_export must be called first"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) { p->comm_peer[r] = p->comm_buf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        SBA_CUDA(cudaIpcOpenMemHandle(&p->comm_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p->comm_ready = true;
+    p->comm_seq = 0;
+    return SBA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI: evaluation entry points
 // ------------------------------------------------------------------------------------------------
@@ -829,7 +881,7 @@ extern "C" int sba_solve_device(sba_problem* p, const double* x0_dev, const sba_
                                 double* r_dev, sba_solve_info* info)
 {
     if (!p || !x0_dev || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
-    if (p->world > 1 && !p->allreduce) { set_error("world_size > 1 needs sba_problem_set_allreduce"); return SBA_E_INVALID; }
+    if (p->world > 1 && !p->allreduce && !p->comm_ready) { set_error("world_size > 1 needs sba_comm_import or sba_problem_set_allreduce"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     SBA_CUDA(cudaMemcpyAsync(p->x, x0_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     SBA_TRY(solve_on_device(p, opts, info));

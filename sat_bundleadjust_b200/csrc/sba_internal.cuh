@@ -61,6 +61,7 @@ enum Scal {
     SC_PRED,              // predicted reduction of the 2-D model
     SC_STEPH,             // |step_h| (scaled space)
     SC_STEPN,             // |step|   (x space)
+    SC_COMM_FAIL,         // a peer did not arrive within the time-out of the peer-memory all-reduce
     SC_COUNT
 };
 
@@ -124,6 +125,12 @@ struct sba_problem {
     // measurement: event ring for per-phase timing, scratch for L2 flushes
     std::vector<cudaEvent_t> ev_pool;
     int ev_used = 0;
+    // peer-memory all-reduce (multi-GPU): own symmetric buffer + mapped peer buffers
+    void* comm_buf = nullptr;
+    void* comm_peer[16] = {nullptr};
+    long long comm_cap = 0;                  // doubles per parity
+    unsigned long long comm_seq = 0;
+    bool comm_ready = false;
     std::vector<void*> arena_chunks;         // device slabs owned by this problem
     char* arena_ptr = nullptr;
     size_t arena_left = 0;

@@ -12,6 +12,8 @@ rank then factors the same reduced camera system redundantly, so all ranks take 
 Plumbing only: torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests) moves the
 bytes; the arithmetic stays in libsba_b200.so.
 """
+import os
+
 import numpy as np
 
 
@@ -74,12 +76,20 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         t = torch.as_tensor(_CudaView(ptr, count), device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
+    def gather_obj(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj, group=group)
+        return out
+
     with DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank]) as prob:
-        prob.set_allreduce(hook)
+        prob.set_allreduce(hook)                       # NCCL fall-back for exchanges that do not fit the peer buffer
+        if os.environ.get("SBA_COMM", "peer") == "peer":
+            prob.connect_peers(gather_obj)
         xl0 = local_vars(x0, ncv, ranges[rank])
         r0, _ = prob.residuals(xl0)
         xl, rl, info = prob.solve(xl0, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"],
                                   max_nfev=cfg["max_iter"])
+        dist.barrier(group=group)                      # peers keep reading each other's buffers until everybody is done
     # gather the pieces (variable-length -> pad to the longest shard)
     def gather(v):
         size = torch.tensor([v.size], dtype=torch.int64, device="cuda")

@@ -166,6 +166,17 @@ class DeviceProblem:
         check(self.lib.sba_assemble_device(self.handle, ctypes.c_void_p(x_ptr), LOSS_IDS[loss], f_scale, ctypes.byref(ms)))
         return ms.value
 
+    def connect_peers(self, all_gather_object):
+        """
+        Map the symmetric exchange buffers of all ranks (CUDA IPC over NVLink) so that the per-iteration all-reduces run
+        as device-side one-shot kernels.  `all_gather_object(obj) -> list` must return every rank's object in rank order
+        (e.g. a wrapper of torch.distributed.all_gather_object).
+        """
+        mine = ctypes.create_string_buffer(64)
+        check(self.lib.sba_comm_export(self.handle, mine))
+        handles = all_gather_object(bytes(mine.raw))
+        check(self.lib.sba_comm_import(self.handle, b"".join(handles)))
+
     def set_allreduce(self, fn):
         """fn(device_ptr: int, count: int) must SUM-reduce `count` doubles in place across ranks."""
         def trampoline(_user, ptr, count):
