@@ -361,6 +361,11 @@ def run_b200_arm(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that libraries print there (e.g. NCCL's version banner)
+    # is sent to stderr by swapping the file descriptors for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -370,9 +375,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_b200_arm(args)
+    rc = run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":
