@@ -435,10 +435,9 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         k_build_t2<<<elem_grid, 256, 0, p->stream>>>(p->g, p->sinv, p->delta, p->t1, p->t2, p->n, ns, p->rank == 0,
                                                      p->red_partials, p->counters + 5, p->scal);
         SBA_TRY(check_launch(p));
-        SBA_TRY(allreduce_scal(p, SC_WW, 5));
         Slots sb; sb.s[0] = SC_B11; sb.s[1] = SC_B12; sb.s[2] = SC_B22;
         SBA_TRY(run_jvp(p, loss, fs, 2, sb));
-        SBA_TRY(allreduce_scal(p, SC_B11, 3));
+        SBA_TRY(allreduce_scal(p, SC_WW, 8));      // [ww wg t11 t12 t22 | b11 b12 b22] in one exchange
         tm.end();
         return enqueue_trial(-1.0);
     };
