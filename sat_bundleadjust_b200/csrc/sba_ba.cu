@@ -317,7 +317,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
         switch (p->nc) {
         case 3: k_schur<3, 0, 3><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 5: k_schur<5, 0, 5><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
-        case 6: k_schur6_split<<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
+        case 6: k_schur<6, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 8: k_schur<8, 0, 8><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS); break;
         case 11:
             k_schur<11, 0, 6><<<p->n_schur_items, TPB, 0, p->stream>>>(SCHUR_ARGS);

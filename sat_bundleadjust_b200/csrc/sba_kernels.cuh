@@ -782,83 +782,6 @@ k_schur(const int* __restrict__ slice_block, const int* __restrict__ slice_p0, c
     }
 }
 
-// Variant for c = 6 (rotation + translation, the common case): a pair is shared by two adjacent lanes, each owning
-// three of the six rows of the 6 x 6 block.  Half the accumulators per thread (21 instead of 42 doubles) doubles the
-// number of resident warps, which is what this latency-bound gather needs; the Z_b record is read by both lanes at
-// the same address (one request), Z_a is split between them.
-__global__ void __launch_bounds__(TPB, 5)
-k_schur6_split(const int* __restrict__ slice_block, const int* __restrict__ slice_p0, const int* __restrict__ slice_p1,
-               const int* __restrict__ sb_j, const int* __restrict__ sb_jp, const int2* __restrict__ pairs,
-               const int* __restrict__ pts_ind, const double* __restrict__ Zin, const double* __restrict__ q,
-               double* __restrict__ schur_partials)
-{
-    constexpr int NC = 6, NR = 3, NV = NR * NC + NR, NVALL = NC * NC + NC;
-    constexpr int PPT = 2 * SLICE / TPB;                   // pairs per lane pair
-    __shared__ double sm[2 * NV * (TPB / 32)];
-    const int sl = blockIdx.x, blk = slice_block[sl];
-    const bool diag = sb_j[blk] == sb_jp[blk];
-    const int p0 = slice_p0[sl], p1 = slice_p1[sl];
-    const int half = threadIdx.x & 1, pt = threadIdx.x >> 1;
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    constexpr int BATCH = 8;
-    for (int e0 = 0; e0 < PPT; e0 += BATCH) {
-        int2 pr[BATCH];
-#pragma unroll
-        for (int e = 0; e < BATCH; ++e) {
-            const int p = p0 + pt + (e0 + e) * (TPB / 2);
-            pr[e] = p < p1 ? pairs[p] : make_int2(-1, -1);
-        }
-#pragma unroll
-        for (int e = 0; e < BATCH; ++e) {
-            const int a = pr[e].x, b = pr[e].y;
-            if (a < 0) continue;
-            const double* za = Zin + (size_t)a * 18 + half * 9;
-            const double2* zb2 = reinterpret_cast<const double2*>(Zin + (size_t)b * 18);
-            double A[9], B[18];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) A[k] = za[k];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { const double2 v = zb2[k]; B[2 * k] = v.x; B[2 * k + 1] = v.y; }
-#pragma unroll
-            for (int s = 0; s < NC; ++s) {
-#pragma unroll
-                for (int r = 0; r < NR; ++r)
-                    acc[r * NC + s] += A[3 * r] * B[3 * s] + A[3 * r + 1] * B[3 * s + 1] + A[3 * r + 2] * B[3 * s + 2];
-            }
-            if (diag) {
-                const int i = pts_ind[a];
-                const double q0 = q[3 * (size_t)i], q1 = q[3 * (size_t)i + 1], q2 = q[3 * (size_t)i + 2];
-#pragma unroll
-                for (int r = 0; r < NR; ++r) acc[NR * NC + r] += A[3 * r] * q0 + A[3 * r + 1] * q1 + A[3 * r + 2] * q2;
-            }
-        }
-    }
-    // reduce over the lanes of equal parity (xor 16, 8, 4, 2), then over the warps
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double x = acc[k];
-#pragma unroll
-        for (int o = 16; o > 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        acc[k] = x;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane < 2) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) sm[(warp * 2 + lane) * NV + k] = acc[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * NV) {
-        const int h = threadIdx.x / NV, k = threadIdx.x % NV;
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < TPB / 32; ++w) s += sm[(w * 2 + h) * NV + k];
-        const int pos = (k < NR * NC) ? (h * 3 * NC + k) : (NC * NC + h * 3 + (k - NR * NC));
-        schur_partials[(size_t)sl * NVALL + pos] = s;
-    }
-}
-
 // one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum over the block's slices ;
 // rhs_j = -g_j + sum.  One warp per value: lanes stride over the slices, fixed-shape shuffle tree -> deterministic.
 template <int NC>
