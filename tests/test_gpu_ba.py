@@ -236,3 +236,38 @@ def test_cholesky_solve(built):
     info = ctypes.c_int32(0)
     _lib.check(lib.sba_cholesky_solve(_lib.dptr(S), _lib.dptr(np.ones(2)), 2, ctypes.byref(info)))
     assert info.value == 2
+
+
+def test_long_tracks_and_many_cameras(built):
+    """40 cameras, tracks seen by ~36 of them: exercises the long-track (> 32 observations) paths of the warp-tile
+    kernels, a 240 x 240 reduced camera system (global-memory Cholesky variant) and the pair lists of 820 blocks."""
+    from scipy.optimize._lsq.common import scale_for_robust_loss_function
+    from scipy.optimize._lsq.least_squares import construct_loss_function
+    sc = synth.make_scene(n_cam=40, n_tracks=60, p_vis=0.9, cam_model="perspective", seed=8)
+    p = synth.scene_to_params(sc, ["R", "T"], n_cam_fix=1)
+    lengths = np.bincount(p.pts_ind)
+    assert lengths.max() > 32 and lengths.min() >= 2
+    x0 = initial_vars(p)
+    with DeviceProblem(p) as prob:
+        r, cost = prob.residuals(x0, "soft_l1", 1.0)
+        Jc, Jp = prob.jacobian_blocks(x0)
+        U, V, g = prob.normal_blocks(x0, "soft_l1", 1.0)
+        x, rr, info = prob.solve(x0, loss="soft_l1", ftol=1e-12, xtol=0.0, max_nfev=300)
+    f = ba_oracle.residuals(x0.copy(), p)
+    assert np.abs(r - f).max() < RES_TOL_PX
+    J = util.dense_jacobian_from_blocks(p, Jc, Jp)
+    rho = construct_loss_function(f.size, "soft_l1", 1.0)(f.copy())
+    Js, fs = scale_for_robust_loss_function(J.copy(), f.copy(), rho)
+    H, gd = Js.T @ Js, Js.T @ fs
+    c, off = p.n_params, p.n_cam * p.n_params
+    Ud = np.array([H[j * c:(j + 1) * c, j * c:(j + 1) * c] for j in range(p.n_cam)])
+    idx = ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))
+    Vd = np.array([[H[off + 3 * i + a, off + 3 * i + b] for a, b in idx] for i in range(p.n_pts)])
+    assert np.abs(U - Ud).max() <= 1e-8 * np.abs(Ud).max()
+    assert np.abs(V - Vd).max() <= 1e-8 * np.abs(Vd).max()
+    assert np.abs(g - gd).max() <= 1e-8 * np.abs(gd).max()
+    # the solve reaches a stationary point of the oracle's cost function
+    cost_gpu = ba_oracle.robust_cost(ba_oracle.residuals(x.copy(), p), "soft_l1", 1.0)
+    assert abs(cost_gpu - info["cost"]) <= 1e-9 * cost_gpu and cost_gpu < 0.05 * info["cost_init"]
+    xc, cc, _ = ba_oracle.solve_converged(p, "soft_l1", 1.0, x_start=x, max_nfev=30)
+    assert abs(cost_gpu - cc) <= 1e-6 * cc, (cost_gpu, cc)

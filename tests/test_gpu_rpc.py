@@ -150,3 +150,33 @@ def test_rpc_model_class_and_triangulation_binding(built):
     ref_xyz = np.stack(rpc_oracle.latlon_to_ecef(R["ref_tri_lonlatalt"][:, 1], R["ref_tri_lonlatalt"][:, 0],
                                                  R["ref_tri_lonlatalt"][:, 2]), axis=1)
     assert np.abs(xyz - ref_xyz).max() < 2e-3
+
+
+def test_init_pts3d_rpc_branch(built):
+    """init_pts3d (ft_triangulate.py:57-127) for cam_model='rpc': GPU triangulation + the reference's float32 running mean."""
+    from sat_bundleadjust_b200 import ft_triangulate
+    from sat_bundleadjust_b200.rpc_model import RPCModel
+    from oracle import rpc_oracle
+    cams_o = [util.rpc_from_array(a) for a in R["rpc_cams"][:3]]
+    cams = [RPCModel(c.to_dict()) for c in cams_o]
+    C = R["rpcba/C"][:6]
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    got = ft_triangulate.init_pts3d(C, cams, "rpc", pairs)
+    assert got.dtype == np.float32 and got.shape == (C.shape[1], 3)
+    # checker: the compiled-reference-pinned C port + the same running mean
+    port = rpc_ctypes.load_port()
+    avg = np.zeros((C.shape[1], 3), dtype=np.float32)
+    cnt = np.zeros(C.shape[1], dtype=np.float32)
+    mask = ~np.isnan(C[::2])
+    for ci, cj in pairs:
+        t = np.where(mask[ci] & mask[cj])[0]
+        lla, _ = rpc_ctypes.triangulate(port, cams_o[ci], cams_o[cj], C[2 * ci:2 * ci + 2, t].T, C[2 * cj:2 * cj + 2, t].T, delta=0.1)
+        xyz = np.stack(rpc_oracle.latlon_to_ecef(lla[:, 1], lla[:, 0], lla[:, 2]), axis=1)
+        new = np.zeros((C.shape[1], 3), dtype=np.float32)
+        new[t] = xyz
+        cnt[t] += 1.0
+        avg[t] = ((cnt[t, None] - 1.0) * avg[t] + new[t]) / cnt[t, None]
+    seen = cnt > 0
+    assert seen.sum() > 100
+    assert np.abs(got[seen] - avg[seen]).max() <= 1.0      # float32 ulp at 6.4e6 m is 0.5 m
+    assert np.array_equal(got[~seen], avg[~seen])
