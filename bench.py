@@ -2,7 +2,7 @@
 """
 Benchmark of the bundle-adjustment hot path (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|1m|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|1m|small|cfg3|cfg3a|cfg4s]
 
 One JSON line on stdout (rank 0).  A "step" is one trust-region (Levenberg-Marquardt) iteration of the
 BASELINE.json config-2 problem: synthetic 10-view perspective BA, 1e5 tracks / ~5e5 observations,
@@ -39,6 +39,13 @@ WORKLOADS = {
     "1m": (10, 200000, 0.5, "perspective", ["R", "T"],
            "config 2 doubled: 10-view perspective BA, 2e5 tracks / ~1e6 observations, soft_l1, R+T"),
     "small": (6, 4000, 0.5, "perspective", ["R", "T"], "smoke-size: 6 views, 4e3 tracks"),
+    # BASELINE configs 3 and 4 per GPU (parity / scaling cases, not the bench line): 8 x 125k tracks = 1e6 tracks, ~5e6 obs
+    "cfg3": (50, 125000, 0.1, "perspective", ["R", "T"],
+             "BASELINE config 3 shard: 50-view perspective BA, 1.25e5 tracks / ~6e5 observations per GPU, soft_l1, R+T"),
+    "cfg3a": (50, 125000, 0.1, "affine", ["R", "T"],
+              "BASELINE config 3 shard: 50-view affine BA, 1.25e5 tracks / ~6e5 observations per GPU, soft_l1, R+T"),
+    "cfg4s": (300, 100000, 0.02, "perspective", ["R", "T"],
+              "BASELINE config 4 reduced: 300-view perspective BA, 1e5 tracks / ~6e5 observations per GPU (1800 x 1800 reduced system)"),
 }
 LS = {"loss": "soft_l1", "f_scale": 1.0}
 L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2

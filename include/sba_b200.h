@@ -174,6 +174,8 @@ int sba_rpcfit_weighted_lsq(const double *target, const double *input_locs, int3
 /* FP64 dense Cholesky solve of an n x n SPD system on the device (host buffers in/out), exposed for
  * tests of the reduced-camera-system factorisation.  A is column-major, overwritten by L. */
 int sba_cholesky_solve(double *A, double *b, int32_t n, int32_t *info);
+/* The same solve repeated `reps` times on device-resident copies; *ms = mean device time (CUDA events) of one solve. */
+int sba_cholesky_solve_timed(const double *A, const double *b, int32_t n, int32_t reps, double *x, double *ms);
 
 #ifdef __cplusplus
 }

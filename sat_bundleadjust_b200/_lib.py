@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsba_b200.so")
+LIB_PATH = os.environ.get("SBA_LIB_PATH") or os.path.join(HERE, "libsba_b200.so")     # override: A/B runs of two builds
 
 MODEL_IDS = {"affine": 0, "perspective": 1, "rpc": 2}
 LOSS_IDS = {"linear": 0, "huber": 1, "soft_l1": 2, "cauchy": 3, "arctan": 4}
@@ -64,6 +64,7 @@ EXPORTED_SYMBOLS = [
     "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_solve",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
+    "sba_cholesky_solve_timed",
     "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import",
 ]
 

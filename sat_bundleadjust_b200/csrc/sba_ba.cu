@@ -27,7 +27,7 @@ namespace sba {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
-                          cudaStream_t stream);
+                          cudaStream_t stream, bool write_factor);
 
 static inline int grid_for(long long work, int threads, int max_blocks)
 {
@@ -345,7 +345,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
     tm.end();
     tm.begin(SBA_PH_CHOLESKY);
     SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->chol_work,
-                                  p->stream));
+                                  p->stream, false));
     p->launches++;
     tm.end();
     tm.begin(SBA_PH_BACKSUB);
@@ -720,7 +720,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     if (p->world > 1) SBA_TRY(dev_alloc(p, &p->camsys, ns * nc + ns));
     else p->camsys = p->camsys_local;
     SBA_TRY(dev_alloc(p, &p->S, ns * ns + ns));
-    if (ns > 160) SBA_TRY(dev_alloc(p, &p->chol_work, (ns + 1) * (ns | 1) + ns));
+    SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
     const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
     SBA_TRY(dev_alloc(p, &p->cam_partials, (size_t)p->chunks.n * nv_cam));
     SBA_TRY(dev_alloc(p, &p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));

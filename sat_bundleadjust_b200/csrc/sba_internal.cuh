@@ -112,7 +112,7 @@ struct sba_problem {
     double *V = nullptr, *F = nullptr, *q = nullptr, *Z = nullptr;
     double *camsys_local = nullptr, *camsys = nullptr;     // [U (M*nc*nc) | g_c (M*nc)]
     double *S = nullptr;                                   // [S (ns*ns) | rhs (ns)], ns = M*nc
-    double *chol_work = nullptr;                           // (ns+1)*ns scratch of the factorisation when ns > 160
+    double *chol_work = nullptr;                           // 34*(ns+32) scratch of the blocked factorisation
     int algebraic_subspace = 0;                            // 1: experimental B_S from normal-equation identities
     double *cam_partials = nullptr, *schur_partials = nullptr, *red_partials = nullptr;
     unsigned* counters = nullptr;

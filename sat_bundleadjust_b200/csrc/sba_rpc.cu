@@ -189,7 +189,7 @@ static inline int grid_n(long long n, int threads)
 }
 
 int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
-                          cudaStream_t stream);
+                          cudaStream_t stream, bool write_factor);
 
 }  // namespace sba
 
@@ -292,16 +292,48 @@ extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info
     if (!A || !b || n < 1) { set_error("bad argument"); return SBA_E_INVALID; }
     SBA_TRY(require_device());
     DevBuf dA, db, dx, df, dw;
-    SBA_TRY(dw.alloc(((size_t)(n + 1) * (n | 1) + n) * sizeof(double)));
+    SBA_TRY(dw.alloc((size_t)34 * (n + 32) * sizeof(double)));
     SBA_TRY(dA.alloc((size_t)n * n * sizeof(double))); SBA_TRY(db.alloc(n * sizeof(double)));
     SBA_TRY(dx.alloc(n * sizeof(double))); SBA_TRY(df.alloc(sizeof(double)));
     SBA_CUDA(cudaMemcpy(dA.p, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
     SBA_CUDA(cudaMemcpy(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice));
-    SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), dw.as<double>(), 0));
+    SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), dw.as<double>(), 0, true));
     double fail = 0.0;
     SBA_CUDA(cudaMemcpy(&fail, df.p, sizeof(double), cudaMemcpyDeviceToHost));
     SBA_CUDA(cudaMemcpy(A, dA.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
     SBA_CUDA(cudaMemcpy(b, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (info) *info = (int32_t)fail;
+    return SBA_OK;
+}
+
+// the same solve `reps` times on device-resident data (A restored from a pristine copy before each repetition,
+// outside the event pair); *ms receives the mean device time of one factor + solve
+extern "C" int sba_cholesky_solve_timed(const double* A, const double* b, int32_t n, int32_t reps, double* x, double* ms)
+{
+    if (!A || !b || !x || !ms || n < 1 || reps < 1) { set_error("bad argument"); return SBA_E_INVALID; }
+    SBA_TRY(require_device());
+    DevBuf dA0, dA, db, dx, df, dw;
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    SBA_TRY(dw.alloc((size_t)34 * (n + 32) * sizeof(double)));
+    SBA_TRY(dA0.alloc(bytes)); SBA_TRY(dA.alloc(bytes)); SBA_TRY(db.alloc(n * sizeof(double)));
+    SBA_TRY(dx.alloc(n * sizeof(double))); SBA_TRY(df.alloc(sizeof(double)));
+    SBA_CUDA(cudaMemcpy(dA0.p, A, bytes, cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    SBA_CUDA(cudaEventCreate(&e0)); SBA_CUDA(cudaEventCreate(&e1));
+    double total = 0.0;
+    for (int r = -2; r < reps; ++r) {            // two warm-up repetitions
+        SBA_CUDA(cudaMemcpyAsync(dA.p, dA0.p, bytes, cudaMemcpyDeviceToDevice, 0));
+        SBA_CUDA(cudaEventRecord(e0, 0));
+        SBA_TRY(launch_cholesky_solve(dA.as<double>(), db.as<double>(), dx.as<double>(), n, df.as<double>(), dw.as<double>(), 0, false));
+        SBA_CUDA(cudaEventRecord(e1, 0));
+        SBA_CUDA(cudaEventSynchronize(e1));
+        float t = 0.f;
+        SBA_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (r >= 0) total += t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SBA_CUDA(cudaMemcpy(x, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    *ms = total / reps;
     return SBA_OK;
 }

@@ -203,8 +203,11 @@ def test_full_size_properties(built):
     with DeviceProblem(p2) as prob2:
         r1, _ = prob2.residuals(x0)
     assert np.abs((r1 - r0) + d.ravel()).max() < 1e-9
-    ls = {"loss": "soft_l1", "f_scale": 1.0, "max_iter": 300, "ftol": 1e-10, "xtol": 1e-12, "verbose": 0}
+    # with the first camera frozen at its perturbed attitude every track has to travel ~2.5 m to agree with it: TRF
+    # needs several hundred boundary-limited steps for that (old and new builds alike), hence the generous cap
+    ls = {"loss": "soft_l1", "f_scale": 1.0, "max_iter": 3000, "ftol": 1e-10, "xtol": 1e-12, "verbose": 0}
     v0, v1, e0, e1, nfev, info = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+    assert info["status"] > 0 and nfev < 3000
     assert info["cost"] < info["cost_init"] * 0.05
     assert np.sqrt(np.mean(e1 ** 2)) < np.sqrt(np.mean(e0 ** 2)) * 0.5
     c = p.n_params
@@ -220,7 +223,7 @@ def test_cholesky_solve(built):
     from sat_bundleadjust_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(0)
-    for n in (1, 7, 60, 100, 101, 130, 161, 300):
+    for n in (1, 7, 31, 32, 33, 60, 63, 64, 95, 96, 100, 127, 128, 130, 161, 192, 300, 333, 1800):
         A = rng.standard_normal((n, n + 5))
         S = A @ A.T + 0.1 * np.eye(n)
         b = rng.standard_normal(n)
