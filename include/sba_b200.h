@@ -171,6 +171,19 @@ int sba_stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, const float *
 int sba_rpcfit_weighted_lsq(const double *target, const double *input_locs, int32_t n_cam, int32_t n_samples, double h,
                             double tol, int32_t max_iter, double *rpc_out, int32_t *n_iter_out, double *rmse_out);
 
+/* Outlier detection between the two bundle-adjustment passes -- device part of bundle_adjust/ba_outliers.py:14-58
+ * (get_elbow_value) and :112-153 (compute_obs_to_remove).  Host buffers in and out.
+ * sba_outlier_elbow: one stable radix sort of all K observations by (camera, reprojection error), then per camera the
+ * elbow of the sorted curve (the sample furthest from the chord first-last, evaluated in the reference's operation
+ * order so that the arg-max is bit-identical).  stats is n_cam x 5: elbow value, the order statistics at positions
+ * q_lo[c] and q_hi[c] (what np.percentile interpolates between), the maximum, the arg-max position; counts (optional)
+ * receives the observations per camera.
+ * sba_outlier_mark: remove[k] = err[k] > thr[cam_ind[k]]. */
+int sba_outlier_elbow(const double *err, const int32_t *cam_ind, int64_t K, int32_t n_cam, const int64_t *q_lo,
+                      const int64_t *q_hi, double *stats, int64_t *counts);
+int sba_outlier_mark(const double *err, const int32_t *cam_ind, int64_t K, int32_t n_cam, const double *thr,
+                     uint8_t *remove);
+
 /* FP64 dense Cholesky solve of an n x n SPD system on the device (host buffers in/out), exposed for
  * tests of the reduced-camera-system factorisation.  A is column-major, overwritten by L. */
 int sba_cholesky_solve(double *A, double *b, int32_t n, int32_t *info);
