@@ -52,6 +52,10 @@ typedef struct sba_problem_desc {
     int32_t rpc_float32;      /* 1: round the RPC projection to float32 like ba_core.py:150 (fun parity) */
     /* multi-GPU: this rank's position among the ranks that share the cameras; the tracks are sharded */
     int32_t rank, world_size;
+    /* COMMON_K (ba_params.py:167-171): the last n_common (0 | 3 | 5) of the n_params camera variables are ONE set of
+       unknowns shared by all cameras.  The device vector keeps n_params slots per camera: the shared values live in
+       camera 0's slots, the same slots of cameras 1..M-1 are unused and must be 0.  Requires n_cam_fix == 0. */
+    int32_t n_common;
 } sba_problem_desc;
 
 /* Solver options = the reference's ls_params (bundle_adjust/ba_core.py:222-241) + scipy's gtol default */
@@ -125,6 +129,12 @@ int sba_jacobian_blocks(sba_problem *p, const double *x, double *Jc, double *Jp)
 
 /* Normal-equation blocks at x (robust rescale applied): U (M,c,c), V (N,6: xx xy xz yy yz zz), g (n). */
 int sba_normal_blocks(sba_problem *p, const double *x, int32_t loss, double f_scale, double *U, double *V, double *g);
+
+/* The reduced camera system of the damped normal equations at x exactly as the solver forms it (scaling D taken from
+ * this one evaluation; shared calibration folded, see n_common): S = U + reg D_c^2 - W (V + reg D_p^2)^-1 W^T,
+ * rhs = -(g_c - W (V + reg D_p^2)^-1 g_p).  For the parity tests of the Schur complement (there is no reference
+ * counterpart: the reference never forms S).  Host buffers; S is (n_cam n_params)^2, column-major. */
+int sba_reduced_system(sba_problem *p, const double *x, int32_t loss, double f_scale, double reg, double *S, double *rhs);
 
 /* Replaces scipy.optimize.least_squares(fun, x0, jac_sparsity=A, x_scale='jac', method='trf', ...)
  * as called by ba_core.run_ba_optimization (ba_core.py:284-297).

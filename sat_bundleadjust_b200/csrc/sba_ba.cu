@@ -169,7 +169,7 @@ struct PhaseTimer {
 static int run_prepare(sba_problem* p, const double* x, double* camrec)
 {
     k_prepare_cameras<<<grid_for(p->M, 128, 1 << 20), 128, 0, p->stream>>>(x, p->cam_static, camrec, p->M, p->P, p->nc,
-                                                                             p->n_cam_fix, p->model);
+                                                                             p->n_cam_fix, p->n_common, p->model);
     return check_launch(p);
 }
 
@@ -268,23 +268,31 @@ static int run_scale_dots(sba_problem* p, int first)
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_GMAX_SLOTS, 0, 16 * sizeof(double), p->stream));
     const int grid = grid_for(p->n, 256, NUM_SMS * 8);
     k_scale_dots<<<grid, 256, 0, p->stream>>>(p->camsys, p->V, p->x, p->g, p->sinv, p->t1, p->n, p->M * p->nc, p->nc, p->M,
-                                              first, p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal);
+                                              p->n_common, first, p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal);
     return check_launch(p);
 }
 
 static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out)
 {
     const int grid = grid_for(p->K, TPB, NUM_SMS * 16);
+    const int ns = p->M * p->nc;
+    const double *v1c = p->t1, *v2c = p->t2;
+    if (p->n_common) {       // J acts on per-camera slots: expand the shared ones
+        k_expand_common<<<grid_for(ns, 256, 64), 256, 0, p->stream>>>(p->t1, p->cvec + ns, ns, p->nc, p->n_common);
+        if (nvec == 2) k_expand_common<<<grid_for(ns, 256, 64), 256, 0, p->stream>>>(p->t2, p->cvec + 2 * ns, ns, p->nc, p->n_common);
+        SBA_TRY(check_launch(p));
+        v1c = p->cvec + ns; v2c = p->cvec + 2 * ns;
+    }
 #define L(MODEL, NC)                                                                                                  \
     if (nvec == 1)                                                                                                    \
         k_jvp<MODEL, NC, 1><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->x + (size_t)p->M * p->nc, p->camrec,        \
                                                          p->rpc_tab, p->K, p->M * p->nc, p->n_cam_fix, p->n_pts_fix,   \
-                                                         loss, f_scale, p->t1, p->t2, p->red_partials,                 \
+                                                         loss, f_scale, p->t1, p->t2, v1c, v2c, p->red_partials,       \
                                                          p->counters + 3, p->scal, out);                               \
     else                                                                                                              \
         k_jvp<MODEL, NC, 2><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), p->x + (size_t)p->M * p->nc, p->camrec,        \
                                                          p->rpc_tab, p->K, p->M * p->nc, p->n_cam_fix, p->n_pts_fix,   \
-                                                         loss, f_scale, p->t1, p->t2, p->red_partials,                 \
+                                                         loss, f_scale, p->t1, p->t2, v1c, v2c, p->red_partials,       \
                                                          p->counters + 3, p->scal, out)
     SBA_DISPATCH(p, L);
 #undef L
@@ -292,7 +300,7 @@ static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out
 }
 
 // Schur complement + Cholesky solve + back-substitution for a given damping `reg`
-static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, PhaseTimer& tm)
+static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, PhaseTimer& tm, bool stop_after_schur = false)
 {
     const int ns = p->M * p->nc;
     const double* xp = p->x + (size_t)ns;
@@ -330,7 +338,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
 #undef SCHUR_ARGS
 #define FIN_ARGS                                                                                                       \
     p->schur_partials, p->sb_first, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, p->scal,           \
-        p->rank == 0, p->S
+        p->rank == 0, p->n_common, p->S
         switch (p->nc) {
         case 3: k_schur_finalize<3><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
         case 5: k_schur_finalize<5><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
@@ -342,7 +350,12 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
 #undef FIN_ARGS
     }
     SBA_TRY(allreduce_any(p, p->S, (long long)ns * ns + ns));
+    if (p->n_common) {
+        k_fold_common<<<1, 256, 0, p->stream>>>(p->S, ns, p->nc, p->M, p->n_common);
+        SBA_TRY(check_launch(p));
+    }
     tm.end();
+    if (stop_after_schur) return SBA_OK;
     tm.begin(SBA_PH_CHOLESKY);
     SBA_TRY(launch_cholesky_solve(p->S, p->S + (size_t)ns * ns, p->delta, ns, p->scal + SC_CHOL_FAIL, p->chol_work,
                                   p->stream, false));
@@ -351,12 +364,18 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
     tm.begin(SBA_PH_BACKSUB);
     {
         const int grid = (p->n_tiles + WPB - 1) / WPB;
+        const double* dcam = p->delta;
+        if (p->n_common) {
+            k_expand_common<<<grid_for(ns, 256, 64), 256, 0, p->stream>>>(p->delta, p->cvec, ns, p->nc, p->n_common);
+            SBA_TRY(check_launch(p));
+            dcam = p->cvec;
+        }
         switch (p->nc) {
-        case 3: k_backsub<3><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
-        case 5: k_backsub<5><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
-        case 6: k_backsub<6><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
-        case 8: k_backsub<8><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
-        default: k_backsub<11><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, p->delta); break;
+        case 3: k_backsub<3><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, dcam, p->delta); break;
+        case 5: k_backsub<5><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, dcam, p->delta); break;
+        case 6: k_backsub<6><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, dcam, p->delta); break;
+        case 8: k_backsub<8><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, dcam, p->delta); break;
+        default: k_backsub<11><<<grid, TPB, 0, p->stream>>>(obs_arrays(p), ns, p->F, p->q, p->Z, dcam, p->delta); break;
         }
         SBA_TRY(check_launch(p));
     }
@@ -407,7 +426,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
         k_control_tr2d<<<1, 32, 0, p->stream>>>(p->scal, radius);
         SBA_TRY(check_launch(p));
         k_step<<<elem_grid, 256, 0, p->stream>>>(p->x, p->t1, p->t2, p->scal, p->x_new, p->n, p->cam_static,
-                                                 p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->model);
+                                                 p->camrec_new, p->M, p->P, p->nc, p->n_cam_fix, p->n_common, p->model);
         SBA_TRY(check_launch(p));
         SBA_TRY(run_residual(p, p->x_new, p->camrec_new, loss, fs, nullptr, SC_COST_NEW, 0));
         SBA_TRY(allreduce_scal(p, SC_COST_NEW, 1));
@@ -721,6 +740,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     else p->camsys = p->camsys_local;
     SBA_TRY(dev_alloc(p, &p->S, ns * ns + ns));
     SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
+    SBA_TRY(dev_alloc(p, &p->cvec, (size_t)3 * ns));
     const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
     SBA_TRY(dev_alloc(p, &p->cam_partials, (size_t)p->chunks.n * nv_cam));
     SBA_TRY(dev_alloc(p, &p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));
@@ -752,6 +772,11 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     if (d->cam_model == MODEL_RPC && !d->rpc_coefs) { set_error("rpc_coefs required for cam_model rpc"); return SBA_E_INVALID; }
     if (!d->cam_ind || !d->pts_ind || !d->pts2d || !d->pts2d_w || !d->cam_params) { set_error("null array"); return SBA_E_INVALID; }
     if (d->n_cam_fix < 0 || d->n_cam_fix > d->n_cam || d->n_pts_fix < 0 || d->n_pts_fix > d->n_pts) { set_error("bad n_cam_fix / n_pts_fix"); return SBA_E_INVALID; }
+    if (d->n_common < 0 || d->n_common > 5 || d->n_common >= d->n_params || (d->n_common > 0 && d->n_cam_fix > 0)) {
+        // the reference's COMMON_K packing is only self-consistent without frozen cameras (ba_params.py:170 vs :244)
+        set_error("bad n_common (shared calibration needs n_cam_fix == 0)");
+        return SBA_E_INVALID;
+    }
     if (d->world_size < 1 || d->world_size > 16 || d->rank < 0 || d->rank >= d->world_size) { set_error("bad rank / world_size"); return SBA_E_INVALID; }
     if ((double)d->n_cam * d->n_pts > 1.5e9) { set_error("n_cam * n_pts too large for the dense (camera, track) table; use the matrix-free path"); return SBA_E_INVALID; }
     if ((int64_t)d->n_cam * d->n_params > 4096) { set_error("reduced camera system larger than 4096: use the matrix-free path"); return SBA_E_INVALID; }
@@ -764,6 +789,7 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->model = d->cam_model; p->M = d->n_cam; p->N = d->n_pts; p->K = d->n_obs; p->nc = d->n_params; p->P = P;
     p->n_cam_fix = d->n_cam_fix; p->n_pts_fix = d->n_pts_fix; p->rpc_f32 = d->rpc_float32;
     p->rank = d->rank; p->world = d->world_size;
+    p->n_common = d->n_common;
     p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
@@ -872,6 +898,32 @@ extern "C" int sba_normal_blocks(sba_problem* p, const double* x, int32_t loss, 
         SBA_CUDA(cudaMemcpyAsync(g, p->camsys + ns * p->nc, ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         SBA_CUDA(cudaMemcpyAsync(g + ns, p->g + ns, 3 * (size_t)p->N * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     }
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
+// The reduced camera system of the damped normal equations at x, as the solver forms it (scaling D from this one
+// evaluation): S = U + reg D_c^2 - W (V + reg D_p^2)^-1 W^T and rhs = -(g_c - W (V + reg D_p^2)^-1 g_p), COMMON_K folded.
+// Exposed for the parity tests of the Schur complement; host buffers, S is (M n_params)^2 column-major.
+extern "C" int sba_reduced_system(sba_problem* p, const double* x, int32_t loss, double f_scale, double reg, double* S,
+                                  double* rhs)
+{
+    if (!p || !x || !S || !rhs || !(reg >= 0.0)) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (p->world > 1) { set_error("sba_reduced_system: single-rank problems only"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    const size_t ns = (size_t)p->M * p->nc;
+    SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), p->stream));
+    SBA_CUDA(cudaMemcpyAsync(p->x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    SBA_TRY(run_prepare(p, p->x, p->camrec));
+    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
+    SBA_TRY(run_scale_dots(p, 1));
+    k_control_reg<<<1, 32, 0, p->stream>>>(p->scal, -1.0, reg);
+    SBA_TRY(check_launch(p));
+    PhaseTimer tm;
+    tm.p = p;
+    SBA_TRY(run_gauss_newton_step(p, loss, f_scale, tm, true));
+    SBA_CUDA(cudaMemcpyAsync(S, p->S, ns * ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_CUDA(cudaMemcpyAsync(rhs, p->S + ns * ns, ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     SBA_CUDA(cudaStreamSynchronize(p->stream));
     return SBA_OK;
 }

@@ -104,8 +104,10 @@ __device__ __forceinline__ void write_camrec(const double (&v)[MAX_CAM_PARAMS], 
     build_camrec(v, model, r);
 }
 
+// n_common > 0 (COMMON_K, ba_params.py:167-171, :254-255): the last n_common of the nc variables are shared by all
+// cameras and live in camera 0's slots; the same slots of the other cameras are unused (zero, never stepped)
 __global__ void k_prepare_cameras(const double* __restrict__ x, const double* __restrict__ cam_static,
-                                  double* __restrict__ camrec, int M, int P, int nc, int n_cam_fix, int model)
+                                  double* __restrict__ camrec, int M, int P, int nc, int n_cam_fix, int n_common, int model)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
@@ -113,7 +115,10 @@ __global__ void k_prepare_cameras(const double* __restrict__ x, const double* __
 #pragma unroll
     for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
         double val = 0.0;
-        if (s < P) val = (s < nc && j >= n_cam_fix) ? x[(size_t)j * nc + s] : cam_static[(size_t)j * P + s];
+        if (s < P) {
+            const int src = (s >= nc - n_common) ? 0 : j;
+            val = (s < nc && j >= n_cam_fix) ? x[(size_t)src * nc + s] : cam_static[(size_t)j * P + s];
+        }
         v[s] = val;
     }
     write_camrec(v, camrec + (size_t)j * CAMREC_STRIDE, model);
@@ -425,7 +430,7 @@ k_reduce_cameras(const double* __restrict__ cam_partials, const int* __restrict_
 __global__ void __launch_bounds__(256)
 k_scale_dots(const double* __restrict__ camsys, const double* __restrict__ V, const double* __restrict__ x,
              double* __restrict__ g, double* __restrict__ sinv, double* __restrict__ t1, long long n, int ns, int nc,
-             int M, int first, int count_cameras, int rank, double* partials, unsigned* counter, double* scal)
+             int M, int n_common, int first, int count_cameras, int rank, double* partials, unsigned* counter, double* scal)
 {
     __shared__ double sm[4 * (256 / 32)];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};   // gg, xs, xx, gmax
@@ -437,6 +442,16 @@ k_scale_dots(const double* __restrict__ camsys, const double* __restrict__ V, co
             const int j = (int)idx / nc, s = (int)idx % nc;
             diag = camsys[(size_t)j * nc * nc + s * nc + s];
             gv = camsys[(size_t)M * nc * nc + idx];
+            if (s >= nc - n_common) {        // shared column: its squared norm and gradient are the sums over the cameras
+                if (j == 0) {
+                    for (int jj = 1; jj < M; ++jj) {
+                        diag += camsys[(size_t)jj * nc * nc + s * nc + s];
+                        gv += camsys[(size_t)M * nc * nc + (size_t)jj * nc + s];
+                    }
+                } else {
+                    diag = 0.0; gv = 0.0;
+                }
+            }
             g[idx] = gv;
         } else {
             const long long e = idx - ns;
@@ -487,8 +502,8 @@ template <int MODEL, int NC, int NVEC>
 __global__ void __launch_bounds__(TPB, (MODEL == MODEL_RPC || NC > 6) ? 3 : 6)
 k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ camrec,
       const double* __restrict__ rpc_tab, long long K, int ns, int n_cam_fix, int n_pts_fix, int loss, double f_scale,
-      const double* __restrict__ v1, const double* __restrict__ v2, double* partials, unsigned* counter, double* scal,
-      Slots out)
+      const double* __restrict__ v1, const double* __restrict__ v2, const double* __restrict__ v1c,
+      const double* __restrict__ v2c, double* partials, unsigned* counter, double* scal, Slots out)
 {
     __shared__ double sm[3 * (TPB / 32)];
     double acc[3] = {0.0, 0.0, 0.0};
@@ -503,9 +518,9 @@ k_jvp(ObsArrays o, const double* __restrict__ xp, const double* __restrict__ cam
         double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-            const double a1 = v1[(size_t)j * NC + k];
+            const double a1 = v1c[(size_t)j * NC + k];        // camera part (expanded copy when variables are shared)
             y0 += e.Jc[k] * a1; y1 += e.Jc[NC + k] * a1;
-            if (NVEC == 2) { const double a2 = v2[(size_t)j * NC + k]; z0 += e.Jc[k] * a2; z1 += e.Jc[NC + k] * a2; }
+            if (NVEC == 2) { const double a2 = v2c[(size_t)j * NC + k]; z0 += e.Jc[k] * a2; z1 += e.Jc[NC + k] * a2; }
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -789,7 +804,7 @@ __global__ void __launch_bounds__(128)
 k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ sb_first,
                  const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M, int n_cam_fix,
                  const double* __restrict__ camsys_local, const double* __restrict__ sinv,
-                 const double* __restrict__ scal, int add_diag, double* __restrict__ S)
+                 const double* __restrict__ scal, int add_diag, int n_common, double* __restrict__ S)
 {
     constexpr int NVALL = NC * NC + NC;
     const double reg = scal[SC_REG];
@@ -808,7 +823,7 @@ k_schur_finalize(const double* __restrict__ schur_partials, const int* __restric
             double val = -s;
             if (j == jp) {
                 val += camsys_local[(size_t)j * NC * NC + r * NC + c];
-                if (r == c && add_diag) {
+                if (r == c && add_diag && !(j > 0 && r >= NC - n_common)) {      // unused shared slots: see k_fold_common
                     const double si = sinv[(size_t)j * NC + r];
                     val += (j < n_cam_fix) ? 1.0 : reg * si * si;
                 }
@@ -823,12 +838,55 @@ k_schur_finalize(const double* __restrict__ schur_partials, const int* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// COMMON_K (ba_params.py:167-171): the last n_common variables of every camera are ONE set of unknowns.  The blocks
+// are assembled per camera as usual; the reduced system is then folded, S' = P^T S P with P the 0/1 map from
+// [shared | per-camera] unknowns to per-camera slots: rows and columns of the shared slots of cameras 1..M-1 are
+// added onto camera 0's and replaced by identity rows with a zero right-hand side (their step is 0).
+// One CTA; S is ns x ns column-major followed by the right-hand side.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold_common(double* __restrict__ S, int ns, int nc, int M, int n_common)
+{
+    double* rhs = S + (size_t)ns * ns;
+    const int s0 = nc - n_common;
+    // rows (and the right-hand side)
+    for (int t = threadIdx.x; t < n_common * (ns + 1); t += blockDim.x) {
+        const int s = s0 + t / (ns + 1), col = t % (ns + 1);
+        double* base = col < ns ? S + (size_t)col * ns : rhs;
+        double acc = base[s];
+        for (int j = 1; j < M; ++j) { acc += base[j * nc + s]; base[j * nc + s] = 0.0; }
+        base[s] = acc;
+    }
+    __syncthreads();
+    // columns
+    for (int t = threadIdx.x; t < n_common * ns; t += blockDim.x) {
+        const int s = s0 + t / ns, row = t % ns;
+        double acc = S[(size_t)s * ns + row];
+        for (int j = 1; j < M; ++j) { acc += S[(size_t)(j * nc + s) * ns + row]; S[(size_t)(j * nc + s) * ns + row] = 0.0; }
+        S[(size_t)s * ns + row] = acc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_common * (M - 1); t += blockDim.x) {
+        const int e = (1 + t / n_common) * nc + s0 + t % n_common;
+        S[(size_t)e * ns + e] = 1.0;
+    }
+}
+
+// camera part of a variable vector with the shared slots of camera 0 copied to every camera (what J acts on)
+__global__ void k_expand_common(const double* __restrict__ src, double* __restrict__ dst, int ns, int nc, int n_common)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ns; e += gridDim.x * blockDim.x) {
+        const int s = e % nc;
+        dst[e] = s >= nc - n_common ? src[s] : src[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // G6: back-substitution  dp_i = -G^T (q_i + sum_a Z_a^T dc_cam(a)), warp tiles like k_point_prep
 // ------------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(TPB)
 k_backsub(ObsArrays o, int ns, const double* __restrict__ F, const double* __restrict__ q,
-          const double* __restrict__ Zin, double* __restrict__ delta)
+          const double* __restrict__ Zin, const double* __restrict__ dcam, double* __restrict__ delta)
 {
     constexpr int ZS = NC * 3, ZP = ZS + 1;
     __shared__ double sv[WPB][3][32];
@@ -850,7 +908,7 @@ k_backsub(ObsArrays o, int ns, const double* __restrict__ F, const double* __res
             const double* z = &sZ[warp][lane * ZP];
 #pragma unroll
             for (int r = 0; r < NC; ++r) {
-                const double dc = delta[(size_t)j * NC + r];
+                const double dc = dcam[(size_t)j * NC + r];
                 s0 += z[3 * r] * dc; s1 += z[3 * r + 1] * dc; s2 += z[3 * r + 2] * dc;
             }
         }
@@ -876,7 +934,7 @@ k_backsub(ObsArrays o, int ns, const double* __restrict__ F, const double* __res
             const double* z = Zin + (size_t)a * ZS;
 #pragma unroll
             for (int r = 0; r < NC; ++r) {
-                const double dc = delta[(size_t)j * NC + r];
+                const double dc = dcam[(size_t)j * NC + r];
                 s[0] += z[3 * r] * dc; s[1] += z[3 * r + 1] * dc; s[2] += z[3 * r + 2] * dc;
             }
         }
@@ -954,7 +1012,7 @@ __device__ __forceinline__ double step_value(double x, double a, double d, doubl
 __global__ void __launch_bounds__(256)
 k_step(const double* __restrict__ x, const double* __restrict__ t1, const double* __restrict__ delta,
        const double* __restrict__ scal, double* __restrict__ x_new, long long n, const double* __restrict__ cam_static,
-       double* __restrict__ camrec_new, int M, int P, int nc, int n_cam_fix, int model)
+       double* __restrict__ camrec_new, int M, int P, int nc, int n_cam_fix, int n_common, int model)
 {
     const double ca = scal[SC_C1], cb = scal[SC_C2];
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -970,7 +1028,7 @@ k_step(const double* __restrict__ x, const double* __restrict__ t1, const double
             double val = 0.0;
             if (s < P) {
                 if (s < nc && j >= n_cam_fix) {
-                    const size_t e = (size_t)j * nc + s;
+                    const size_t e = (size_t)((s >= nc - n_common) ? 0 : j) * nc + s;
                     val = step_value(x[e], t1[e], delta[e], ca, cb);
                 } else {
                     val = cam_static[(size_t)j * P + s];

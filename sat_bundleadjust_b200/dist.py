@@ -59,6 +59,9 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
     torch.distributed NCCL process group (one process per GPU).  Every rank passes the same `p`.
     Returns (vars_init, vars_ba, err_init, err_ba, nfev, info) with the global vectors on every rank.
     """
+    from .solver import n_common_params
+    if n_common_params(p):
+        raise NotImplementedError("COMMON_K is not supported by the distributed driver")
     import torch
     import torch.distributed as dist
 

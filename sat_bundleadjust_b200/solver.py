@@ -23,11 +23,19 @@ def rpc_table(rpc):
                            np.asarray(rpc.col_num, dtype=np.float64), np.asarray(rpc.col_den, dtype=np.float64)])
 
 
-def check_supported(p):
+def n_common_params(p):
+    """Number of calibration variables shared by all cameras (COMMON_K, bundle_adjust/ba_params.py:167-171), else 0."""
     opt = p.cam_params_to_optimize
     if "K" in opt and "COMMON_K" in opt and "T" in opt and "R" in opt:
-        raise NotImplementedError("COMMON_K (one calibration shared by all cameras) is not supported by the "
-                                  "B200 solver yet")
+        return 3 if p.cam_model == "affine" else 5
+    return 0
+
+
+def check_supported(p):
+    if n_common_params(p) and p.n_cam_fix > 0:
+        # the reference packs n_cam_opt cameras (ba_params.py:170) but unpacks n_cam (ba_params.py:244): with frozen
+        # cameras its own vector is inconsistent, so there is no behaviour to mirror
+        raise NotImplementedError("COMMON_K with n_cam_fix > 0 is inconsistent in the reference and not supported")
     if p.cam_model == "rpc" and p.n_params > 6:
         raise ValueError("cam_model 'rpc' has no calibration parameters to optimise")
 
@@ -39,7 +47,7 @@ def initial_vars(p):
     (bundle_adjust/ba_params.py:246-249 via ba_core.py:276-277).
     """
     x0 = np.array(p.params_opt, dtype=np.float64, copy=True)
-    if p.n_cam_fix > 0:
+    if p.n_cam_fix > 0 and not n_common_params(p):
         c = p.n_params
         x0[: p.n_cam * c].reshape(p.n_cam, c)[: p.n_cam_fix] = p.cam_params[: p.n_cam_fix, :c]
     return x0
@@ -79,9 +87,12 @@ class DeviceProblem:
             d.rpc_coefs = dptr(self._keep[-1])
         d.rpc_float32 = 1 if rpc_float32 else 0
         d.rank, d.world_size = rank, world_size
+        self.n_common = d.n_common = n_common_params(p)
         self.handle = ctypes.c_void_p()
         check(self.lib.sba_problem_create(ctypes.byref(self.handle), ctypes.byref(d), ctypes.c_void_p(stream)))
-        self.n_vars = int(self.lib.sba_problem_num_vars(self.handle))
+        self.n_vars_device = int(self.lib.sba_problem_num_vars(self.handle))
+        # length of the caller's vector (the reference's params_opt layout); the device keeps n_params slots per camera
+        self.n_vars = self.n_vars_device - (self.n_cam - 1) * self.n_common
         self._cb = None
 
     def close(self):
@@ -97,16 +108,37 @@ class DeviceProblem:
     def __exit__(self, *a):
         self.close()
 
+    def _to_device_layout(self, v):
+        """[K | cam_0[:c'] ... cam_M-1[:c'] | points] (ba_params.py:167-171) -> n_params slots per camera, K in camera 0's"""
+        k, c, m = self.n_common, self.n_params, self.n_cam
+        x = np.zeros(self.n_vars_device)
+        cams = x[: m * c].reshape(m, c)
+        cams[:, : c - k] = v[k: k + m * (c - k)].reshape(m, c - k)
+        cams[0, c - k:] = v[:k]
+        x[m * c:] = v[k + m * (c - k):]
+        return x
+
+    def _from_device_layout(self, x):
+        k, c, m = self.n_common, self.n_params, self.n_cam
+        cams = x[: m * c].reshape(m, c)
+        return np.concatenate([cams[0, c - k:], cams[:, : c - k].ravel(), x[m * c:]])
+
     def _vars(self, x):
-        """float64 copy-if-needed of a variable vector with the frozen points pinned to their initial values"""
+        """float64 device-layout vector (copy if needed) with the frozen points pinned to their initial values"""
         x = f64(x)
         assert x.size == self.n_vars
+        if self.n_common:
+            x = self._to_device_layout(x)
         if self._fixed_pts.size:
             off = self.n_cam * self.n_params
             if not np.array_equal(x[off: off + self._fixed_pts.size], self._fixed_pts):
                 x = x.copy()
                 x[off: off + self._fixed_pts.size] = self._fixed_pts
         return x
+
+    def _no_common(self, what):
+        if self.n_common:
+            raise NotImplementedError("%s is not available with COMMON_K (blocks are per camera)" % what)
 
     # -- evaluation ------------------------------------------------------------------------------
     def residuals(self, x, loss="linear", f_scale=1.0):
@@ -117,6 +149,8 @@ class DeviceProblem:
         return r, cost.value
 
     def jacobian_blocks(self, x):
+        """Per-observation Jacobian blocks d r / d (camera slots), d r / d point.  With COMMON_K the blocks stay per camera:
+        the column of a shared variable is the sum of its slot's columns over the cameras."""
         x = self._vars(x)
         Jc = np.empty((self.n_obs, 2, self.n_params))
         Jp = np.empty((self.n_obs, 2, 3))
@@ -124,6 +158,7 @@ class DeviceProblem:
         return Jc, Jp
 
     def normal_blocks(self, x, loss="linear", f_scale=1.0):
+        self._no_common("normal_blocks")
         x = self._vars(x)
         c = self.n_params
         U = np.empty((self.n_cam, c, c))
@@ -131,6 +166,16 @@ class DeviceProblem:
         g = np.empty(self.n_vars)
         check(self.lib.sba_normal_blocks(self.handle, dptr(x), LOSS_IDS[loss], f_scale, dptr(U), dptr(V), dptr(g)))
         return U, V, g
+
+    def reduced_system(self, x, loss="linear", f_scale=1.0, reg=0.0):
+        """(S, rhs) of the damped normal equations reduced onto the cameras, in the device layout (n_params slots per camera)."""
+        x = self._vars(x)
+        ns = self.n_cam * self.n_params
+        S = np.empty((ns, ns), order="F")
+        rhs = np.empty(ns)
+        check(self.lib.sba_reduced_system(self.handle, dptr(x), LOSS_IDS[loss], ctypes.c_double(f_scale), ctypes.c_double(reg),
+                                          dptr(S), dptr(rhs)))
+        return S, rhs
 
     @staticmethod
     def make_opts(loss="linear", f_scale=1.0, ftol=1e-4, xtol=1e-10, gtol=1e-8, max_nfev=300, verbose=0,
@@ -150,10 +195,12 @@ class DeviceProblem:
         opts = self.make_opts(**kw)
         check(self.lib.sba_solve(self.handle, dptr(x0), ctypes.byref(opts), dptr(x), dptr(r) if r is not None else None,
                                  ctypes.byref(info)))
+        if self.n_common:
+            x = self._from_device_layout(x)
         return x, r, info.as_dict()
 
     def solve_device(self, x0_ptr, x_ptr=None, r_ptr=None, **kw):
-        """Device pointers (ints) in and out; nothing but the steering scalars crosses PCIe."""
+        """Device pointers (ints) in and out (device layout); nothing but the steering scalars crosses PCIe."""
         info = SolveInfo()
         opts = self.make_opts(**kw)
         check(self.lib.sba_solve_device(self.handle, ctypes.c_void_p(x0_ptr), ctypes.byref(opts),

@@ -27,7 +27,7 @@ SOLVE_CASES = [c for c in CASES if (c + "/ref_vars_ba") in G.files]
 RES_TOL_PX = 1e-6
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if "common" not in c])
+@pytest.mark.parametrize("name", CASES)
 def test_fun_matches_reference_golden(built, name):
     p = util.params_from_golden(G, name)
     pre = name + "/"
@@ -274,3 +274,95 @@ def test_long_tracks_and_many_cameras(built):
     assert abs(cost_gpu - info["cost"]) <= 1e-9 * cost_gpu and cost_gpu < 0.05 * info["cost_init"]
     xc, cc, _ = ba_oracle.solve_converged(p, "soft_l1", 1.0, x_start=x, max_nfev=30)
     assert abs(cost_gpu - cc) <= 1e-6 * cc, (cost_gpu, cc)
+
+
+@pytest.mark.parametrize("model,corr", [("perspective", ["R", "T", "K"]), ("perspective", ["R", "T", "K", "COMMON_K"]),
+                                        ("affine", ["R", "T", "K"]), ("affine", ["R", "T", "K", "COMMON_K"])])
+def test_calibration_variables_solve(built, model, corr):
+    """
+    Per-camera K (c = 11 / 8) and COMMON_K (one calibration shared by all cameras, ba_params.py:167-171).  The reference's
+    packing starts these from mis-initialised intrinsics, so the start vector is repaired here.  With narrow
+    satellite fields of view calibration and pose are nearly interchangeable: the problem has flat valleys in which
+    neither this solver nor scipy's exact TRF on the oracle terminates on ftol within thousands of evaluations.  The
+    checks are therefore: same residuals as the oracle, consistent reported cost, a large monotone decrease, and a final
+    cost at least as low as the one scipy's exact TRF reaches on the oracle from the same start (the linear algebra of the
+    shared-calibration border itself is pinned by test_reduced_camera_system).
+    """
+    sc = synth.make_scene(n_cam=4, n_tracks=80, p_vis=0.8, cam_model=model, seed=12)
+    p = synth.scene_to_params(sc, corr)
+    nK, c = (3 if model == "affine" else 5), p.n_params
+    x0 = p.params_opt.copy()
+    if "COMMON_K" in corr:
+        assert x0.size == nK + p.n_cam * (c - nK) + 3 * p.n_pts
+        x0[:nK] = p.cam_params[0, -nK:]
+    else:
+        x0[: p.n_cam * c].reshape(p.n_cam, c)[:, c - nK:] = p.cam_params[:, -nK:]
+    with DeviceProblem(p) as prob:
+        assert prob.n_vars == x0.size
+        r, cost0 = prob.residuals(x0, "soft_l1", 1.0)
+        f = ba_oracle.residuals(x0.copy(), p)
+        assert np.abs(r - f).max() < RES_TOL_PX
+        x, rr, info = prob.solve(x0, loss="soft_l1", ftol=1e-12, xtol=0.0, max_nfev=1000)
+    assert x.shape == x0.shape
+    cost_gpu = ba_oracle.robust_cost(ba_oracle.residuals(x.copy(), p), "soft_l1", 1.0)
+    assert abs(cost_gpu - info["cost"]) <= 1e-9 * cost_gpu and cost_gpu < 0.5 * info["cost_init"]
+    xc, cc, _ = ba_oracle.solve_converged(p, "soft_l1", 1.0, x_start=x0, max_nfev=40)
+    assert cost_gpu <= cc * (1 + 1e-6), (cost_gpu, cc)
+
+
+@pytest.mark.parametrize("model,corr,loss", [("perspective", ["R", "T"], "linear"), ("perspective", ["R", "T"], "soft_l1"),
+                                             ("perspective", ["R", "T", "K", "COMMON_K"], "soft_l1"),
+                                             ("affine", ["R", "T", "K", "COMMON_K"], "linear"),
+                                             ("affine", ["R", "T", "K"], "huber")])
+@pytest.mark.parametrize("reg", [0.0, 0.37])
+def test_reduced_camera_system(built, model, corr, loss, reg):
+    """
+    The Schur complement the solver factors, against dense linear algebra on the same Jacobian: S = H_cc - H_cp H_pp^-1 H_pc
+    of H = J^T J + reg diag(J^T J) and rhs = -(g_c - H_cp H_pp^-1 g_p).  With COMMON_K the shared calibration columns are the
+    sums of the per-camera ones (dense border of S, folded onto camera 0's slots on the device).
+    """
+    from scipy.optimize._lsq.common import scale_for_robust_loss_function
+    from scipy.optimize._lsq.least_squares import construct_loss_function
+    if loss == "huber" and reg == 0.0:
+        # huber zeroes the Jacobian rows of outlying residuals (rho' + 2 rho'' f^2 = 0): a point seen only through such rows
+        # has a singular block unless it is damped, and there is nothing well defined to compare
+        pytest.skip("undamped point blocks can be singular under huber")
+    sc = synth.make_scene(n_cam=4, n_tracks=80, p_vis=0.8, cam_model=model, seed=21)
+    p = synth.scene_to_params(sc, corr)
+    nK, c, M = (3 if model == "affine" else 5), p.n_params, p.n_cam
+    x0 = p.params_opt.copy()
+    common = "COMMON_K" in corr
+    if common:
+        x0[:nK] = p.cam_params[0, -nK:]
+    elif "K" in corr:
+        x0[: M * c].reshape(M, c)[:, c - nK:] = p.cam_params[:, -nK:]
+    with DeviceProblem(p) as prob:
+        Jc, Jp = prob.jacobian_blocks(x0)
+        S, rhs = prob.reduced_system(x0, loss, 1.0, reg)
+    f = ba_oracle.residuals(x0.copy(), p)
+    J = util.dense_jacobian_from_blocks(p, Jc, Jp)                   # device layout: c slots per camera
+    if loss != "linear":
+        rho = construct_loss_function(f.size, loss, 1.0)(f.copy())
+        J, f = scale_for_robust_loss_function(J, f.copy(), rho)
+    ns = M * c
+    used = np.ones(ns, dtype=bool)
+    if common:                                                       # fold the shared columns onto camera 0's slots
+        for j in range(1, M):
+            J[:, c - nK: c] += J[:, j * c + c - nK: (j + 1) * c]
+            J[:, j * c + c - nK: (j + 1) * c] = 0.0
+            used[j * c + c - nK: (j + 1) * c] = False
+    H, g = J.T @ J, J.T @ f
+    d2 = np.diag(H).copy()
+    d2[d2 == 0.0] = 1.0
+    H = H + reg * np.diag(d2)
+    Hcc, Hcp, Hpp = H[:ns, :ns], H[:ns, ns:], H[ns:, ns:]
+    X = np.linalg.solve(Hpp, np.column_stack([Hcp.T, g[ns:]]))
+    S_np = Hcc - Hcp @ X[:, :ns]
+    rhs_np = -(g[:ns] - Hcp @ X[:, ns])
+    u = np.where(used)[0]
+    scale = np.abs(Hcc).max()
+    assert np.abs(S[np.ix_(u, u)] - S_np[np.ix_(u, u)]).max() <= 1e-10 * scale, np.abs(S[np.ix_(u, u)] - S_np[np.ix_(u, u)]).max() / scale
+    assert np.abs(rhs[u] - rhs_np[u]).max() <= 1e-9 * np.abs(rhs_np).max()
+    assert np.allclose(S, S.T, rtol=0, atol=1e-12 * scale)
+    n = np.where(~used)[0]                                           # unused slots: identity rows, zero right-hand side
+    assert np.array_equal(S[np.ix_(n, n)], np.eye(n.size)) and not S[np.ix_(n, u)].any() and not rhs[n].any()

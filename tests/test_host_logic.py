@@ -161,9 +161,30 @@ def test_no_cpu_fallback(built):
 
 
 def test_unsupported_configurations_raise():
+    """COMMON_K with frozen cameras: the reference packs n_cam_opt cameras but unpacks n_cam (ba_params.py:170 vs :244)."""
+    from sat_bundleadjust_b200.solver import check_supported, n_common_params
     p = util.params_from_golden(G, "persp_RTK_common")
+    assert n_common_params(p) == 5
+    check_supported(p)
+    p.n_cam_fix = 1
     with pytest.raises(NotImplementedError):
-        DeviceProblem(p)
+        check_supported(p)
+
+
+def test_common_K_device_layout_round_trip():
+    """[K | cam[:c'] ... | points] <-> n_params slots per camera with K in camera 0's slots (include/sba_b200.h n_common)."""
+    from sat_bundleadjust_b200.solver import DeviceProblem as DP
+    d = DP.__new__(DP)
+    d.n_common, d.n_params, d.n_cam = 5, 11, 4
+    n_pts = 7
+    d.n_vars_device = d.n_cam * d.n_params + 3 * n_pts
+    v = np.arange(5 + 4 * 6 + 3 * n_pts, dtype=np.float64) + 1.0
+    x = d._to_device_layout(v)
+    cams = x[:44].reshape(4, 11)
+    assert np.array_equal(cams[0, 6:], v[:5]) and np.all(cams[1:, 6:] == 0.0)
+    assert np.array_equal(cams[:, :6].ravel(), v[5:29]) and np.array_equal(x[44:], v[29:])
+    assert np.array_equal(d._from_device_layout(x), v)
+    d.handle = None
 
 
 # ---------------------------------------------------------------------------------------------------
