@@ -109,6 +109,9 @@ int sba_version(void);
  * and ba_core.build_jacobian_sparsity (ba_core.py:186-219).  `stream` is a cudaStream_t (0 = default). */
 int sba_problem_create(sba_problem **out, const sba_problem_desc *desc, void *stream);
 int sba_problem_destroy(sba_problem *p);
+/* Device slabs of destroyed problems are cached for the next sba_problem_create (the pipeline solves twice per run);
+ * this returns them to the driver. */
+int sba_release_cached_memory(void);
 int sba_problem_set_allreduce(sba_problem *p, sba_allreduce_fn fn, void *user);
 /* Multi-GPU exchange without the hook: a device-side one-shot all-reduce over NVLink peer memory.  Every rank calls
  * sba_comm_export (writes the 64-byte CUDA IPC handle of its symmetric buffer), the handles are gathered by any means
@@ -140,6 +143,12 @@ int sba_reduced_system(sba_problem *p, const double *x, int32_t loss, double f_s
  * as called by ba_core.run_ba_optimization (ba_core.py:284-297).
  * x0 (n) in, x (n) out, r (2K) = un-scaled residuals at the solution (res.fun), may be NULL. */
 int sba_solve(sba_problem *p, const double *x0, const sba_solve_opts *opts, double *x, double *r, sba_solve_info *info);
+
+/* sba_solve plus the two per-observation reprojection-error vectors the reference's driver returns
+ * (compute_reprojection_error, ba_core.py:304-305,335-349), computed on the device: err_init (K) at x0 and err (K) at the
+ * solution; either may be NULL.  Saves the 2 x 2K residual read-backs and the host-side norms of the end-to-end call. */
+int sba_solve_errors(sba_problem *p, const double *x0, const sba_solve_opts *opts, double *x, double *err_init, double *err,
+                     sba_solve_info *info);
 
 /* Same solve with x0 / x / r as DEVICE pointers (inputs already resident in HBM; nothing is copied
  * to the host except the few scalars that steer the iteration). */

@@ -60,8 +60,8 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 
 # every symbol include/sba_b200.h declares
 EXPORTED_SYMBOLS = [
-    "sba_last_error", "sba_version", "sba_problem_create", "sba_problem_destroy", "sba_problem_set_allreduce",
-    "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve",
+    "sba_last_error", "sba_version", "sba_problem_create", "sba_problem_destroy", "sba_release_cached_memory", "sba_problem_set_allreduce",
+    "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve", "sba_solve_errors",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",

@@ -16,6 +16,7 @@ libsba_b200.so.  There is no scipy call and no CPU fallback on this path.
 """
 import numpy as np
 
+from ._lib import SbaError
 from .solver import DeviceProblem, initial_vars
 
 
@@ -108,21 +109,20 @@ def run_ba_optimization(p, ls_params=None, verbose=False, plots=True, return_inf
     t0 = time.perf_counter()
     with DeviceProblem(p) as prob:
         t1 = time.perf_counter()
-        residuals_init, _ = prob.residuals(vars_init)
-        if not np.all(np.isfinite(residuals_init)):
-            raise ValueError("Residuals are not finite in the initial point.")
-        t2 = time.perf_counter()
-        vars_ba, residuals_ba, info = prob.solve(
-            vars_init, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"],
-            max_nfev=cfg["max_iter"], verbose=2 if cfg["verbose"] >= 2 else 0)
+        try:
+            vars_ba, err_init, err_ba, info = prob.solve_with_errors(
+                vars_init, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"],
+                max_nfev=cfg["max_iter"], verbose=2 if cfg["verbose"] >= 2 else 0)
+        except SbaError as exc:
+            if "not finite" in str(exc):      # scipy's message and exception type (least_squares.py:945-946)
+                raise ValueError("Residuals are not finite in the initial point.") from exc
+            raise
         t3 = time.perf_counter()
-    info["wall_s"] = {"create": t1 - t0, "fun": t2 - t1, "solve": t3 - t2, "destroy": time.perf_counter() - t3}
+    info["wall_s"] = {"create": t1 - t0, "fun": 0.0, "solve": t3 - t1, "destroy": time.perf_counter() - t3}
     if verbose:
         flush_print("Shape of Jacobian sparsity: {}x{}".format(2 * p.pts_ind.size, vars_init.size))
         flush_print("Optimization took {:.4f} seconds on the device ({} function evaluations)\n".format(
             info["solve_ms"] * 1e-3, info["nfev"]))
-    err_init = compute_reprojection_error(residuals_init, p.pts2d_w)
-    err_ba = compute_reprojection_error(residuals_ba, p.pts2d_w)
     if verbose:
         flush_print("Reprojection error before BA (mean / median): {:.2f} / {:.2f}".format(np.mean(err_init), np.median(err_init)))
         flush_print("Reprojection error after  BA (mean / median): {:.2f} / {:.2f}\n".format(np.mean(err_ba), np.median(err_ba)))

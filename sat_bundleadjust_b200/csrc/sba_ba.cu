@@ -16,7 +16,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "sba_comm.cuh"
 #include "sba_kernels.cuh"
@@ -39,16 +44,57 @@ static inline int grid_for(long long work, int threads, int max_blocks)
 
 // Device memory of a problem comes from a few large slabs (cudaMalloc / cudaFree of ~50 separate buffers was
 // measured at up to 0.8 s per problem on a busy box); 256-byte aligned bump allocation, freed all at once.
+// Slabs of destroyed problems are kept in a process-wide pool (up to SLAB_POOL_MAX bytes) and handed to the next
+// problem: the pipeline solves twice per run (before / after outlier removal) and cudaFree + cudaMalloc of the same
+// ~0.5 GB cost 5-25 ms per solve.  sba_release_cached_memory() empties the pool.
+struct Slab { void* ptr; size_t bytes; int device; };
+static std::mutex g_pool_mutex;
+static std::vector<Slab> g_slab_pool;
+static std::vector<double*> g_pinned_pool;          // pinned scalar blocks (SC_COUNT doubles)
+static size_t g_pool_bytes = 0;
+constexpr size_t SLAB_POOL_MAX = (size_t)16 << 30;
+
+static void* pool_take(size_t want, int device, size_t* got)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    int best = -1;
+    for (int i = 0; i < (int)g_slab_pool.size(); ++i) {
+        const Slab& c = g_slab_pool[i];
+        if (c.device != device || c.bytes < want || c.bytes > 2 * want + ((size_t)64 << 20)) continue;
+        if (best < 0 || c.bytes < g_slab_pool[best].bytes) best = i;
+    }
+    if (best < 0) return nullptr;
+    const Slab c = g_slab_pool[best];
+    g_slab_pool.erase(g_slab_pool.begin() + best);
+    g_pool_bytes -= c.bytes;
+    *got = c.bytes;
+    return c.ptr;
+}
+
+static void pool_give(void* ptr, size_t bytes, int device)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (g_pool_bytes + bytes <= SLAB_POOL_MAX) {
+            g_slab_pool.push_back({ptr, bytes, device});
+            g_pool_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
+
 static int arena_alloc(sba_problem* p, void** ptr, size_t bytes)
 {
     constexpr size_t ALIGN = 256, CHUNK_BYTES = 64u << 20;
     bytes = (bytes + ALIGN - 1) / ALIGN * ALIGN;
     if (bytes == 0) bytes = ALIGN;
     if (bytes > p->arena_left) {
-        const size_t want = bytes > CHUNK_BYTES ? bytes : CHUNK_BYTES;
-        void* chunk = nullptr;
-        SBA_CUDA(cudaMalloc(&chunk, want));
+        size_t want = bytes > CHUNK_BYTES ? bytes : CHUNK_BYTES;
+        void* chunk = pool_take(want, p->device, &want);
+        if (!chunk) SBA_CUDA(cudaMalloc(&chunk, want));
         p->arena_chunks.push_back(chunk);
+        p->arena_chunk_bytes.push_back(want);
         if (bytes >= CHUNK_BYTES) { *ptr = chunk; return SBA_OK; }     // dedicated slab, keep the open chunk
         p->arena_ptr = (char*)chunk;
         p->arena_left = want;
@@ -562,15 +608,29 @@ using namespace sba;
 extern "C" const char* sba_last_error(void) { return g_error.c_str(); }
 extern "C" int sba_version(void) { return 100; }
 
+extern "C" int sba_release_cached_memory(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Slab& c : g_slab_pool) { cudaSetDevice(c.device); cudaFree(c.ptr); }
+    for (double* h : g_pinned_pool) cudaFreeHost(h);
+    g_slab_pool.clear(); g_pinned_pool.clear(); g_pool_bytes = 0;
+    cudaSetDevice(dev);
+    return SBA_OK;
+}
+
 extern "C" int sba_problem_destroy(sba_problem* p)
 {
     if (!p) return SBA_OK;
     cudaSetDevice(p->device);
-    for (void* c : p->arena_chunks) cudaFree(c);
+    if (p->stream2) cudaStreamSynchronize(p->stream2);
+    cudaStreamSynchronize(p->stream);               // nothing of this problem may still be running on the slabs
+    for (size_t i = 0; i < p->arena_chunks.size(); ++i) pool_give(p->arena_chunks[i], p->arena_chunk_bytes[i], p->device);
     for (int r = 0; r < p->world; ++r)
         if (p->comm_ready && r != p->rank && p->comm_peer[r]) cudaIpcCloseMemHandle(p->comm_peer[r]);
     if (p->comm_buf) cudaFree(p->comm_buf);
-    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->h_scal) { std::lock_guard<std::mutex> lock(g_pool_mutex); g_pinned_pool.push_back(p->h_scal); }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -587,26 +647,67 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     const int M = p->M, N = p->N, nc = p->nc;
     const int64_t K = p->K;
     cudaStream_t s = p->stream;
-    // --- indices: int64 -> int32, track offsets, camera-major order (host, O(K)) ---
+    const bool timing = getenv("SBA_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sba create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
+    // --- indices: int64 -> int32, track offsets, camera-major order (host, O(K), a few threads) ---
     std::vector<int> cam(K), pts(K), track_ptr(N + 1, 0), cam_cnt(M + 1, 0);
-    for (int64_t a = 0; a < K; ++a) {
-        const int64_t c = d->cam_ind[a], t = d->pts_ind[a];
-        if (c < 0 || c >= M || t < 0 || t >= N) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
-        if (a > 0 && t < d->pts_ind[a - 1]) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
-        cam[a] = (int)c; pts[a] = (int)t;
-        track_ptr[t + 1]++;
-        cam_cnt[c + 1]++;
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), K / 65536 + 1}));
+    std::vector<std::vector<int>> thr_cnt(nthr, std::vector<int>(M, 0));
+    std::vector<int> thr_err(nthr, 0);
+    std::vector<char> seen(N + 1, 0);
+    auto range_of = [&](int t, int64_t& a0, int64_t& a1) { a0 = K * t / nthr; a1 = K * (t + 1) / nthr; };
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; ++t)
+            th.emplace_back([&, t]() {
+                int64_t a0, a1;
+                range_of(t, a0, a1);
+                std::vector<int>& cnt = thr_cnt[t];
+                for (int64_t a = a0; a < a1; ++a) {
+                    const int64_t c = d->cam_ind[a], tr = d->pts_ind[a];
+                    if (c < 0 || c >= M || tr < 0 || tr >= N) { thr_err[t] = 1; return; }
+                    if (a > 0 && tr < d->pts_ind[a - 1]) { thr_err[t] = 2; return; }
+                    cam[a] = (int)c; pts[a] = (int)tr;
+                    cnt[c]++;
+                    // first observation of a track: its offset (pts_ind is non-decreasing, so tracks are contiguous runs)
+                    if (a == 0 || tr != d->pts_ind[a - 1]) { track_ptr[tr] = (int)a; seen[tr] = 1; }
+                }
+            });
+        for (auto& t : th) t.join();
     }
-    for (int i = 0; i < N; ++i) track_ptr[i + 1] += track_ptr[i];
-    for (int j = 0; j < M; ++j) cam_cnt[j + 1] += cam_cnt[j];
-    std::vector<int> cm_obs(K), cm_pts(K), fill(cam_cnt.begin(), cam_cnt.end() - 1);
-    std::vector<double> cm_pts2d(2 * K), cm_w(K);
-    for (int64_t a = 0; a < K; ++a) {
-        const int t = fill[cam[a]]++;
-        cm_obs[t] = (int)a; cm_pts[t] = pts[a];
-        cm_pts2d[2 * (size_t)t] = d->pts2d[2 * a]; cm_pts2d[2 * (size_t)t + 1] = d->pts2d[2 * a + 1];
-        cm_w[t] = d->pts2d_w[a];
+    for (int t = 0; t < nthr; ++t) {
+        if (thr_err[t] == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
+        if (thr_err[t] == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
     }
+    // tracks without observations take the offset of the next track that has some
+    track_ptr[N] = (int)K;
+    for (int i = N - 1; i >= 0; --i) if (!seen[i]) track_ptr[i] = track_ptr[i + 1];
+    for (int j = 0; j < M; ++j) {
+        int tot = 0;
+        for (int t = 0; t < nthr; ++t) { const int c = thr_cnt[t][j]; thr_cnt[t][j] = tot; tot += c; }   // per-thread start inside camera j
+        cam_cnt[j + 1] = cam_cnt[j] + tot;
+    }
+    std::vector<int> cm_obs(K);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; ++t)
+            th.emplace_back([&, t]() {
+                int64_t a0, a1;
+                range_of(t, a0, a1);
+                std::vector<int> fill(M);
+                for (int j = 0; j < M; ++j) fill[j] = cam_cnt[j] + thr_cnt[t][j];
+                for (int64_t a = a0; a < a1; ++a) cm_obs[fill[cam[a]]++] = (int)a;
+            });
+        for (auto& t : th) t.join();
+    }
+    stamp("host index pass");
     // chunk table (camera-major work items)
     std::vector<int> ch_cam, ch_beg, ch_end, first_chunk(M + 1, 0);
     for (int j = 0; j < M; ++j) {
@@ -645,13 +746,11 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     }
     p->n_tiles = (int)tile_obs.size() - 1;
 
+    stamp("host tables");
     SBA_TRY(dev_upload(p, &p->cam_ind, cam, s));
     SBA_TRY(dev_upload(p, &p->pts_ind, pts, s));
     SBA_TRY(dev_upload(p, &p->track_ptr, track_ptr, s));
     SBA_TRY(dev_upload(p, &p->cm_obs, cm_obs, s));
-    SBA_TRY(dev_upload(p, &p->cm_pts, cm_pts, s));
-    SBA_TRY(dev_upload(p, &p->cm_pts2d, cm_pts2d, s));
-    SBA_TRY(dev_upload(p, &p->cm_w, cm_w, s));
     SBA_TRY(dev_upload(p, &p->cam_ptr, first_chunk, s));   // camera -> first chunk (used by k_reduce_cameras)
     SBA_TRY(dev_upload(p, &p->chunks.cam, ch_cam, s));
     SBA_TRY(dev_upload(p, &p->chunks.beg, ch_beg, s));
@@ -673,10 +772,16 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         SBA_CUDA(cudaMemcpyAsync(p->rpc_tab, d->rpc_coefs, (size_t)M * RPC_TAB_STRIDE * sizeof(double),
                                  cudaMemcpyHostToDevice, s));
     }
+    // camera-major copies of the observation data: gathered on the device from the track-major arrays
+    SBA_TRY(dev_alloc(p, &p->cm_pts, (size_t)K)); SBA_TRY(dev_alloc(p, &p->cm_pts2d, 2 * (size_t)K)); SBA_TRY(dev_alloc(p, &p->cm_w, (size_t)K));
+    k_gather_camera_major<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cm_obs, p->pts_ind, (const double2*)p->pts2d, p->w, K,
+                                                                       p->cm_pts, (double2*)p->cm_pts2d, p->cm_w);
+    SBA_CUDA(cudaGetLastError());
     SBA_TRY(dev_alloc(p, &p->obs_of, (size_t)M * N));
     SBA_CUDA(cudaMemsetAsync(p->obs_of, 0xFF, (size_t)M * N * sizeof(int), s));
     k_fill_obs_of<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cam_ind, p->pts_ind, K, N, p->obs_of);
     SBA_CUDA(cudaGetLastError());
+    stamp("uploads + obs_of");
     // --- static pair lists of the Schur complement: count, scan on the host, fill ---
     {
         const int n_items = item_base.back();
@@ -722,6 +827,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         SBA_CUDA(cudaStreamSynchronize(s));   // `off` and the slice vectors go out of scope
     }
 
+    stamp("pair lists");
     // --- iteration state ---
     const size_t n = (size_t)p->n, ns = (size_t)M * nc;
     SBA_TRY(dev_alloc(p, &p->x, n)); SBA_TRY(dev_alloc(p, &p->x_new, n)); SBA_TRY(dev_alloc(p, &p->g, n));
@@ -750,14 +856,20 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));
     SBA_TRY(dev_alloc(p, &p->scal, SC_COUNT));
     SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), s));
-    SBA_CUDA(cudaMallocHost((void**)&p->h_scal, SC_COUNT * sizeof(double)));
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_pinned_pool.empty()) { p->h_scal = g_pinned_pool.back(); g_pinned_pool.pop_back(); }
+    }
+    if (!p->h_scal) SBA_CUDA(cudaMallocHost((void**)&p->h_scal, SC_COUNT * sizeof(double)));
     SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
+    SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
     SBA_CUDA(cudaEventCreate(&p->ev0));
     SBA_CUDA(cudaEventCreate(&p->ev1));
     SBA_CUDA(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     SBA_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     SBA_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     SBA_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope
+    stamp("state buffers");
     return SBA_OK;
 }
 
@@ -977,4 +1089,31 @@ extern "C" int sba_assemble_device(sba_problem* p, const double* x_dev, int32_t 
 extern "C" int sba_tr2d(const double B[4], const double g[2], double Delta, double p_out[2])
 {
     return sba::solve_trust_region_2d(B[0], B[1], B[3], g[0], g[1], Delta, p_out) ? 1 : 0;
+}
+
+// sba_solve plus the two per-observation error vectors the reference's driver returns (ba_core.py:304-305), computed
+// on the device: err_init at x0, err at the solution (K doubles each, either may be NULL).
+extern "C" int sba_solve_errors(sba_problem* p, const double* x0, const sba_solve_opts* opts, double* x, double* err_init,
+                                double* err, sba_solve_info* info)
+{
+    if (!p || !x0 || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    const int grid = grid_for(p->K, 256, NUM_SMS * 8);
+    SBA_CUDA(cudaMemcpyAsync(p->io_x, x0, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (err_init) {
+        SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
+        SBA_TRY(run_residual(p, p->io_x, p->camrec_new, SBA_LOSS_LINEAR, 1.0, p->r_out, SC_SCRATCH, p->rpc_f32));
+        k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)p->r_out, p->w, p->K, p->err_out);
+        SBA_TRY(check_launch(p));
+        SBA_CUDA(cudaMemcpyAsync(err_init, p->err_out, (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    SBA_TRY(sba_solve_device(p, p->io_x, opts, nullptr, err ? p->r_out : nullptr, info));
+    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (err) {
+        k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)p->r_out, p->w, p->K, p->err_out);
+        SBA_TRY(check_launch(p));
+        SBA_CUDA(cudaMemcpyAsync(err, p->err_out, (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
 }

@@ -121,6 +121,7 @@ struct sba_problem {
     double* scal = nullptr;          // device scalar block
     double* h_scal = nullptr;        // pinned host mirror
     double* r_out = nullptr;         // (2K) residual output buffer
+    double* err_out = nullptr;       // (K) per-observation reprojection errors (sba_solve_errors)
     double *io_x = nullptr;          // (n) staging for host-pointer entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
@@ -134,6 +135,7 @@ struct sba_problem {
     unsigned long long comm_seq = 0;
     bool comm_ready = false;
     std::vector<void*> arena_chunks;         // device slabs owned by this problem
+    std::vector<size_t> arena_chunk_bytes;
     char* arena_ptr = nullptr;
     size_t arena_left = 0;
     void* flush_buf = nullptr;

@@ -236,6 +236,19 @@ k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict_
     grid_sum_finalize<1, 256>(tot, partials, counter, scal, slots, sm);
 }
 
+// un-weighted reprojection error of every observation, err_k = |(r_2k, r_2k+1) / w_k|_2  (ba_core.py:335-349);
+// individually rounded operations in numpy's order, so the values equal the host expression bit for bit
+__global__ void k_reproj_error(const double2* __restrict__ r, const double* __restrict__ w, long long K,
+                               double* __restrict__ err)
+{
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
+        const double2 f = r[a];
+        const double wa = w[a];
+        const double q0 = __ddiv_rn(f.x, wa), q1 = __ddiv_rn(f.y, wa);
+        err[a] = __dsqrt_rn(__dadd_rn(__dmul_rn(q0, q0), __dmul_rn(q1, q1)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // G2a: point side of the assembly -- V_i = sum Jp^T Jp, g_p = sum Jp^T f.
 // One observation per lane (coalesced index / observation loads, no divergence in the Jacobian); the 9 sums
@@ -1115,6 +1128,17 @@ __global__ void k_jac_blocks(ObsArrays o, const double* __restrict__ xp, const d
 }
 
 // scatter for obs_of[M][N]
+// camera-major copies (static) of the per-observation data, from the camera-major permutation cm_obs
+__global__ void k_gather_camera_major(const int* __restrict__ cm_obs, const int* __restrict__ pts_ind,
+                                      const double2* __restrict__ pts2d, const double* __restrict__ w, long long K,
+                                      int* __restrict__ cm_pts, double2* __restrict__ cm_pts2d, double* __restrict__ cm_w)
+{
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < K; t += (long long)gridDim.x * blockDim.x) {
+        const int a = cm_obs[t];
+        cm_pts[t] = pts_ind[a]; cm_pts2d[t] = pts2d[a]; cm_w[t] = w[a];
+    }
+}
+
 __global__ void k_fill_obs_of(const int* __restrict__ cam_ind, const int* __restrict__ pts_ind, long long K, int N,
                               int* __restrict__ obs_of)
 {

@@ -89,26 +89,20 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         if os.environ.get("SBA_COMM", "peer") == "peer":
             prob.connect_peers(gather_obj)
         xl0 = local_vars(x0, ncv, ranges[rank])
-        r0, _ = prob.residuals(xl0)
-        xl, rl, info = prob.solve(xl0, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"],
-                                  max_nfev=cfg["max_iter"])
+        xl, e0, e1, info = prob.solve_with_errors(xl0, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"],
+                                                  xtol=cfg["xtol"], max_nfev=cfg["max_iter"])
         dist.barrier(group=group)                      # peers keep reading each other's buffers until everybody is done
-    # gather the pieces (variable-length -> pad to the longest shard)
-    def gather(v):
-        size = torch.tensor([v.size], dtype=torch.int64, device="cuda")
-        dist.all_reduce(size, op=dist.ReduceOp.MAX, group=group)
-        buf = torch.zeros(int(size.item()), dtype=torch.float64, device="cuda")
-        buf[: v.size] = torch.from_numpy(v).cuda()
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf, group=group)
-        return [o.cpu().numpy() for o in out]
-
-    xs = gather(xl)
-    x = merge_vars([xs[r][: ncv + 3 * (ranges[r][1] - ranges[r][0])] for r in range(world)], ncv)
+    # one all-gather of [x_local | err_init | err] per rank (variable length -> padded to the longest shard)
     a = [np.searchsorted(p.pts_ind, [t0, t1]) for t0, t1 in ranges]
-    rs0, rs1 = gather(r0), gather(rl)
-    res0 = np.concatenate([rs0[r][: 2 * (a[r][1] - a[r][0])] for r in range(world)])
-    res1 = np.concatenate([rs1[r][: 2 * (a[r][1] - a[r][0])] for r in range(world)])
-    err0 = ba_core.compute_reprojection_error(res0, p.pts2d_w)
-    err1 = ba_core.compute_reprojection_error(res1, p.pts2d_w)
+    n_loc = [ncv + 3 * (t1 - t0) for t0, t1 in ranges]
+    k_loc = [int(a1 - a0) for a0, a1 in a]
+    longest = max(n + 2 * k for n, k in zip(n_loc, k_loc))
+    buf = torch.zeros(longest, dtype=torch.float64, device="cuda")
+    buf[: n_loc[rank] + 2 * k_loc[rank]] = torch.from_numpy(np.concatenate([xl, e0, e1])).cuda()
+    out = torch.empty((world, longest), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.cpu().numpy()
+    x = merge_vars([out[r, : n_loc[r]] for r in range(world)], ncv)
+    err0 = np.concatenate([out[r, n_loc[r]: n_loc[r] + k_loc[r]] for r in range(world)])
+    err1 = np.concatenate([out[r, n_loc[r] + k_loc[r]: n_loc[r] + 2 * k_loc[r]] for r in range(world)])
     return x0, x, err0, err1, info["nfev"], info

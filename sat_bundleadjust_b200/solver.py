@@ -199,6 +199,19 @@ class DeviceProblem:
             x = self._from_device_layout(x)
         return x, r, info.as_dict()
 
+    def solve_with_errors(self, x0, **kw):
+        """The end-to-end call of ba_core.run_ba_optimization: x, err_init, err (un-weighted pixel errors, computed on the device)."""
+        x0 = self._vars(x0)
+        x = np.empty_like(x0)
+        err_init, err = np.empty(self.n_obs), np.empty(self.n_obs)
+        info = SolveInfo()
+        opts = self.make_opts(**kw)
+        check(self.lib.sba_solve_errors(self.handle, dptr(x0), ctypes.byref(opts), dptr(x), dptr(err_init), dptr(err),
+                                        ctypes.byref(info)))
+        if self.n_common:
+            x = self._from_device_layout(x)
+        return x, err_init, err, info.as_dict()
+
     def solve_device(self, x0_ptr, x_ptr=None, r_ptr=None, **kw):
         """Device pointers (ints) in and out (device layout); nothing but the steering scalars crosses PCIe."""
         info = SolveInfo()
