@@ -288,9 +288,13 @@ static int allreduce_any(sba_problem* p, double* buf, long long count)
         c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
         const unsigned long long seq = ++p->comm_seq;
         const int grid = grid_for(count, 256, 16);
-        k_comm_push<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->counters + 8);
-        SBA_TRY(check_launch(p));
-        k_comm_pull<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->scal);
+        if (p->comm_split) {        // SBA_COMM_SPLIT=1: the two-launch form (push, then pull)
+            k_comm_push<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->counters + 8);
+            SBA_TRY(check_launch(p));
+            k_comm_pull<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->scal);
+            return check_launch(p);
+        }
+        k_comm_allreduce<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->counters + 8, p->scal);
         return check_launch(p);
     }
     if (!p->allreduce || p->allreduce(p->allreduce_user, buf, count) != 0) {
@@ -906,6 +910,7 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
     if (const char* e = getenv("SBA_ALGEBRAIC_SUBSPACE")) p->algebraic_subspace = atoi(e);
+    if (const char* e = getenv("SBA_COMM_SPLIT")) p->comm_split = atoi(e) != 0;
     const int rc = problem_create_impl(p, d);
     if (rc != SBA_OK) { sba_problem_destroy(p); return rc; }
     *out = p;

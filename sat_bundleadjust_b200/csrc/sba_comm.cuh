@@ -87,4 +87,46 @@ k_comm_pull(CommView c, double* __restrict__ dst, long long count, unsigned long
     }
 }
 
+// push + pull in ONE launch (the exchanges are latency: every launch saved is ~5 us of a ~20 us exchange).  The grid
+// is at most 16 CTAs, all resident, so a CTA may spin on the peers' flags while its siblings are still pushing; the
+// peers publish their flags independently of us, so there is no circular wait.  In place: buf -> own slot -> sum -> buf.
+__global__ void __launch_bounds__(256)
+k_comm_allreduce(CommView c, double* __restrict__ buf, long long count, unsigned long long seq, unsigned* counter, double* scal)
+{
+    const int parity = (int)(seq & 1ull);
+    double* mine = c.data[c.me] + (long long)parity * c.cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        mine[i] = buf[i];
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    __shared__ int ok;
+    if (threadIdx.x == 0) { last = (atomicAdd(counter, 1u) == gridDim.x - 1); ok = 1; }
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < c.world && threadIdx.x != c.me)
+            st_release_sys(c.flag[threadIdx.x] + parity * COMM_MAX_RANKS + c.me, seq);
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+    if (threadIdx.x < c.world && threadIdx.x != c.me) {
+        const unsigned long long* f = c.flag[c.me] + parity * COMM_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 4000000000LL) { ok = 0; break; }     // ~2 s: a peer is gone; report instead of hanging
+        }
+    }
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) scal[SC_COMM_FAIL] = 1.0;
+        return;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < c.world; ++r)
+            acc += (r == c.me) ? mine[i] : ld_volatile_f64(c.data[r] + (long long)parity * c.cap + i);
+        buf[i] = acc;
+    }
+}
+
 }  // namespace sba

@@ -112,6 +112,7 @@ struct sba_problem {
     double *V = nullptr, *F = nullptr, *q = nullptr, *Z = nullptr;
     double *camsys_local = nullptr, *camsys = nullptr;     // [U (M*nc*nc) | g_c (M*nc)]
     double *S = nullptr;                                   // [S (ns*ns) | rhs (ns)], ns = M*nc
+    bool comm_split = false;                               // two-launch all-reduce (push, pull) instead of the fused kernel
     int n_common = 0;                                      // COMMON_K: trailing per-camera variables shared by all cameras
     double *cvec = nullptr;                                // 3 * ns: camera parts of delta, t1, t2 with the shared slots expanded
     double *chol_work = nullptr;                           // 34*(ns+32) scratch of the blocked factorisation
