@@ -59,6 +59,24 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(phase, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's main kernel, from the committed summary of one
+    `ncu --set full` capture of this workload (profiles/r01_ncu_full_selected_metrics.csv); None when there is none."""
+    main_kernel = {"schur": "k_schur<", "assemble": "k_assemble_points<", "point_prep": "k_point_prep<", "backsub": "k_backsub<",
+                   "cholesky": "k_chol_fused<", "scale_jvp": "k_jvp<1, 6, 1>", "subspace": "k_jvp<1, 6, 2>",
+                   "step_eval": "k_residual<"}.get(phase)
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_selected_metrics.csv")
+    if workload != "cfg2" or main_kernel is None or not os.path.exists(path):
+        return None, None
+    import csv
+    with open(path) as f:
+        for row in csv.DictReader(f):
+            if row["kernel"].startswith(main_kernel):
+                return (float(row["dram rd MB"]) + float(row["dram wr MB"])) * 1e6, \
+                    "profiles/r01_ncu_full_selected_metrics.csv (%s, one ncu --set full capture, cold L2)" % row["kernel"]
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples during the timed region (recipe of B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -334,6 +352,7 @@ def run_b200_arm(args):
         K_loc, N_loc = prob.n_obs, prob.n_pts
         ab = algorithmic_bytes(K_loc, N_loc, M, c)
         dominant = max(phase_ms, key=lambda k: phase_ms[k])
+        traffic, traffic_src = ncu_traffic(dominant, args.workload)
         roof_all = {k: {"ms": phase_ms[k], "algorithmic_bytes": ab[k],
                         "achieved_GBps": ab[k] / (phase_ms[k] * 1e-3) / 1e9 if phase_ms[k] > 0 else None}
                     for k in phase_ms}
@@ -353,19 +372,19 @@ def run_b200_arm(args):
             "jacobian_pass_ms": jac_ms_mean,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(info["gpu_launches"]),
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "jacobian_assembly": {"achieved": jac_ach, "frac": jac_ach / peak, "ms": jac_ms_mean,
                                                "algorithmic_bytes": ab["assemble"]}},
             "phases_ms_per_iteration": phase_ms, "phases": roof_all,
         }
         if world == 1 and not args.no_cpu_baseline:
             q = p
-            sec_it, done, _ = cpu_reference_iterations(q, 3, 0)
-            line["cpu_baseline"] = {"value": q.n_obs / sec_it, "unit": "obs*it/s", "cores": os.cpu_count() or 1, "kind": "port",
+            sec_it, done, _ = cpu_reference_iterations(q, 3, 1)
+            line["cpu_baseline"] = {"value": q.n_obs / sec_it, "unit": "obs*it/s", "cores": 1, "kind": "port",
                                     "lm_iters_per_s": 1.0 / sec_it,
-                                    "sample": "3 TRF iterations of scipy least_squares (2-point sparse differences + LSMR) "
-                                              "on the full workload, 1 of %d host cores (the path is single-threaded)"
-                                              % (os.cpu_count() or 1)}
+                                    "sample": "3 TRF iterations (after 1 warm-up iteration) of scipy least_squares (2-point "
+                                              "sparse differences + LSMR) on the full workload; the path is single-threaded "
+                                              "numpy / scipy.sparse (%d host cores present)" % (os.cpu_count() or 1)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()      # peers may still be reading this rank's exchange buffer
