@@ -70,6 +70,7 @@ typedef struct sba_solve_opts {
     int32_t timed_from;       /* iter_ms / phase_ms accumulate over iterations >= timed_from */
     int64_t l2_flush_bytes;   /* > 0: overwrite a scratch buffer of this size between iterations, outside
                                  the per-iteration event pairs, so that every timed iteration starts L2-cold */
+    int32_t no_phase_timing;  /* 1: time whole iterations only (two events per iteration instead of ~18) */
 } sba_solve_opts;
 
 /* phases of one trust-region iteration, for sba_solve_info.phase_ms */

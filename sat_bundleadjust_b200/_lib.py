@@ -37,7 +37,7 @@ class SolveOpts(ctypes.Structure):
     _fields_ = [("loss", ctypes.c_int32), ("f_scale", ctypes.c_double), ("ftol", ctypes.c_double),
                 ("xtol", ctypes.c_double), ("gtol", ctypes.c_double), ("max_nfev", ctypes.c_int32),
                 ("verbose", ctypes.c_int32), ("max_iterations", ctypes.c_int32), ("timed_from", ctypes.c_int32),
-                ("l2_flush_bytes", ctypes.c_int64)]
+                ("l2_flush_bytes", ctypes.c_int64), ("no_phase_timing", ctypes.c_int32)]
 
 
 class SolveInfo(ctypes.Structure):

@@ -390,11 +390,11 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
     p->schur_partials, p->sb_first, p->sb_j, p->sb_jp, p->M, p->n_cam_fix, p->camsys_local, p->sinv, p->scal,           \
         p->rank == 0, p->n_common, p->S
         switch (p->nc) {
-        case 3: k_schur_finalize<3><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
-        case 5: k_schur_finalize<5><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
-        case 6: k_schur_finalize<6><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
-        case 8: k_schur_finalize<8><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
-        default: k_schur_finalize<11><<<p->n_schur_blocks, 128, 0, p->stream>>>(FIN_ARGS); break;
+        case 3: k_schur_finalize<3><<<p->n_schur_blocks, 256, 0, p->stream>>>(FIN_ARGS); break;
+        case 5: k_schur_finalize<5><<<p->n_schur_blocks, 256, 0, p->stream>>>(FIN_ARGS); break;
+        case 6: k_schur_finalize<6><<<p->n_schur_blocks, 256, 0, p->stream>>>(FIN_ARGS); break;
+        case 8: k_schur_finalize<8><<<p->n_schur_blocks, 256, 0, p->stream>>>(FIN_ARGS); break;
+        default: k_schur_finalize<11><<<p->n_schur_blocks, 256, 0, p->stream>>>(FIN_ARGS); break;
         }
         SBA_TRY(check_launch(p));
 #undef FIN_ARGS
@@ -514,7 +514,8 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     while (true) {
         if (o->max_iterations > 0 && iteration >= o->max_iterations) break;
         if (nfev >= o->max_nfev) break;
-        tm.on = it_tm.on = iteration >= o->timed_from && (o->timed_from > 0 || o->l2_flush_bytes > 0 || o->max_iterations > 0);
+        it_tm.on = iteration >= o->timed_from && (o->timed_from > 0 || o->l2_flush_bytes > 0 || o->max_iterations > 0);
+        tm.on = it_tm.on && !o->no_phase_timing;     // the ~16 extra event records per iteration cost ~1 us each on the stream
         if (o->l2_flush_bytes > 0)
             SBA_CUDA(cudaMemsetAsync(p->flush_buf, iteration & 0xff, (size_t)o->l2_flush_bytes, p->stream));
         it_tm.begin(-1);

@@ -216,18 +216,34 @@ k_residual(ObsArrays o, const double* __restrict__ xp, const double* __restrict_
 {
     __shared__ double sm[1 * (256 / 32)];
     double acc[1] = {0.0};
-    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < K; a += (long long)gridDim.x * blockDim.x) {
-        const int j = o.cam_ind[a], i = o.pts_ind[a];
-        const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
-        const double X = xp[3 * (size_t)i], Y = xp[3 * (size_t)i + 1], Z = xp[3 * (size_t)i + 2];
-        double u, v;
-        project<MODEL>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, X, Y, Z, u, v);
-        if (MODEL == MODEL_RPC && rpc_f32) { u = (double)(float)u; v = (double)(float)v; }
-        const double2 ob = o.pts2d[a];
-        const double w = o.w[a];
-        const double f0 = w * (u - ob.x), f1 = w * (v - ob.y);
-        if (r_out) r_out[a] = make_double2(f0, f1);
-        acc[0] += loss_cost(loss, f0, f_scale) + loss_cost(loss, f1, f_scale);
+    // two observations per trip, all their loads requested before either is used: at ~1.6 observations per resident thread
+    // the kernel is a chain of dependent memory round trips (index -> point -> result), not a bandwidth problem
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long a0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; a0 < K; a0 += 2 * stride) {
+        const long long a1 = a0 + stride;
+        const bool two = a1 < K;
+        const long long b = two ? a1 : a0;
+        const int j0 = o.cam_ind[a0], i0 = o.pts_ind[a0], j1 = o.cam_ind[b], i1 = o.pts_ind[b];
+        const double2 ob0 = o.pts2d[a0], ob1 = o.pts2d[b];
+        const double w0 = o.w[a0], w1 = o.w[b];
+        const double X0 = xp[3 * (size_t)i0], Y0 = xp[3 * (size_t)i0 + 1], Z0 = xp[3 * (size_t)i0 + 2];
+        const double X1 = xp[3 * (size_t)i1], Y1 = xp[3 * (size_t)i1 + 1], Z1 = xp[3 * (size_t)i1 + 2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const long long a = h ? a1 : a0;
+            const int j = h ? j1 : j0;
+            const CamRec c = load_camrec(camrec + (size_t)j * CAMREC_STRIDE);
+            double u, v;
+            project<MODEL>(c, MODEL == MODEL_RPC ? rpc_tab + (size_t)j * RPC_TAB_STRIDE : nullptr, h ? X1 : X0, h ? Y1 : Y0,
+                           h ? Z1 : Z0, u, v);
+            if (MODEL == MODEL_RPC && rpc_f32) { u = (double)(float)u; v = (double)(float)v; }
+            const double2 ob = h ? ob1 : ob0;
+            const double w = h ? w1 : w0;
+            const double f0 = w * (u - ob.x), f1 = w * (v - ob.y);
+            if (r_out) r_out[a] = make_double2(f0, f1);
+            acc[0] += loss_cost(loss, f0, f_scale) + loss_cost(loss, f1, f_scale);
+        }
     }
     const double tot = block_reduce_sum<1, 256>(acc, sm);
     __shared__ int slots[1];
@@ -813,39 +829,54 @@ k_schur(const int* __restrict__ slice_block, const int* __restrict__ slice_p0, c
 // one block per (j, j') block: S_jj' = [j==j'] (U_j + reg diag(sinv_c^2)) - sum over the block's slices ;
 // rhs_j = -g_j + sum.  One warp per value: lanes stride over the slices, fixed-shape shuffle tree -> deterministic.
 template <int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_schur_finalize(const double* __restrict__ schur_partials, const int* __restrict__ sb_first,
                  const int* __restrict__ sb_j, const int* __restrict__ sb_jp, int M, int n_cam_fix,
                  const double* __restrict__ camsys_local, const double* __restrict__ sinv,
                  const double* __restrict__ scal, int add_diag, int n_common, double* __restrict__ S)
 {
-    constexpr int NVALL = NC * NC + NC;
+    constexpr int NVALL = NC * NC + NC, NW = 8, G = 4;      // 8 warps, 4 values per warp in flight
     const double reg = scal[SC_REG];
     const int blk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = sb_j[blk], jp = sb_jp[blk];
     const int ns = M * NC;
     const int s0 = sb_first[blk], s1 = sb_first[blk + 1];
-    for (int k = warp; k < NVALL; k += 4) {
-        double s = 0.0;
-        for (int sl = s0 + lane; sl < s1; sl += 32) s += schur_partials[(size_t)sl * NVALL + k];
+    for (int k0 = warp; k0 < NVALL; k0 += NW * G) {
+        double sum[G];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane != 0) continue;
-        if (k < NC * NC) {
-            const int r = k / NC, c = k % NC;
-            double val = -s;
-            if (j == jp) {
-                val += camsys_local[(size_t)j * NC * NC + r * NC + c];
-                if (r == c && add_diag && !(j > 0 && r >= NC - n_common)) {      // unused shared slots: see k_fold_common
-                    const double si = sinv[(size_t)j * NC + r];
-                    val += (j < n_cam_fix) ? 1.0 : reg * si * si;
-                }
+        for (int u = 0; u < G; ++u) sum[u] = 0.0;
+        for (int sl = s0 + lane; sl < s1; sl += 32)
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const int k = k0 + NW * u;
+                if (k < NVALL) sum[u] += schur_partials[(size_t)sl * NVALL + k];
             }
-            S[(size_t)(j * NC + r) + (size_t)(jp * NC + c) * ns] = val;
-            if (j != jp) S[(size_t)(jp * NC + c) + (size_t)(j * NC + r) * ns] = val;
-        } else if (j == jp) {
-            const int r = k - NC * NC;
-            S[(size_t)ns * ns + (size_t)j * NC + r] = -camsys_local[(size_t)M * NC * NC + (size_t)j * NC + r] + s;
+#pragma unroll
+        for (int u = 0; u < G; ++u)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+        if (lane != 0) continue;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const int k = k0 + NW * u;
+            if (k >= NVALL) continue;
+            const double s = sum[u];
+            if (k < NC * NC) {
+                const int r = k / NC, c = k % NC;
+                double val = -s;
+                if (j == jp) {
+                    val += camsys_local[(size_t)j * NC * NC + r * NC + c];
+                    if (r == c && add_diag && !(j > 0 && r >= NC - n_common)) {      // unused shared slots: see k_fold_common
+                        const double si = sinv[(size_t)j * NC + r];
+                        val += (j < n_cam_fix) ? 1.0 : reg * si * si;
+                    }
+                }
+                S[(size_t)(j * NC + r) + (size_t)(jp * NC + c) * ns] = val;
+                if (j != jp) S[(size_t)(jp * NC + c) + (size_t)(j * NC + r) * ns] = val;
+            } else if (j == jp) {
+                const int r = k - NC * NC;
+                S[(size_t)ns * ns + (size_t)j * NC + r] = -camsys_local[(size_t)M * NC * NC + (size_t)j * NC + r] + s;
+            }
         }
     }
 }

@@ -179,11 +179,12 @@ class DeviceProblem:
 
     @staticmethod
     def make_opts(loss="linear", f_scale=1.0, ftol=1e-4, xtol=1e-10, gtol=1e-8, max_nfev=300, verbose=0,
-                  max_iterations=0, timed_from=0, l2_flush_bytes=0):
+                  max_iterations=0, timed_from=0, l2_flush_bytes=0, no_phase_timing=0):
         o = SolveOpts()
         o.loss, o.f_scale, o.ftol, o.xtol, o.gtol = LOSS_IDS[loss], f_scale, ftol, xtol, gtol
         o.max_nfev, o.verbose = int(max_nfev), int(verbose)
         o.max_iterations, o.timed_from, o.l2_flush_bytes = int(max_iterations), int(timed_from), int(l2_flush_bytes)
+        o.no_phase_timing = int(no_phase_timing)
         return o
 
     def solve(self, x0, want_residuals=True, **kw):
