@@ -96,7 +96,8 @@ typedef struct sba_solve_info {
     int32_t timed_iterations; /* iterations that contributed to iter_ms / phase_ms */
     double iter_ms;           /* sum of per-iteration device times (CUDA events) over the timed iterations */
     double phase_ms[8];       /* the same, split by phase (SBA_PH_*) */
-    int32_t explicit_subspace_passes; /* iterations that needed the explicit J*[t1 t2] pass */
+    int32_t explicit_subspace_passes; /* iterations that ran the explicit J*[t1 t2] pass (= all of them: the algebraic
+                                         shortcut through the normal equations cancels catastrophically) */
 } sba_solve_info;
 
 /* Optional hook for the multi-GPU exchange step: must SUM `count` doubles at device pointer `buf`

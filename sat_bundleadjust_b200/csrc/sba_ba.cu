@@ -910,7 +910,6 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
-    if (const char* e = getenv("SBA_ALGEBRAIC_SUBSPACE")) p->algebraic_subspace = atoi(e);
     if (const char* e = getenv("SBA_COMM_SPLIT")) p->comm_split = atoi(e) != 0;
     const int rc = problem_create_impl(p, d);
     if (rc != SBA_OK) { sba_problem_destroy(p); return rc; }

@@ -116,7 +116,6 @@ struct sba_problem {
     int n_common = 0;                                      // COMMON_K: trailing per-camera variables shared by all cameras
     double *cvec = nullptr;                                // 3 * ns: camera parts of delta, t1, t2 with the shared slots expanded
     double *chol_work = nullptr;                           // 34*(ns+32) scratch of the blocked factorisation
-    int algebraic_subspace = 0;                            // 1: experimental B_S from normal-equation identities
     double *cam_partials = nullptr, *schur_partials = nullptr, *red_partials = nullptr;
     unsigned* counters = nullptr;
     double* scal = nullptr;          // device scalar block
