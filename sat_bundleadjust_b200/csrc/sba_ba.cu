@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "sba_comm.cuh"
+#include "sba_index.h"
 #include "sba_kernels.cuh"
 #include "sba_tr2d.h"
 
@@ -661,67 +662,15 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         fprintf(stderr, "[sba create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
-    // --- indices: int64 -> int32, track offsets, camera-major order (host, O(K), a few threads) ---
-    std::vector<int> cam(K), pts(K), track_ptr(N + 1, 0), cam_cnt(M + 1, 0);
-    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), K / 65536 + 1}));
-    std::vector<std::vector<int>> thr_cnt(nthr, std::vector<int>(M, 0));
-    std::vector<int> thr_err(nthr, 0);
-    std::vector<char> seen(N + 1, 0);
-    auto range_of = [&](int t, int64_t& a0, int64_t& a1) { a0 = K * t / nthr; a1 = K * (t + 1) / nthr; };
-    {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthr; ++t)
-            th.emplace_back([&, t]() {
-                int64_t a0, a1;
-                range_of(t, a0, a1);
-                std::vector<int>& cnt = thr_cnt[t];
-                for (int64_t a = a0; a < a1; ++a) {
-                    const int64_t c = d->cam_ind[a], tr = d->pts_ind[a];
-                    if (c < 0 || c >= M || tr < 0 || tr >= N) { thr_err[t] = 1; return; }
-                    if (a > 0 && tr < d->pts_ind[a - 1]) { thr_err[t] = 2; return; }
-                    cam[a] = (int)c; pts[a] = (int)tr;
-                    cnt[c]++;
-                    // first observation of a track: its offset (pts_ind is non-decreasing, so tracks are contiguous runs)
-                    if (a == 0 || tr != d->pts_ind[a - 1]) { track_ptr[tr] = (int)a; seen[tr] = 1; }
-                }
-            });
-        for (auto& t : th) t.join();
-    }
-    for (int t = 0; t < nthr; ++t) {
-        if (thr_err[t] == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
-        if (thr_err[t] == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
-    }
-    // tracks without observations take the offset of the next track that has some
-    track_ptr[N] = (int)K;
-    for (int i = N - 1; i >= 0; --i) if (!seen[i]) track_ptr[i] = track_ptr[i + 1];
-    for (int j = 0; j < M; ++j) {
-        int tot = 0;
-        for (int t = 0; t < nthr; ++t) { const int c = thr_cnt[t][j]; thr_cnt[t][j] = tot; tot += c; }   // per-thread start inside camera j
-        cam_cnt[j + 1] = cam_cnt[j] + tot;
-    }
-    std::vector<int> cm_obs(K);
-    {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthr; ++t)
-            th.emplace_back([&, t]() {
-                int64_t a0, a1;
-                range_of(t, a0, a1);
-                std::vector<int> fill(M);
-                for (int j = 0; j < M; ++j) fill[j] = cam_cnt[j] + thr_cnt[t][j];
-                for (int64_t a = a0; a < a1; ++a) cm_obs[fill[cam[a]]++] = (int)a;
-            });
-        for (auto& t : th) t.join();
-    }
+    // --- indices: int64 -> int32, track offsets, camera-major order, chunks, warp tiles (host, O(K), a few threads) ---
+    HostIndex hidx;
+    const int irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx);
+    if (irc == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
+    if (irc == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
+    std::vector<int>&cam = hidx.cam, &pts = hidx.pts, &track_ptr = hidx.track_ptr, &cm_obs = hidx.cm_obs;
+    std::vector<int>&ch_cam = hidx.ch_cam, &ch_beg = hidx.ch_beg, &ch_end = hidx.ch_end, &first_chunk = hidx.first_chunk;
+    std::vector<int>& tile_obs = hidx.tile_obs;
     stamp("host index pass");
-    // chunk table (camera-major work items)
-    std::vector<int> ch_cam, ch_beg, ch_end, first_chunk(M + 1, 0);
-    for (int j = 0; j < M; ++j) {
-        first_chunk[j] = (int)ch_cam.size();
-        for (int b = cam_cnt[j]; b < cam_cnt[j + 1]; b += CHUNK) {
-            ch_cam.push_back(j); ch_beg.push_back(b); ch_end.push_back(std::min(b + CHUNK, cam_cnt[j + 1]));
-        }
-    }
-    first_chunk[M] = (int)ch_cam.size();
     p->chunks.n = (int)ch_cam.size();
     p->chunks.h_cam = ch_cam;
     p->chunks.h_first_of_cam = first_chunk;
@@ -735,22 +684,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         for (int jp = j; jp < M; ++jp) { sb_j.push_back(j); sb_jp.push_back(jp); }
     p->n_schur_items = item_base.back();
     p->n_schur_blocks = (int)sb_j.size();
-    // warp tiles: runs of whole tracks with <= 32 observations; a longer track is a tile of its own
-    std::vector<int> tile_obs;
-    tile_obs.push_back(0);
-    {
-        int cur = 0;   // observations in the open tile
-        for (int i = 0; i < N; ++i) {
-            const int L = track_ptr[i + 1] - track_ptr[i];
-            if (L == 0) continue;
-            if (cur > 0 && cur + L > 32) { tile_obs.push_back(track_ptr[i]); cur = 0; }
-            cur += L;
-            if (cur >= 32) { tile_obs.push_back(track_ptr[i + 1]); cur = 0; }
-        }
-        if (cur > 0) tile_obs.push_back(track_ptr[N]);
-    }
     p->n_tiles = (int)tile_obs.size() - 1;
-
     stamp("host tables");
     SBA_TRY(dev_upload(p, &p->cam_ind, cam, s));
     SBA_TRY(dev_upload(p, &p->pts_ind, pts, s));

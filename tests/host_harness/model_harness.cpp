@@ -2,6 +2,7 @@
 // the analytic Jacobians can be checked on a machine without a GPU.  Not part of the product library.
 #include "../../sat_bundleadjust_b200/csrc/sba_models.cuh"
 #include "../../sat_bundleadjust_b200/csrc/sba_tr2d.h"
+#include "../../sat_bundleadjust_b200/csrc/sba_index.h"
 
 using namespace sba;
 
@@ -67,6 +68,25 @@ double hh_loss_rescale(int loss, double f_scale, double f, double* f_out, double
 int hh_tr2d(const double* B, const double* g, double Delta, double* p)
 {
     return solve_trust_region_2d(B[0], B[1], B[3], g[0], g[1], Delta, p) ? 1 : 0;
+}
+
+// host index construction of a problem (csrc/sba_index.h): sizes first (pass NULL outputs), then the arrays
+int hh_host_index(const long long* cam_ind, const long long* pts_ind, long long K, int M, int N, int chunk, int max_threads,
+                  int* sizes /* [n_chunks, n_tiles+1] */, int* cam, int* pts, int* track_ptr, int* cam_cnt, int* cm_obs,
+                  int* ch_cam, int* ch_beg, int* ch_end, int* first_chunk, int* tile_obs)
+{
+    HostIndex h;
+    const int rc = build_host_index((const int64_t*)cam_ind, (const int64_t*)pts_ind, K, M, N, chunk, max_threads, h);
+    if (rc) return rc;
+    sizes[0] = (int)h.ch_cam.size(); sizes[1] = (int)h.tile_obs.size();
+    if (!cam) return 0;
+    std::copy(h.cam.begin(), h.cam.end(), cam); std::copy(h.pts.begin(), h.pts.end(), pts);
+    std::copy(h.track_ptr.begin(), h.track_ptr.end(), track_ptr); std::copy(h.cam_cnt.begin(), h.cam_cnt.end(), cam_cnt);
+    std::copy(h.cm_obs.begin(), h.cm_obs.end(), cm_obs);
+    std::copy(h.ch_cam.begin(), h.ch_cam.end(), ch_cam); std::copy(h.ch_beg.begin(), h.ch_beg.end(), ch_beg);
+    std::copy(h.ch_end.begin(), h.ch_end.end(), ch_end); std::copy(h.first_chunk.begin(), h.first_chunk.end(), first_chunk);
+    std::copy(h.tile_obs.begin(), h.tile_obs.end(), tile_obs);
+    return 0;
 }
 
 }

@@ -307,3 +307,66 @@ def test_robust_rescale_matches_scipy(built, loss):
         assert np.isclose(s, exp_scale[i], rtol=1e-10, atol=0)
         assert np.isclose(fo.value, exp_f[i], rtol=1e-10, atol=1e-300)
         assert np.isclose(co.value, exp_cost[i], rtol=1e-10, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host index construction of a device problem (csrc/sba_index.h), compiled into the host harness
+# ---------------------------------------------------------------------------------------------------
+def _host_index(cam_ind, pts_ind, M, N, chunk=1024, threads=8):
+    lib = _harness()
+    ip, lp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)
+    cam_ind, pts_ind = np.ascontiguousarray(cam_ind, dtype=np.int64), np.ascontiguousarray(pts_ind, dtype=np.int64)
+    K = cam_ind.size
+    sizes = np.zeros(2, dtype=np.int32)
+    null = ctypes.cast(None, ip)
+    args = [cam_ind.ctypes.data_as(lp), pts_ind.ctypes.data_as(lp), ctypes.c_longlong(K), M, N, chunk, threads,
+            sizes.ctypes.data_as(ip)]
+    rc = lib.hh_host_index(*args, *([null] * 10))
+    if rc:
+        return rc, None
+    out = {"cam": np.zeros(K, np.int32), "pts": np.zeros(K, np.int32), "track_ptr": np.zeros(N + 1, np.int32),
+           "cam_cnt": np.zeros(M + 1, np.int32), "cm_obs": np.zeros(K, np.int32), "ch_cam": np.zeros(sizes[0], np.int32),
+           "ch_beg": np.zeros(sizes[0], np.int32), "ch_end": np.zeros(sizes[0], np.int32),
+           "first_chunk": np.zeros(M + 1, np.int32), "tile_obs": np.zeros(sizes[1], np.int32)}
+    rc = lib.hh_host_index(*args, *[out[k].ctypes.data_as(ip) for k in
+                                    ("cam", "pts", "track_ptr", "cam_cnt", "cm_obs", "ch_cam", "ch_beg", "ch_end", "first_chunk", "tile_obs")])
+    return rc, out
+
+
+@pytest.mark.parametrize("M,N,p_vis,threads", [(10, 100000, 0.5, 8), (10, 100000, 0.5, 1), (40, 3000, 0.9, 8), (3, 50, 0.5, 8),
+                                                 (7, 200000, 0.3, 5)])
+def test_host_index_tables(built, M, N, p_vis, threads):
+    """track offsets, camera-major permutation, chunks and warp tiles against their numpy definitions (threaded build)."""
+    rng = np.random.default_rng(M * 1000 + N)
+    seen = rng.random((N, M)) < p_vis
+    seen[rng.random(N) < 0.05] = False                     # some tracks without any observation
+    pts_ind, cam_ind = np.nonzero(seen)                    # the reference's order: by track, cameras ascending
+    K = pts_ind.size
+    rc, h = _host_index(cam_ind, pts_ind, M, N, chunk=1024, threads=threads)
+    assert rc == 0
+    assert np.array_equal(h["cam"], cam_ind) and np.array_equal(h["pts"], pts_ind)
+    assert np.array_equal(h["track_ptr"], np.searchsorted(pts_ind, np.arange(N + 1), side="left"))
+    assert np.array_equal(h["cam_cnt"], np.concatenate([[0], np.cumsum(np.bincount(cam_ind, minlength=M))]))
+    assert np.array_equal(h["cm_obs"], np.argsort(cam_ind, kind="stable"))
+    # chunks: consecutive ranges of <= 1024 observations, never across cameras, covering [0, K)
+    assert h["ch_beg"][0] == 0 and h["ch_end"][-1] == K and np.array_equal(h["ch_beg"][1:], h["ch_end"][:-1])
+    assert np.all(h["ch_end"] - h["ch_beg"] <= 1024) and np.all(h["ch_end"] > h["ch_beg"])
+    for c in range(h["ch_cam"].size):
+        assert h["cam_cnt"][h["ch_cam"][c]] <= h["ch_beg"][c] and h["ch_end"][c] <= h["cam_cnt"][h["ch_cam"][c] + 1]
+    assert np.array_equal(h["first_chunk"], np.searchsorted(h["ch_cam"], np.arange(M + 1), side="left"))
+    # warp tiles: whole tracks, <= 32 observations unless the tile is a single longer track, covering [0, K)
+    t = h["tile_obs"]
+    assert t[0] == 0 and t[-1] == K and np.all(np.diff(t) > 0)
+    starts = set(h["track_ptr"].tolist())
+    assert all(int(v) in starts for v in t)
+    lens = np.diff(t)
+    track_len = np.diff(h["track_ptr"])
+    for a0, L in zip(t[:-1][lens > 32], lens[lens > 32]):
+        i = pts_ind[a0]
+        assert track_len[i] == L                          # an over-long tile is exactly one track
+
+
+def test_host_index_rejects_bad_input(built):
+    assert _host_index([0, 1, 5], [0, 0, 1], 3, 2)[0] == 1          # camera out of range
+    assert _host_index([0, 1, 0], [0, 2, 1], 3, 3)[0] == 2          # tracks not sorted
+    assert _host_index([0, 1], [0, 7], 3, 3)[0] == 1                # track out of range
