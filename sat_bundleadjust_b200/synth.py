@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import ba_rotate, cam_utils, geo_utils
+from . import cam_utils, geo_utils
 from .ba_params import BundleAdjustmentParameters, load_cam_params_from_camera
 
 SCENE_LAT, SCENE_LON, SCENE_ALT = 11.02, -72.71, 3500.0
