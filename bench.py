@@ -60,21 +60,21 @@ def load_peaks():
 
 
 def ncu_traffic(phase, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's main kernel, from the committed summary of one
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch, source, FP64 pipe utilisation) of the phase's main kernel, from the committed summary of one
     `ncu --set full` capture of this workload (profiles/r01_ncu_full_selected_metrics.csv); None when there is none."""
     main_kernel = {"schur": "k_schur<", "assemble": "k_assemble_points<", "point_prep": "k_point_prep<", "backsub": "k_backsub<",
                    "cholesky": "k_chol_fused<", "scale_jvp": "k_jvp<1, 6, 1>", "subspace": "k_jvp<1, 6, 2>",
                    "step_eval": "k_residual<"}.get(phase)
     path = os.path.join(ROOT, "profiles", "r01_ncu_full_selected_metrics.csv")
     if workload != "cfg2" or main_kernel is None or not os.path.exists(path):
-        return None, None
+        return None, None, None
     import csv
     with open(path) as f:
         for row in csv.DictReader(f):
             if row["kernel"].startswith(main_kernel):
-                return (float(row["dram rd MB"]) + float(row["dram wr MB"])) * 1e6, \
-                    "profiles/r01_ncu_full_selected_metrics.csv (%s, one ncu --set full capture, cold L2)" % row["kernel"]
-    return None, None
+                src = "profiles/r01_ncu_full_selected_metrics.csv (%s, one ncu --set full capture, cold L2)" % row["kernel"]
+                return (float(row["dram rd MB"]) + float(row["dram wr MB"])) * 1e6, src, float(row["fp64 pipe %"]) / 100.0
+    return None, None, None
 
 
 class ClockSampler:
@@ -365,7 +365,7 @@ def run_b200_arm(args):
         K_loc, N_loc = prob.n_obs, prob.n_pts
         ab = algorithmic_bytes(K_loc, N_loc, M, c)
         dominant = max(phase_ms, key=lambda k: phase_ms[k])
-        traffic, traffic_src = ncu_traffic(dominant, args.workload)
+        traffic, traffic_src, fp64_frac = ncu_traffic(dominant, args.workload)
         roof_all = {k: {"ms": phase_ms[k], "algorithmic_bytes": ab[k],
                         "achieved_GBps": ab[k] / (phase_ms[k] * 1e-3) / 1e9 if phase_ms[k] > 0 else None}
                     for k in phase_ms}
@@ -386,6 +386,8 @@ def run_b200_arm(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(info["gpu_launches"]),
             "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         # the other roofline of this FP64 path: share of the FP64 pipe's issue slots the kernel used (ncu)
+                         "fp64_pipe_frac": fp64_frac,
                          "jacobian_assembly": {"achieved": jac_ach, "frac": jac_ach / peak, "ms": jac_ms_mean,
                                                "algorithmic_bytes": ab["assemble"]}},
             "phases_ms_per_iteration": phase_ms, "phases": roof_all,
