@@ -41,6 +41,19 @@ def test_build_jacobian_sparsity_bit_exact(name):
     assert A.dtype == np.dtype(int)
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", CASES)
+def test_jacobian_sparsity_is_the_reference_lil_matrix(name):
+    """Same type, dtype and row / data lists as the lil_matrix the unmodified reference builds (ba_core.py:186-219)."""
+    ref = load_reference()
+    p = util.params_from_golden(G, name)
+    A, B = ba_core.build_jacobian_sparsity(p), ref.ba_core.build_jacobian_sparsity(p)
+    assert type(A) is type(B) and A.shape == B.shape and A.dtype == B.dtype
+    assert all(a == b for a, b in zip(A.rows, B.rows)) and all(a == b for a, b in zip(A.data, B.data))
+    A[0, A.shape[1] - 1] = 1                      # still a working LIL matrix
+    assert A.nnz == B.nnz + 1
+
+
 def test_get_vars_ready_for_fun_and_reconstruct():
     p = util.params_from_golden(G, "persp_RT_fix")
     v = p.params_opt.copy()
