@@ -34,6 +34,28 @@ def test_filter_pairs_matches_the_loop_definition():
     assert np.array_equal(ba_outliers.filter_C_using_pairs_to_triangulate(C, pairs), want)
 
 
+def test_filter_pairs_matches_the_live_reference():
+    """feature_tracks/ft_utils.py:38-62 of the unmodified reference, where the reference tree is present."""
+    from oracle.ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    import sys
+    load_reference()
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        from bundle_adjust.feature_tracks import ft_utils
+    finally:
+        sys.dont_write_bytecode = old
+    rng = np.random.default_rng(3)
+    for n_cam, n_tr, p_vis in ((6, 400, 0.5), (12, 300, 0.2), (3, 50, 0.9)):
+        C = rng.normal(size=(2 * n_cam, n_tr))
+        C[np.repeat(rng.random((n_cam, n_tr)) > p_vis, 2, axis=0)] = np.nan
+        pairs = [(int(a), int(b)) for a, b in rng.integers(0, n_cam, size=(7, 2))]
+        want = ft_utils.filter_C_using_pairs_to_triangulate(C, pairs)
+        assert np.array_equal(ba_outliers.filter_C_using_pairs_to_triangulate(C, pairs), want)
+
+
 @pytest.mark.gpu
 def test_elbow_values_bit_exact(built):
     for k in range(int(G["elbow/n"])):
