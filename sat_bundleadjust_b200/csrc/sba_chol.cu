@@ -178,7 +178,7 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Blocked right-looking factorisation for n > CHOL_SMEM_MAX_N (cfg3: n = 300, cfg4: n = 1800), many CTAs, in place
+// Blocked right-looking factorisation for n > CHOL_FUSED_MAX_N (cfg3: n = 300, cfg4: n = 1800), many CTAs, in place
 // in the column-major matrix (which stays L2-resident: 26 MB at n = 1800).  Per panel of CB = 32 columns:
 //   k_chol_panel   every CTA factors the 32 x 32 diagonal block redundantly (same arithmetic, same bits) in shared
 //                  memory with one warp, then each warp solves one row of the panel below it against that block;
