@@ -116,42 +116,43 @@ def filter_C_using_pairs_to_triangulate(C, pairs_to_triangulate):
 
 
 def reset_ba_params_after_outlier_removal(C_new, p, verbose=True):
-    """Bundle-adjustment parameters coherent with the filtered correspondence matrix (ba_outliers.py:61-109)."""
+    """
+    Bundle-adjustment parameters coherent with the filtered correspondence matrix (ba_outliers.py:61-109): tracks left
+    with fewer than two observations or without a pair suitable for triangulation are dropped, the surviving tracks are
+    re-triangulated from the observations they kept (frozen points keep their coordinates) and a fresh
+    BundleAdjustmentParameters object is built with the options of `p`.
+    """
     from .ba_params import BundleAdjustmentParameters
     from .ft_triangulate import init_pts3d
 
-    obs_per_track = np.sum(1 * np.invert(np.isnan(C_new)), axis=0)
-    tracks_to_preserve_1 = np.where(obs_per_track >= 4)[0]
-    C_new = C_new[:, tracks_to_preserve_1]
-    tracks_to_preserve_2 = filter_C_using_pairs_to_triangulate(C_new, p.pairs_to_triangulate)
-    C_new = C_new[:, tracks_to_preserve_2]
-    final_indices_left = tracks_to_preserve_1[tracks_to_preserve_2]
-    n_pts_fix_new = np.sum(1 * (final_indices_left < p.n_pts_fix))
-    pts3d_new = init_pts3d(C_new, p.cameras, p.cam_model, p.pairs_to_triangulate, verbose=verbose)
-    if n_pts_fix_new > 0:
-        pts3d_new[:n_pts_fix_new, :] = p.pts3d[final_indices_left[final_indices_left < p.n_pts_fix], :]
-    args = [C_new, pts3d_new, p.cameras, p.cam_model, p.pairs_to_triangulate, p.camera_centers]
-    d = {
-        "n_cam_fix": p.n_cam_fix,
-        "n_pts_fix": n_pts_fix_new,
-        "reduce": False,
-        "verbose": verbose,
-        "correction_params": p.cam_params_to_optimize,
-        "ref_cam_weight": p.ref_cam_weight,
-    }
-    new_p = BundleAdjustmentParameters(*args, d)
-    new_p.pts_prev_indices = p.pts_prev_indices[final_indices_left]
+    # an observation occupies two rows of C, hence ">= 4 finite entries" == ">= 2 observations"
+    long_enough = np.flatnonzero(np.count_nonzero(~np.isnan(C_new), axis=0) >= 4)
+    C_kept = C_new[:, long_enough]
+    triangulable = filter_C_using_pairs_to_triangulate(C_kept, p.pairs_to_triangulate)
+    C_kept = C_kept[:, triangulable]
+    survivors = long_enough[triangulable]                      # indices into the tracks of p
+    frozen = survivors[survivors < p.n_pts_fix]                # frozen tracks are the first n_pts_fix of p
+    pts3d = init_pts3d(C_kept, p.cameras, p.cam_model, p.pairs_to_triangulate, verbose=verbose)
+    if frozen.size > 0:
+        pts3d[: frozen.size, :] = p.pts3d[frozen, :]
+    options = {"n_cam_fix": p.n_cam_fix, "n_pts_fix": np.sum(1 * (survivors < p.n_pts_fix)), "reduce": False, "verbose": verbose,
+               "correction_params": p.cam_params_to_optimize, "ref_cam_weight": p.ref_cam_weight}
+    new_p = BundleAdjustmentParameters(C_kept, pts3d, p.cameras, p.cam_model, p.pairs_to_triangulate, p.camera_centers, options)
+    new_p.pts_prev_indices = p.pts_prev_indices[survivors]
     return new_p
 
 
 def rm_outliers(err, p, predef_thr=None, min_thr=1.0, verbose=False):
-    """Remove outlier observations according to their reprojection error (ba_outliers.py:156-186)."""
-    C_new, cam_thr, n_detected_outliers = compute_obs_to_remove(err, p, predef_thr=predef_thr, min_thr=min_thr)
-    new_p = reset_ba_params_after_outlier_removal(C_new, p, verbose=verbose) if n_detected_outliers > 0 else p
+    """
+    Remove outlier observations according to their reprojection error (ba_outliers.py:156-186).  Returns `p` itself
+    when nothing is removed, else the rebuilt parameters.
+    """
+    C_new, cam_thr, n_removed = compute_obs_to_remove(err, p, predef_thr=predef_thr, min_thr=min_thr)
+    new_p = p if n_removed == 0 else reset_ba_params_after_outlier_removal(C_new, p, verbose=verbose)
     if verbose:
-        n_obs_in, n_obs_rm = len(p.cam_ind), n_detected_outliers
-        n_tracks_in, n_tracks_rm = p.C.shape[1], p.C.shape[1] - new_p.C.shape[1]
+        n_obs, n_tracks = len(p.cam_ind), p.C.shape[1]
+        n_tracks_removed = n_tracks - new_p.C.shape[1]
         print("Reprojection error threshold per camera: {} px".format(cam_thr))
-        args = [n_obs_rm, n_obs_rm / n_obs_in * 100, n_tracks_rm, n_tracks_rm / n_tracks_in * 100]
-        print("Deleted {} observations ({:.2f}%) and {} tracks ({:.2f}%)".format(*args))
+        print("Deleted {} observations ({:.2f}%) and {} tracks ({:.2f}%)".format(
+            n_removed, 100.0 * n_removed / n_obs, n_tracks_removed, 100.0 * n_tracks_removed / n_tracks))
     return new_p

@@ -56,19 +56,37 @@ def test_filter_pairs_matches_the_live_reference():
         assert np.array_equal(ba_outliers.filter_C_using_pairs_to_triangulate(C, pairs), want)
 
 
+def _scene_params():
+    d = {"correction_params": ["R", "T"], "n_cam_fix": 0, "n_pts_fix": 30, "ref_cam_weight": 1.0, "reduce": False, "verbose": False}
+    pairs = [tuple(int(v) for v in p) for p in G["scene/pairs"]]
+    return BundleAdjustmentParameters(G["scene/C"], G["scene/pts3d"], list(G["scene/cameras"]), "perspective", pairs,
+                                      list(G["scene/centers"]), d)
+
+
+def test_reset_ba_params_from_golden_masks():
+    """reset_ba_params_after_outlier_removal (ba_outliers.py:61-109) on the correspondence matrix the reference filtered: CPU only."""
+    p = _scene_params()
+    C_new = p.C.copy()
+    C_new[G["scene/auto/C_new_nan"]] = np.nan
+    new_p = ba_outliers.reset_ba_params_after_outlier_removal(C_new, p, verbose=False)
+    assert np.array_equal(np.isnan(new_p.C), G["scene/new/C_nan"])
+    assert np.array_equal(new_p.pts_ind, G["scene/new/pts_ind"]) and np.array_equal(new_p.cam_ind, G["scene/new/cam_ind"])
+    assert np.array_equal(new_p.pts2d, G["scene/new/pts2d"])
+    assert int(new_p.n_pts_fix) == int(G["scene/new/n_pts_fix"])
+    assert np.array_equal(new_p.pts_prev_indices, G["scene/new/pts_prev_indices"])
+    ref_pts = G["scene/new/pts3d"]
+    diff = np.abs(new_p.pts3d.astype(np.float64) - ref_pts.astype(np.float64))
+    assert new_p.pts3d.dtype == ref_pts.dtype and np.all(diff <= np.spacing(np.abs(ref_pts))) and np.mean(diff > 0) < 1e-3
+    n_cam_vars = new_p.n_cam * new_p.n_params
+    assert np.array_equal(new_p.params_opt[:n_cam_vars], G["scene/new/params_opt"][:n_cam_vars])
+
+
 @pytest.mark.gpu
 def test_elbow_values_bit_exact(built):
     for k in range(int(G["elbow/n"])):
         val, ok = ba_outliers.get_elbow_value(G["elbow/%d/err" % k])
         assert val == float(G["elbow/%d/value" % k]), k
         assert ok == bool(G["elbow/%d/success" % k]), k
-
-
-def _scene_params():
-    d = {"correction_params": ["R", "T"], "n_cam_fix": 0, "n_pts_fix": 30, "ref_cam_weight": 1.0, "reduce": False, "verbose": False}
-    pairs = [tuple(int(v) for v in p) for p in G["scene/pairs"]]
-    return BundleAdjustmentParameters(G["scene/C"], G["scene/pts3d"], list(G["scene/cameras"]), "perspective", pairs,
-                                      list(G["scene/centers"]), d)
 
 
 @pytest.mark.gpu
