@@ -96,38 +96,34 @@ class BundleAdjustmentParameters:
             camera_centers: M camera centres (ECEF)
             d: options -- n_cam_fix, n_pts_fix, reduce, verbose, correction_params, ref_cam_weight
         """
-        self.C = C.copy()
-        self.pts3d = pts3d.copy()
-        self.cameras = cameras.copy()
-        self.cam_model = cam_model
+        # inputs are copied, options come from `d` with the reference's defaults (ba_params.py:103-115)
+        self.C, self.pts3d = C.copy(), pts3d.copy()
+        self.cameras, self.camera_centers = cameras.copy(), camera_centers.copy()
         self.pairs_to_triangulate = pairs_to_triangulate.copy()
-        self.camera_centers = camera_centers.copy()
-
-        self.cam_params_to_optimize = d.get("correction_params", ["R"])
-        self.ref_cam_weight = d.get("ref_cam_weight", 1.0)
-        self.n_cam_fix = d.get("n_cam_fix", 0)
-        self.n_pts_fix = d.get("n_pts_fix", 0)
-        verbose = d.get("verbose", True)
-
+        self.cam_model = cam_model
+        defaults = {"correction_params": ["R"], "ref_cam_weight": 1.0, "n_cam_fix": 0, "n_pts_fix": 0, "verbose": True,
+                    "reduce": True}
+        opts = {k: d.get(k, v) for k, v in defaults.items()}
+        self.cam_params_to_optimize, self.ref_cam_weight = opts["correction_params"], opts["ref_cam_weight"]
+        self.n_cam_fix, self.n_pts_fix = opts["n_cam_fix"], opts["n_pts_fix"]
+        verbose = opts["verbose"]
         if verbose:
-            print("\nDefining bundle adjustment parameters...")
-            print("     - cam_params_to_optimize: {}\n".format(self.cam_params_to_optimize))
+            print("\nDefining bundle adjustment parameters...\n     - cam_params_to_optimize: {}\n".format(
+                self.cam_params_to_optimize))
 
         self.n_cam, self.n_pts = C.shape[0] // 2, C.shape[1]
-        self.n_cam_opt = self.n_cam - self.n_cam_fix
-        self.n_pts_opt = self.n_pts - self.n_pts_fix
-        self.cam_prev_indices = np.arange(self.n_cam)
-        self.pts_prev_indices = np.arange(self.n_pts)
-        if d.get("reduce", True):
+        self.n_cam_opt, self.n_pts_opt = self.n_cam - self.n_cam_fix, self.n_pts - self.n_pts_fix
+        self.cam_prev_indices, self.pts_prev_indices = np.arange(self.n_cam), np.arange(self.n_pts)
+        if opts["reduce"]:
+            shape_before = C.shape
             self.reduce(C, pts3d, cameras, pairs_to_triangulate, camera_centers)
             if verbose:
-                print("C.shape before reduce", C.shape)
+                print("C.shape before reduce", shape_before)
                 print("C.shape after reduce", self.C.shape)
 
-        # per-camera parameter vectors
-        self.cam_params = np.array(
-            [load_cam_params_from_camera(c, oC, self.cam_model) for c, oC in zip(self.cameras, self.camera_centers)]
-        )
+        # per-camera parameter vectors (M x 8 | 11 | 9)
+        self.cam_params = np.array([load_cam_params_from_camera(cam, center, self.cam_model)
+                                    for cam, center in zip(self.cameras, self.camera_centers)])
 
         # observation list (vectorised; same order as the reference's double loop)
         self.pts_ind, self.cam_ind, self.pts2d = observations_from_C(self.C)
@@ -165,8 +161,9 @@ class BundleAdjustmentParameters:
             self.pts2d_w[self.cam_ind == 0] = self.ref_cam_weight
 
         if verbose:
-            print("{} 3d points, {} fixed and {} to be optimized".format(self.n_pts, self.n_pts_fix, self.n_pts_opt))
-            print("{} cameras, {} fixed and {} to be optimized".format(self.n_cam, self.n_cam_fix, self.n_cam_opt))
+            for what, total, fixed, free in (("3d points", self.n_pts, self.n_pts_fix, self.n_pts_opt),
+                                             ("cameras", self.n_cam, self.n_cam_fix, self.n_cam_opt)):
+                print("{} {}, {} fixed and {} to be optimized".format(total, what, fixed, free))
             print("{} parameters to optimize per camera\n".format(self.n_params))
 
     # ------------------------------------------------------------------------------------------
@@ -235,18 +232,11 @@ class BundleAdjustmentParameters:
         before `reduce` (ba_params.py:259-286).
         """
         self.pts3d_ba, cam_params = self.get_vars_ready_for_fun(v)
-        self.cameras_ba = [load_camera_from_cam_params(cam_params[i, :], self.cam_model) for i in range(self.n_cam)]
-
-        self.estimated_params = []
-        for i in range(cam_params.shape[0]):
-            est = {}
-            if "R" in self.cam_params_to_optimize:
-                est["R"] = cam_params[i, :3]
-            if "T" in self.cam_params_to_optimize:
-                est["T"] = cam_params[i, 3:6]
-            if self.cam_model == "rpc":
-                est["C"] = cam_params[i, 6:9]
-            self.estimated_params.append(est)
+        self.cameras_ba = [load_camera_from_cam_params(row, self.cam_model) for row in cam_params]
+        wanted = [(key, sl) for key, sl in (("R", slice(0, 3)), ("T", slice(3, 6))) if key in self.cam_params_to_optimize]
+        if self.cam_model == "rpc":
+            wanted.append(("C", slice(6, 9)))
+        self.estimated_params = [{key: row[sl] for key, sl in wanted} for row in cam_params]
 
         corrected_pts3d, corrected_cameras = pts3d.copy(), cameras.copy()
         corrected_pts3d[self.pts_prev_indices] = self.pts3d_ba
