@@ -237,7 +237,7 @@ class BundleAdjustmentParameters:
         if self.cam_model == "rpc":
             wanted.append(("C", slice(6, 9)))
         self.estimated_params = [{key: row[sl] for key, sl in wanted} for row in cam_params]
-
+        print("\n")      # the reference's driver output has this blank block here (ba_params.py:279)
         corrected_pts3d, corrected_cameras = pts3d.copy(), cameras.copy()
         corrected_pts3d[self.pts_prev_indices] = self.pts3d_ba
         for ba_idx, prev_idx in enumerate(self.cam_prev_indices):
