@@ -44,6 +44,8 @@ WORKLOADS = {
              "BASELINE config 3 shard: 50-view perspective BA, 1.25e5 tracks / ~6e5 observations per GPU, soft_l1, R+T"),
     "cfg3a": (50, 125000, 0.1, "affine", ["R", "T"],
               "BASELINE config 3 shard: 50-view affine BA, 1.25e5 tracks / ~6e5 observations per GPU, soft_l1, R+T"),
+    "cfg3full": (50, 1000000, 0.1, "perspective", ["R", "T"],
+                 "BASELINE config 3 whole: 50-view perspective BA, 1e6 tracks / ~5e6 observations per GPU, soft_l1, R+T"),
     "cfg4s": (300, 100000, 0.02, "perspective", ["R", "T"],
               "BASELINE config 4 reduced: 300-view perspective BA, 1e5 tracks / ~6e5 observations per GPU (1800 x 1800 reduced system)"),
 }

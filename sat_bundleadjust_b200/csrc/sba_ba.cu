@@ -26,6 +26,7 @@
 #include "sba_comm.cuh"
 #include "sba_index.h"
 #include "sba_kernels.cuh"
+#include "sba_pattern.cuh"
 #include "sba_tr2d.h"
 
 namespace sba {
@@ -604,6 +605,49 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     return SBA_OK;
 }
 
+#include "sba_pattern_host.inl"
+
+// residuals at the internal vector x (camrec prepared) into a device buffer in the CALLER's observation order
+static int residuals_ext(sba_problem* p, const double* x, const double* camrec, int loss, double f_scale, double* r_ext_dev,
+                         int slot, int rpc_f32)
+{
+    if (p->engine == 0) return run_residual(p, x, camrec, loss, f_scale, r_ext_dev, slot, rpc_f32);
+    SBA_TRY(run_residual(p, x, camrec, loss, f_scale, r_ext_dev ? p->r_int : nullptr, slot, rpc_f32));
+    if (r_ext_dev) SBA_TRY(pt_obs_out(p, p->r_int, 2, r_ext_dev));
+    return SBA_OK;
+}
+
+// un-weighted reprojection errors of the residuals just computed by residuals_ext, caller's order
+static int reproj_errors_ext(sba_problem* p, const double* r_ext_dev, double* err_ext_dev)
+{
+    const int grid = grid_for(p->K, 256, NUM_SMS * 8);
+    if (p->engine == 0) {
+        k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)r_ext_dev, p->w, p->K, err_ext_dev);
+        return check_launch(p);
+    }
+    k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)p->r_int, p->w, p->K, p->e_int);
+    SBA_TRY(check_launch(p));
+    return pt_obs_out(p, p->e_int, 1, err_ext_dev);
+}
+
+// caller's variable vector (device) -> internal vector; and back
+static int vars_in(sba_problem* p, const double* x_ext_dev, double* dst)
+{
+    if (p->engine == 0) {
+        SBA_CUDA(cudaMemcpyAsync(dst, x_ext_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        return SBA_OK;
+    }
+    return pt_x_in(p, x_ext_dev, dst);
+}
+static int vars_out(sba_problem* p, const double* src, double* x_ext_dev)
+{
+    if (p->engine == 0) {
+        SBA_CUDA(cudaMemcpyAsync(x_ext_dev, src, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        return SBA_OK;
+    }
+    return pt_x_out(p, src, x_ext_dev);
+}
+
 }  // namespace sba
 
 using namespace sba;
@@ -671,6 +715,17 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     std::vector<int>&ch_cam = hidx.ch_cam, &ch_beg = hidx.ch_beg, &ch_end = hidx.ch_end, &first_chunk = hidx.first_chunk;
     std::vector<int>& tile_obs = hidx.tile_obs;
     stamp("host index pass");
+    if (pattern_engine_applicable(p)) {
+        PatternLayout lay;
+        build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS / 32, lay);
+        stamp("pattern layout");
+        if (lay.ok) {
+            const int rc = pattern_create(p, d, hidx, lay);
+            stamp("pattern uploads + state");
+            return rc;
+        }
+        if (timing) fprintf(stderr, "[sba create] pattern engine not applicable: %s\n", lay.why.c_str());
+    }
     p->chunks.n = (int)ch_cam.size();
     p->chunks.h_cam = ch_cam;
     p->chunks.h_first_of_cam = first_chunk;
@@ -902,8 +957,10 @@ extern "C" int sba_residuals(sba_problem* p, const double* x, double* r, int32_t
     if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
-    SBA_TRY(run_residual(p, p->io_x, p->camrec_new, loss, f_scale, p->r_out, SC_COST_NEW, p->rpc_f32));
+    double* xi = p->io_x;
+    if (p->engine == 1) { SBA_TRY(vars_in(p, p->io_x, p->x_new)); xi = p->x_new; }
+    SBA_TRY(run_prepare(p, xi, p->camrec_new));
+    SBA_TRY(residuals_ext(p, xi, p->camrec_new, loss, f_scale, p->r_out, SC_COST_NEW, p->rpc_f32));
     if (r) SBA_CUDA(cudaMemcpyAsync(r, p->r_out, 2 * (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     SBA_TRY(fetch_scal(p));
     if (cost) *cost = p->h_scal[SC_COST_NEW];
@@ -915,14 +972,17 @@ extern "C" int sba_jacobian_blocks(sba_problem* p, const double* x, double* Jc, 
     if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
+    double* xi = p->io_x;
+    if (p->engine == 1) { SBA_TRY(vars_in(p, p->io_x, p->x_new)); xi = p->x_new; }
+    SBA_TRY(run_prepare(p, xi, p->camrec_new));
     double *dJc = nullptr, *dJp = nullptr;
     if (Jc) SBA_CUDA(cudaMalloc((void**)&dJc, (size_t)p->K * 2 * p->nc * sizeof(double)));
     if (Jp) SBA_CUDA(cudaMalloc((void**)&dJp, (size_t)p->K * 6 * sizeof(double)));
     const int grid = grid_for(p->K, 128, NUM_SMS * 16);
 #define L(MODEL, NC)                                                                                               \
-    k_jac_blocks<MODEL, NC><<<grid, 128, 0, p->stream>>>(obs_arrays(p), p->io_x + (size_t)p->M * p->nc, p->camrec_new, \
-                                                         p->rpc_tab, p->K, p->n_cam_fix, p->n_pts_fix, dJc, dJp)
+    k_jac_blocks<MODEL, NC><<<grid, 128, 0, p->stream>>>(obs_arrays(p), xi + (size_t)p->M * p->nc, p->camrec_new,   \
+                                                         p->rpc_tab, p->K, p->n_cam_fix,                             \
+                                                         p->engine == 1 ? p->n_pts_fix_int : p->n_pts_fix, dJc, dJp)
     SBA_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
@@ -931,15 +991,45 @@ extern "C" int sba_jacobian_blocks(sba_problem* p, const double* x, double* Jc, 
     SBA_CUDA(cudaStreamSynchronize(p->stream));
     if (dJc) cudaFree(dJc);
     if (dJp) cudaFree(dJp);
+    if (p->engine == 1) {          // test-only entry point: un-permute on the host
+        auto unperm = [&](double* buf, size_t width) {
+            std::vector<double> tmp(buf, buf + (size_t)p->K * width);
+            for (int64_t a = 0; a < p->K; ++a)
+                std::memcpy(buf + (size_t)p->h_obs_new2old[a] * width, tmp.data() + (size_t)a * width, width * sizeof(double));
+        };
+        if (Jc) unperm(Jc, 2 * (size_t)p->nc);
+        if (Jp) unperm(Jp, 6);
+    }
     return SBA_OK;
 }
 
+// frozen points of the internal order: the generic kernels test `track index >= n_pts_fix`, which only holds for the caller's
+// order; the pattern engine carries the flag per run instead (PUnit::pts_free)
 extern "C" int sba_normal_blocks(sba_problem* p, const double* x, int32_t loss, double f_scale, double* U, double* V,
                                  double* g)
 {
     if (!p || !x) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     const size_t ns = (size_t)p->M * p->nc;
+    if (p->engine == 1) {
+        SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        SBA_TRY(vars_in(p, p->io_x, p->x));
+        SBA_TRY(pt_reset_state(p));
+        SBA_TRY(pt_run_assemble(p, 1, 1, loss, f_scale));
+        pt_accept(p);
+        std::vector<double> Vi(V ? 6 * (size_t)p->N : 0), gi(g ? (size_t)p->n : 0);
+        if (U) SBA_CUDA(cudaMemcpyAsync(U, p->camsys, ns * p->nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (V) SBA_CUDA(cudaMemcpyAsync(Vi.data(), p->V, Vi.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (g) SBA_CUDA(cudaMemcpyAsync(gi.data(), p->g, gi.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        SBA_CUDA(cudaStreamSynchronize(p->stream));
+        for (int t = 0; t < p->N; ++t) {
+            const size_t o = (size_t)p->h_trk_new2old[t];
+            if (V) std::memcpy(V + 6 * o, Vi.data() + 6 * (size_t)t, 6 * sizeof(double));
+            if (g) std::memcpy(g + ns + 3 * o, gi.data() + ns + 3 * (size_t)t, 3 * sizeof(double));
+        }
+        if (g) std::memcpy(g, gi.data(), ns * sizeof(double));
+        return SBA_OK;
+    }
     SBA_CUDA(cudaMemcpyAsync(p->x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     SBA_TRY(run_prepare(p, p->x, p->camrec));
     SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
@@ -963,16 +1053,28 @@ extern "C" int sba_reduced_system(sba_problem* p, const double* x, int32_t loss,
     if (p->world > 1) { set_error("sba_reduced_system: single-rank problems only"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     const size_t ns = (size_t)p->M * p->nc;
-    SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), p->stream));
-    SBA_CUDA(cudaMemcpyAsync(p->x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    SBA_TRY(run_prepare(p, p->x, p->camrec));
-    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
-    SBA_TRY(run_scale_dots(p, 1));
-    k_control_reg<<<1, 32, 0, p->stream>>>(p->scal, -1.0, reg);
-    SBA_TRY(check_launch(p));
-    PhaseTimer tm;
-    tm.p = p;
-    SBA_TRY(run_gauss_newton_step(p, loss, f_scale, tm, true));
+    if (p->engine == 1) {
+        SBA_CUDA(cudaMemcpyAsync(p->io_x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        SBA_TRY(vars_in(p, p->io_x, p->x));
+        SBA_TRY(pt_reset_state(p));
+        SBA_TRY(pt_run_assemble(p, 1, 1, loss, f_scale));
+        pt_accept(p);
+        SBA_TRY(pt_run_jvp1(p, 1, loss, f_scale, -1.0));
+        k_pt_control_reg<<<1, 32, 0, p->stream>>>(p->scal, -1.0, reg);
+        SBA_TRY(check_launch(p));
+        SBA_TRY(pt_run_schur(p, loss, f_scale));
+    } else {
+        SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), p->stream));
+        SBA_CUDA(cudaMemcpyAsync(p->x, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        SBA_TRY(run_prepare(p, p->x, p->camrec));
+        SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
+        SBA_TRY(run_scale_dots(p, 1));
+        k_control_reg<<<1, 32, 0, p->stream>>>(p->scal, -1.0, reg);
+        SBA_TRY(check_launch(p));
+        PhaseTimer tm;
+        tm.p = p;
+        SBA_TRY(run_gauss_newton_step(p, loss, f_scale, tm, true));
+    }
     SBA_CUDA(cudaMemcpyAsync(S, p->S, ns * ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     SBA_CUDA(cudaMemcpyAsync(rhs, p->S + ns * ns, ns * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     SBA_CUDA(cudaStreamSynchronize(p->stream));
@@ -985,11 +1087,12 @@ extern "C" int sba_solve_device(sba_problem* p, const double* x0_dev, const sba_
     if (!p || !x0_dev || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
     if (p->world > 1 && !p->allreduce && !p->comm_ready) { set_error("world_size > 1 needs sba_comm_import or sba_problem_set_allreduce"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
-    SBA_CUDA(cudaMemcpyAsync(p->x, x0_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    SBA_TRY(solve_on_device(p, opts, info));
-    if (x_dev) SBA_CUDA(cudaMemcpyAsync(x_dev, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    SBA_TRY(vars_in(p, x0_dev, p->x));
+    if (p->engine == 1) SBA_TRY(solve_pattern(p, opts, info));
+    else SBA_TRY(solve_on_device(p, opts, info));
+    if (x_dev) SBA_TRY(vars_out(p, p->x, x_dev));
     if (r_dev) {
-        SBA_TRY(run_residual(p, p->x, p->camrec, SBA_LOSS_LINEAR, 1.0, r_dev, SC_SCRATCH, p->rpc_f32));
+        SBA_TRY(residuals_ext(p, p->x, p->camrec, SBA_LOSS_LINEAR, 1.0, r_dev, SC_SCRATCH, p->rpc_f32));
         info->gpu_launches = p->launches;
     }
     SBA_CUDA(cudaStreamSynchronize(p->stream));
@@ -1002,8 +1105,8 @@ extern "C" int sba_solve(sba_problem* p, const double* x0, const sba_solve_opts*
     if (!p || !x0 || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     SBA_CUDA(cudaMemcpyAsync(p->io_x, x0, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    SBA_TRY(sba_solve_device(p, p->io_x, opts, nullptr, r ? p->r_out : nullptr, info));
-    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_TRY(sba_solve_device(p, p->io_x, opts, x ? p->io_x : nullptr, r ? p->r_out : nullptr, info));
+    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->io_x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (r) SBA_CUDA(cudaMemcpyAsync(r, p->r_out, 2 * (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     SBA_CUDA(cudaStreamSynchronize(p->stream));
     return SBA_OK;
@@ -1013,11 +1116,18 @@ extern "C" int sba_assemble_device(sba_problem* p, const double* x_dev, int32_t 
 {
     if (!p || !x_dev) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
-    SBA_CUDA(cudaMemcpyAsync(p->x, x_dev, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    SBA_TRY(run_prepare(p, p->x, p->camrec));
-    SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
-    SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
-    SBA_CUDA(cudaEventRecord(p->ev1, p->stream));
+    SBA_TRY(vars_in(p, x_dev, p->x));
+    if (p->engine == 1) {
+        SBA_TRY(pt_reset_state(p));
+        SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
+        SBA_TRY(pt_run_assemble(p, 1, 1, loss, f_scale));
+        SBA_CUDA(cudaEventRecord(p->ev1, p->stream));
+    } else {
+        SBA_TRY(run_prepare(p, p->x, p->camrec));
+        SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
+        SBA_TRY(run_assemble(p, p->x, p->camrec, loss, f_scale));
+        SBA_CUDA(cudaEventRecord(p->ev1, p->stream));
+    }
     SBA_CUDA(cudaStreamSynchronize(p->stream));
     float t = 0.f;
     SBA_CUDA(cudaEventElapsedTime(&t, p->ev0, p->ev1));
@@ -1037,20 +1147,18 @@ extern "C" int sba_solve_errors(sba_problem* p, const double* x0, const sba_solv
 {
     if (!p || !x0 || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
-    const int grid = grid_for(p->K, 256, NUM_SMS * 8);
     SBA_CUDA(cudaMemcpyAsync(p->io_x, x0, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     if (err_init) {
-        SBA_TRY(run_prepare(p, p->io_x, p->camrec_new));
-        SBA_TRY(run_residual(p, p->io_x, p->camrec_new, SBA_LOSS_LINEAR, 1.0, p->r_out, SC_SCRATCH, p->rpc_f32));
-        k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)p->r_out, p->w, p->K, p->err_out);
-        SBA_TRY(check_launch(p));
+        SBA_TRY(vars_in(p, p->io_x, p->x_new));
+        SBA_TRY(run_prepare(p, p->x_new, p->camrec_new));
+        SBA_TRY(residuals_ext(p, p->x_new, p->camrec_new, SBA_LOSS_LINEAR, 1.0, p->r_out, SC_SCRATCH, p->rpc_f32));
+        SBA_TRY(reproj_errors_ext(p, p->r_out, p->err_out));
         SBA_CUDA(cudaMemcpyAsync(err_init, p->err_out, (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     }
-    SBA_TRY(sba_solve_device(p, p->io_x, opts, nullptr, err ? p->r_out : nullptr, info));
-    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    SBA_TRY(sba_solve_device(p, p->io_x, opts, x ? p->io_x : nullptr, err ? p->r_out : nullptr, info));
+    if (x) SBA_CUDA(cudaMemcpyAsync(x, p->io_x, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (err) {
-        k_reproj_error<<<grid, 256, 0, p->stream>>>((const double2*)p->r_out, p->w, p->K, p->err_out);
-        SBA_TRY(check_launch(p));
+        SBA_TRY(reproj_errors_ext(p, p->r_out, p->err_out));
         SBA_CUDA(cudaMemcpyAsync(err, p->err_out, (size_t)p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     }
     SBA_CUDA(cudaStreamSynchronize(p->stream));

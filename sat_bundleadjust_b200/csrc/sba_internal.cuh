@@ -62,6 +62,16 @@ enum Scal {
     SC_STEPH,             // |step_h| (scaled space)
     SC_STEPN,             // |step|   (x space)
     SC_COMM_FAIL,         // a peer did not arrive within the time-out of the peer-memory all-reduce
+    // pattern engine, group P (SUM over ranks): Gram scalars of the pair {t1 = D^-2 g, delta = Gauss-Newton step}
+    SC_P_GD,              // g . delta            (= g_h . gn_h)
+    SC_P_DD,              // |D delta|^2          (= |gn_h|^2)
+    SC_P_C12,             // (J t1) . (J delta)
+    SC_P_C22,             // |J delta|^2
+    SC_P_T11,             // |t1|^2
+    SC_P_T1D,             // t1 . delta
+    SC_P_TDD,             // |delta|^2
+    // pattern engine, device-side control: step = pa t1 + pb delta
+    SC_PA, SC_PB,
     SC_COUNT
 };
 
@@ -140,4 +150,18 @@ struct sba_problem {
     size_t arena_left = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+
+    // ---- pattern engine (csrc/sba_pattern.h): internal track order = tracks grouped by visibility pattern ----
+    int engine = 0;                                      // 0: generic (pair lists), 1: pattern-major
+    int n_pts_fix_int = 0;                               // frozen tracks in the internal order: tracks [0, n_pts_fix_int)
+    std::vector<int> h_trk_new2old, h_obs_new2old;       // host copies (test-only entry points un-permute on the host)
+    int *trk_new2old = nullptr, *obs_new2old = nullptr;  // device
+    void* pt_units = nullptr;                            // device PUnit[]
+    int *pt_pat_cams = nullptr, *pt_cta_unit0 = nullptr;
+    int pt_n_cta = 0;
+    double *V2 = nullptr, *g2 = nullptr, *camsys2 = nullptr;        // second buffer set (trial point)
+    double *dsq = nullptr, *idsq = nullptr;                         // (n) squared column scales of the points and their reciprocals
+    double *dsqc = nullptr, *dsqc2 = nullptr, *idsqc = nullptr, *idsqc2 = nullptr;   // (ns) the same for the cameras, double-buffered
+    double *pt_partials = nullptr;                                  // per-CTA partial sums, [value][cta]
+    double *r_int = nullptr, *e_int = nullptr;                      // (2K), (K) residuals / errors in internal order
 };

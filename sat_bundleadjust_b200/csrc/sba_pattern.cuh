@@ -1,0 +1,869 @@
+// Pattern-major engine: the four fused passes of one trust-region iteration for problems whose reduced camera
+// system fits in shared memory (M * n_params <= PT_MAX_NS).  Layout and vocabulary: sba_pattern.h.
+//
+//   k_pt_assemble   trial point x + pa t1 + pb delta, residual, robust cost, analytic Jacobian and the blocks
+//                   V_i, g_i (per track, reduced inside the warp) and U_j, g_j (per camera, in registers over a work
+//                   unit) -- one evaluation per observation.  Doubles as the trial-cost evaluation of the step, so an
+//                   accepted step needs no further pass.                              (G1 + G2 of SURVEY.md 2.2)
+//   k_pt_jvp1       x_scale update of the points, |g_h|^2 and |J_h g_h|^2 -> damping (scipy trf.py:485-490)
+//   k_pt_schur      damped point blocks inverted, Z_a = (Jc^T Jp) G^T staged in shared memory, all products
+//                   Z_a Z_b^T of a track accumulated in registers by fixed (camera pair, row chunk) lanes, flushed
+//                   once per unit into the CTA's shared-memory copy of S -- no Z in HBM, no pair lists    (G3)
+//   k_pt_backsub    point steps from the camera step, and the Gram scalars of the 2-D subspace {g, gn}    (G6)
+// Every reduction has a fixed order (static unit -> CTA -> warp assignment, ticketed flushes), so results are
+// reproducible bit for bit.  Included by sba_ba.cu only.
+#pragma once
+#include "sba_kernels.cuh"
+#include "sba_pattern.h"
+
+namespace sba {
+
+constexpr int PT_CTAS = NUM_SMS;          // one persistent CTA per SM
+constexpr int PT_THREADS = 512;           // assemble / jvp1 / backsub (<= 128 registers)
+constexpr int PT_THREADS_SCHUR = 384;     // schur (<= 168 registers)
+constexpr int PT_MAX_NS = 132;            // reduced camera system that still fits the shared-memory copy of S
+constexpr int PT_RC = 3;                  // rows of a camera block per Schur task
+
+struct PatView {
+    const PUnit* units;
+    const int* pat_cams;
+    const int* cta_unit0;
+    const double2* pts2d;     // internal observation order
+    const double* w;
+    const double* cam_static; // (M, P) initial camera parameters
+    const double* rpc_tab;
+    int M, P, n_cam_fix, n_cta;
+};
+
+__device__ __forceinline__ double step_value2(double x, double t, double d, double pa, double pb)
+{
+    return x + fma(pa, t, pb * d);
+}
+
+// inverse Cholesky factor G (lower: g00 g10 g11 g20 g21 g22) of V + reg diag(d2); false (G = 0) when not positive definite
+__device__ __forceinline__ bool invert_point_block_d2(double v0, double v1, double v2, double v3, double v4, double v5,
+                                                      double d0, double d1, double d2, double reg, double G[6])
+{
+    const double a00 = v0 + reg * d0, a10 = v1, a20 = v2;
+    const double a11 = v3 + reg * d1, a21 = v4, a22 = v5 + reg * d2;
+    bool ok = a00 > 0.0;
+    const double i00 = fast_rsqrt(a00);
+    const double c10 = a10 * i00, c20 = a20 * i00;
+    const double d11 = a11 - c10 * c10;
+    ok = ok && d11 > 0.0;
+    const double i11 = fast_rsqrt(d11);
+    const double c21 = (a21 - c20 * c10) * i11;
+    const double d22 = a22 - c20 * c20 - c21 * c21;
+    ok = ok && d22 > 0.0;
+    const double i22 = fast_rsqrt(d22);
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) G[k] = 0.0;
+        return false;
+    }
+    G[0] = i00; G[2] = i11; G[5] = i22;
+    G[1] = -c10 * i00 * i11;
+    G[4] = -c21 * i11 * i22;
+    G[3] = -(c20 * i00 + c21 * G[1]) * i22;
+    return true;
+}
+
+// block-wide sum of NV values per thread in a fixed order; result valid in thread 0..NV-1 (sm: NV * 32 doubles)
+template <int NV>
+__device__ __forceinline__ double cta_reduce_sum(double (&v)[NV], double* sm)
+{
+    warp_reduce_sum<NV>(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < NV)
+        for (int wq = 0; wq < nw; ++wq) s += sm[wq * NV + threadIdx.x];
+    __syncthreads();
+    return s;
+}
+
+// grid-wide sum: every CTA stores its NV totals (held by threads 0..NV-1), the last CTA to arrive adds them in CTA
+// order and writes scal[slots[k]].  Returns true in the last CTA (all threads), after the sums are visible to it.
+template <int NV>
+__device__ __forceinline__ bool grid_sum_last(double block_total, double* partials, unsigned* counter, double* scal,
+                                              const int* slots)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x < NV) partials[(size_t)blockIdx.x * NV + threadIdx.x] = block_total;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * NV + threadIdx.x);
+        scal[slots[threadIdx.x]] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+    __threadfence();
+    __syncthreads();
+    return true;
+}
+
+// camera records of a CTA: shared copy of camrec (M x CAMREC_STRIDE) and, for RPC, of the coefficient tables
+template <int MODEL>
+__device__ __forceinline__ void load_cameras_shared(const PatView& A, const double* __restrict__ camrec, double* s_cam,
+                                                    double* s_rpc)
+{
+    for (int t = threadIdx.x; t < A.M * CAMREC_STRIDE; t += blockDim.x) s_cam[t] = camrec[t];
+    if (MODEL == MODEL_RPC)
+        for (int t = threadIdx.x; t < A.M * RPC_TAB_STRIDE; t += blockDim.x) s_rpc[t] = A.rpc_tab[t];
+}
+
+// lane geometry of a unit
+struct LaneGeo {
+    int L, T, k, t, cam;
+    bool on;
+};
+__device__ __forceinline__ LaneGeo lane_geometry(const PUnit& u, const int* __restrict__ pat_cams, int lane)
+{
+    LaneGeo g;
+    g.L = u.L; g.T = 32 / u.L;
+    g.t = lane / u.L; g.k = lane - g.t * u.L;
+    g.on = g.t < g.T;
+    g.cam = g.on ? pat_cams[u.pat + g.k] : 0;
+    return g;
+}
+
+// sum over the track slots t of a value held by lane (t, k): afterwards lanes with t == 0 hold the total (fixed tree)
+__device__ __forceinline__ double slot_reduce(double v, const LaneGeo& g)
+{
+    for (int off = 1; off < g.T; off <<= 1) {
+        const double o = __shfl_down_sync(0xffffffffu, v, (unsigned)(off * g.L) & 31);
+        if (g.on && g.t + off < g.T) v += o;
+    }
+    return v;
+}
+
+// ordered critical section of a CTA: units flush in unit order
+__device__ __forceinline__ void ticket_wait(volatile int* ticket, int my)
+{
+    if ((threadIdx.x & 31) == 0) while (*ticket != my) { }
+    __syncwarp();
+}
+__device__ __forceinline__ void ticket_release(volatile int* ticket, int my)
+{
+    __threadfence_block();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) *ticket = my + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: trial point + fused residual / Jacobian / block assembly
+//   x_new = x + pa (g idsq) + pb delta  (initial != 0: x_new = x)
+//   outputs: x_new, camrec_new (by CTA 0), V_new, g_new (point part), per-CTA partials of [U | g_c] and of the cost
+// shared: s_cam[M*40] | s_rpc[M*90] | s_acc[M*NV] | s_stage[nwarps][9][32] | s_red[32]
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict__ g, const double* __restrict__ idsq,
+              const double* __restrict__ idsq_c, const double* __restrict__ delta, const double* __restrict__ scal,
+              int initial, int ns, int loss, double f_scale, double* __restrict__ x_new, double* __restrict__ camrec_new,
+              double* __restrict__ V_new, double* __restrict__ g_new, double* __restrict__ partials)
+{
+    constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
+    extern __shared__ double smem[];
+    double* s_cam = smem;
+    double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
+    double* s_acc = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
+    double* s_stage = s_acc + A.M * NV;
+    double* s_red = s_stage + (blockDim.x >> 5) * 9 * 32;
+    __shared__ int s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double pa = initial ? 0.0 : scal[SC_PA], pb = initial ? 0.0 : scal[SC_PB];
+    // --- prologue: camera records of the trial point (every CTA, same arithmetic; CTA 0 publishes them) ---
+    if (threadIdx.x < A.M) {
+        const int j = threadIdx.x;
+        double v[MAX_CAM_PARAMS];
+#pragma unroll
+        for (int s = 0; s < MAX_CAM_PARAMS; ++s) {
+            double val = 0.0;
+            if (s < A.P) {
+                if (s < NC) {
+                    const size_t e = (size_t)j * NC + s;
+                    const double xv = initial ? x[e] : step_value2(x[e], g[e] * idsq_c[e], delta[e], pa, pb);
+                    if (blockIdx.x == 0) x_new[e] = xv;
+                    val = j >= A.n_cam_fix ? xv : A.cam_static[(size_t)j * A.P + s];
+                } else {
+                    val = A.cam_static[(size_t)j * A.P + s];
+                }
+            }
+            v[s] = val;
+        }
+        build_camrec(v, MODEL, s_cam + j * CAMREC_STRIDE);
+    }
+    if (MODEL == MODEL_RPC)
+        for (int t = threadIdx.x; t < A.M * RPC_TAB_STRIDE; t += blockDim.x) s_rpc[t] = A.rpc_tab[t];
+    for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) s_acc[t] = 0.0;
+    if (threadIdx.x == 0) s_ticket = 0;
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int t = threadIdx.x; t < A.M * CAMREC_STRIDE; t += blockDim.x) camrec_new[t] = s_cam[t];
+
+    double cost[1] = {0.0};
+    double* stg = s_stage + warp * 9 * 32;
+    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
+    for (int u = u0 + warp; u < u1; u += nw) {
+        const PUnit un = A.units[u];
+        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
+        const double* rec = s_cam + G.cam * CAMREC_STRIDE;
+        const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
+        double acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+        for (int tb = 0; tb < un.ntrk; tb += G.T) {
+            const int tt = tb + G.t;
+            const bool on = G.on && tt < un.ntrk;
+            const int nact = min(G.T, un.ntrk - tb);
+            double vals[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) vals[q] = 0.0;
+            if (on) {
+                const int i = un.trk0 + tt;
+                const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
+                const size_t e3 = (size_t)ns + 3 * (size_t)i;
+                const double2 ob = A.pts2d[a];
+                const double wv = A.w[a];
+                double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
+                if (!initial) {
+                    X = step_value2(X, g[e3] * idsq[e3], delta[e3], pa, pb);
+                    Y = step_value2(Y, g[e3 + 1] * idsq[e3 + 1], delta[e3 + 1], pa, pb);
+                    Z = step_value2(Z, g[e3 + 2] * idsq[e3 + 2], delta[e3 + 2], pa, pb);
+                }
+                if (G.k == 0) { x_new[e3] = X; x_new[e3 + 1] = Y; x_new[e3 + 2] = Z; }
+                ObsEval<MODEL, NC> e;
+                eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+                cost[0] += e.cost;
+                vals[0] = e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
+                vals[1] = e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
+                vals[2] = e.Jp[0] * e.Jp[2] + e.Jp[3] * e.Jp[5];
+                vals[3] = e.Jp[1] * e.Jp[1] + e.Jp[4] * e.Jp[4];
+                vals[4] = e.Jp[1] * e.Jp[2] + e.Jp[4] * e.Jp[5];
+                vals[5] = e.Jp[2] * e.Jp[2] + e.Jp[5] * e.Jp[5];
+                vals[6] = e.Jp[0] * e.f0 + e.Jp[3] * e.f1;
+                vals[7] = e.Jp[1] * e.f0 + e.Jp[4] * e.f1;
+                vals[8] = e.Jp[2] * e.f0 + e.Jp[5] * e.f1;
+                int q = 0;
+#pragma unroll
+                for (int r = 0; r < NC; ++r) {
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) { acc[q] += e.Jc[r] * e.Jc[c] + e.Jc[NC + r] * e.Jc[NC + c]; ++q; }
+                }
+#pragma unroll
+                for (int r = 0; r < NC; ++r) acc[NU + r] += e.Jc[r] * e.f0 + e.Jc[NC + r] * e.f1;
+            }
+            // per-track sums of the 9 point values: one lane per (track, value)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) stg[q * 32 + lane] = vals[q];
+            __syncwarp();
+            for (int s = lane; s < 9 * nact; s += 32) {
+                const int tr = s / 9, q = s - 9 * tr;
+                const double* src = stg + q * 32 + tr * G.L;
+                double tsum = 0.0;
+                for (int m = 0; m < G.L; ++m) tsum += src[m];
+                const int it = un.trk0 + tb + tr;
+                if (q < 6) V_new[6 * (size_t)it + q] = tsum;
+                else g_new[(size_t)ns + 3 * (size_t)it + (q - 6)] = tsum;
+            }
+            __syncwarp();
+        }
+        // flush the camera blocks of the unit: sum over the track slots, then into the CTA's accumulators in unit order
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = slot_reduce(acc[q], G);
+        ticket_wait(&s_ticket, u - u0);
+        if (G.on && G.t == 0) {
+            double* dst = s_acc + G.cam * NV;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) dst[q] += acc[q];
+        }
+        ticket_release(&s_ticket, u - u0);
+    }
+    const double ctot = cta_reduce_sum<1>(cost, s_red);       // contains __syncthreads: all flushes are complete
+    for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) partials[(size_t)t * A.n_cta + blockIdx.x] = s_acc[t];
+    if (threadIdx.x == 0) partials[(size_t)A.M * NV * A.n_cta + blockIdx.x] = ctot;
+}
+
+// Sum of the per-CTA partials of k_pt_assemble -> camsys = [U (M, NC, NC) | g_c (M NC) | cost].  One CTA; one warp per
+// value, lanes stride over the CTAs, fixed shuffle tree.  fold != 0 (single GPU): also derive the camera scaling.
+//   dsq_c_new = first ? (diag U == 0 ? 1 : diag U) : max(dsq_c_cur, diag U)      (x_scale='jac', scipy common.py:598-610, squared)
+__device__ __forceinline__ void cam_scale_dev(const double* __restrict__ camsys, const double* __restrict__ dsq_c_cur,
+                                              int first, int M, int NC, double* __restrict__ dsq_c_new,
+                                              double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal)
+{
+    const int ns = M * NC;
+    for (int e = threadIdx.x; e < ns; e += blockDim.x) {
+        const int j = e / NC, s = e - j * NC;
+        const double diag = camsys[(size_t)j * NC * NC + s * NC + s];
+        const double d = first ? (diag == 0.0 ? 1.0 : diag) : fmax(dsq_c_cur[e], diag);
+        dsq_c_new[e] = d;
+        idsq_c_new[e] = 1.0 / d;
+        g_new[e] = camsys[(size_t)M * NC * NC + e];
+    }
+    if (threadIdx.x == 0) scal[SC_COST_NEW] = camsys[(size_t)M * NC * NC + ns];
+}
+
+template <int NC>
+__global__ void __launch_bounds__(1024)
+k_pt_reduce_assemble(const double* __restrict__ partials, int n_cta, int M, double* __restrict__ camsys, int fold,
+                     const double* __restrict__ dsq_c_cur, int first, double* __restrict__ dsq_c_new,
+                     double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal)
+{
+    constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int total = M * NV + 1;
+    for (int v = warp; v < total; v += nw) {
+        double s = 0.0;
+        for (int b = lane; b < n_cta; b += 32) s += partials[(size_t)v * n_cta + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane != 0) continue;
+        if (v == M * NV) { camsys[(size_t)M * NC * NC + (size_t)M * NC] = s; continue; }
+        const int j = v / NV, q = v - j * NV;
+        if (q < NU) {
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= q) ++r;
+            const int c = q - r * (r + 1) / 2;
+            camsys[(size_t)j * NC * NC + r * NC + c] = s;
+            camsys[(size_t)j * NC * NC + c * NC + r] = s;
+        } else {
+            camsys[(size_t)M * NC * NC + (size_t)j * NC + (q - NU)] = s;
+        }
+    }
+    if (!fold) return;
+    __threadfence_block();
+    __syncthreads();
+    cam_scale_dev(camsys, dsq_c_cur, first, M, NC, dsq_c_new, idsq_c_new, g_new, scal);
+}
+
+__global__ void __launch_bounds__(256)
+k_pt_cam_scale(const double* __restrict__ camsys, const double* __restrict__ dsq_c_cur, int first, int M, int NC,
+               double* __restrict__ dsq_c_new, double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal)
+{
+    cam_scale_dev(camsys, dsq_c_cur, first, M, NC, dsq_c_new, idsq_c_new, g_new, scal);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side control (shared by the single-thread kernels and the folded epilogues)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void control_reg_dev(double* scal, double delta_arg, double reg_override)
+{
+    double Delta = delta_arg;
+    if (Delta < 0.0) {
+        Delta = sqrt(scal[SC_XS]);
+        if (Delta == 0.0) Delta = 1.0;
+    }
+    scal[SC_DELTA] = Delta;
+    if (reg_override >= 0.0) { scal[SC_REG] = reg_override; return; }
+    const double gg = scal[SC_GG];
+    const double qa = 0.5 * scal[SC_A], qb = -gg;
+    const double to_tr = Delta / sqrt(gg);
+    double ag = 0.0;
+    ag = fmin(ag, to_tr * (qa * to_tr + qb));
+    if (qa != 0.0) {
+        const double ext = -0.5 * qb / qa;
+        if (ext > 0.0 && ext < to_tr) ag = fmin(ag, ext * (qa * ext + qb));
+    }
+    scal[SC_REG] = -ag / (Delta * Delta);
+}
+
+// 2-D subspace {g_h, gn_h}: the Gram scalars of (t1, delta) are turned into those of the orthogonalised pair (t1, t2 = delta -
+// alpha t1), then the exact 2-D trust-region problem is solved (scipy trf.py:496-509).  Step = pa t1 + pb delta.
+__device__ __forceinline__ void control_tr2d_gram_dev(double* scal, double delta_arg)
+{
+    const double Delta = delta_arg < 0.0 ? scal[SC_DELTA] : delta_arg;
+    const double gg = scal[SC_GG], gd = scal[SC_P_GD], dd = scal[SC_P_DD];
+    const double b11 = scal[SC_A], c12 = scal[SC_P_C12], c22 = scal[SC_P_C22];
+    const double t11 = scal[SC_P_T11], t1d = scal[SC_P_T1D], tdd = scal[SC_P_TDD];
+    const double alpha = gg > 0.0 ? gd / gg : 0.0;
+    double ww = dd - alpha * gd;                       // |gn_h - alpha g_h|^2
+    if (!(ww > 1e-14 * dd)) ww = 0.0;                  // gn_h parallel to g_h to rounding: the subspace is 1-D
+    const double b12 = c12 - alpha * b11, b22 = c22 - 2.0 * alpha * c12 + alpha * alpha * b11;
+    const double t12 = t1d - alpha * t11, t22 = fmax(0.0, tdd - 2.0 * alpha * t1d + alpha * alpha * t11);
+    const double n1 = sqrt(gg);
+    const bool rank2 = ww > 0.0 && b22 > 0.0;
+    const double n2 = rank2 ? sqrt(ww) : 1.0;
+    const double B00 = b11 / (n1 * n1), B01 = rank2 ? b12 / (n1 * n2) : 0.0, B11 = rank2 ? b22 / (n2 * n2) : 1.0;
+    const double gS0 = n1, gS1 = 0.0;                  // w is orthogonal to g_h by construction
+    double pS[2];
+    solve_trust_region_2d(B00, B01, B11, gS0, gS1, Delta, pS);
+    const double c1 = pS[0] / n1, c2 = rank2 ? pS[1] / n2 : 0.0;
+    scal[SC_C1] = c1;
+    scal[SC_C2] = c2;
+    scal[SC_PA] = c1 - c2 * alpha;
+    scal[SC_PB] = c2;
+    scal[SC_PRED] = -(0.5 * (B00 * pS[0] * pS[0] + 2.0 * B01 * pS[0] * pS[1] + B11 * pS[1] * pS[1]) + gS0 * pS[0] + gS1 * pS[1]);
+    scal[SC_STEPH] = sqrt(pS[0] * pS[0] + pS[1] * pS[1]);
+    scal[SC_STEPN] = sqrt(fmax(0.0, c1 * c1 * t11 + 2.0 * c1 * c2 * t12 + c2 * c2 * t22));
+    scal[SC_B22] = b22;                                // diagnostics read by the host
+}
+
+__global__ void k_pt_control_reg(double* scal, double delta_arg, double reg_override)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) control_reg_dev(scal, delta_arg, reg_override);
+}
+__global__ void k_pt_control_tr2d(double* scal, double delta_arg)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) control_tr2d_gram_dev(scal, delta_arg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: scaling of the points + |g_h|^2, |x D|^2, |x|^2, max|g| + |J_h g_h|^2  (-> damping)
+//   dsq_p = first ? (diag V == 0 ? 1 : diag V) : max(dsq_p, diag V), idsq_p = 1 / dsq_p   (in place, one writer per track)
+// shared: s_cam | s_rpc | s_t1c[ns] | s_red
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
+          const double* __restrict__ g, const double* __restrict__ dsq_c, const double* __restrict__ idsq_c,
+          double* __restrict__ dsq, double* __restrict__ idsq, int first, int ns, int loss, double f_scale,
+          int count_cameras, int rank, double* partials, unsigned* counter, double* scal, int fold_ctl, double delta_arg)
+{
+    extern __shared__ double smem[];
+    double* s_cam = smem;
+    double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
+    double* s_t1c = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
+    double* s_red = s_t1c + ns;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
+    for (int e = threadIdx.x; e < ns; e += blockDim.x) s_t1c[e] = g[e] * idsq_c[e];
+    __syncthreads();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};       // gg, xs, xx, |J t1|^2
+    double gmax = 0.0;
+    if (blockIdx.x == 0 && count_cameras) {
+        for (int e = threadIdx.x; e < ns; e += blockDim.x) {
+            const double gv = g[e], xv = x[e];
+            acc[0] += gv * gv * idsq_c[e];
+            acc[1] += xv * xv * dsq_c[e];
+            acc[2] += xv * xv;
+            gmax = fmax(gmax, fabs(gv));
+        }
+    }
+    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
+    for (int u = u0 + warp; u < u1; u += nw) {
+        const PUnit un = A.units[u];
+        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
+        const double* rec = s_cam + G.cam * CAMREC_STRIDE;
+        const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
+        const double* t1c = s_t1c + G.cam * NC;
+        for (int tb = 0; tb < un.ntrk; tb += G.T) {
+            const int tt = tb + G.t;
+            if (!(G.on && tt < un.ntrk)) continue;
+            const int i = un.trk0 + tt;
+            const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
+            const size_t e3 = (size_t)ns + 3 * (size_t)i;
+            const double2 ob = A.pts2d[a];
+            const double wv = A.w[a];
+            const double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
+            const double vd[3] = {V[6 * (size_t)i], V[6 * (size_t)i + 3], V[6 * (size_t)i + 5]};
+            double t1p[3], d2[3], gp[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                gp[q] = g[e3 + q];
+                d2[q] = first ? (vd[q] == 0.0 ? 1.0 : vd[q]) : fmax(dsq[e3 + q], vd[q]);
+                const double id = fast_rcp(d2[q]);
+                t1p[q] = gp[q] * id;
+                if (G.k == 0) { dsq[e3 + q] = d2[q]; idsq[e3 + q] = id; }
+            }
+            if (G.k == 0) {
+                acc[0] += gp[0] * t1p[0] + gp[1] * t1p[1] + gp[2] * t1p[2];
+                acc[1] += X * X * d2[0] + Y * Y * d2[1] + Z * Z * d2[2];
+                acc[2] += X * X + Y * Y + Z * Z;
+                gmax = fmax(gmax, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+            }
+            ObsEval<MODEL, NC> e;
+            eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+            double y0 = e.Jp[0] * t1p[0] + e.Jp[1] * t1p[1] + e.Jp[2] * t1p[2];
+            double y1 = e.Jp[3] * t1p[0] + e.Jp[4] * t1p[1] + e.Jp[5] * t1p[2];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) { y0 += e.Jc[q] * t1c[q]; y1 += e.Jc[NC + q] * t1c[q]; }
+            acc[3] += y0 * y0 + y1 * y1;
+        }
+    }
+    // max |g| of this rank (non-negative doubles order like their bit patterns; the slot is zeroed by the host)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
+    if (lane == 0 && gmax > 0.0)
+        atomicMax((unsigned long long*)(scal + SC_GMAX_SLOTS + rank), (unsigned long long)__double_as_longlong(gmax));
+    const double tot = cta_reduce_sum<4>(acc, s_red);
+    __shared__ int slots[4];
+    if (threadIdx.x == 0) { slots[0] = SC_GG; slots[1] = SC_XS; slots[2] = SC_XX; slots[3] = SC_A; }
+    __syncthreads();
+    const bool last = grid_sum_last<4>(tot, partials, counter, scal, slots);
+    if (last && fold_ctl && threadIdx.x == 0) control_reg_dev(scal, delta_arg, -1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: point elimination + Schur complement in shared memory
+// shared: s_cam | s_rpc | s_S[NC*NC*M(M+1)/2] | s_rhs[ns] | s_Z[nwarps][32 * ZP]
+// S is stored by upper block rows: block (j, j' >= j) at NC*NC * (j M - j (j-1)/2 + j' - j), row-major NC x NC.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int pt_block_offset(int j, int jp, int M, int NC)
+{
+    return NC * NC * (j * M - j * (j - 1) / 2 + (jp - j));
+}
+
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(PT_THREADS_SCHUR, 1)
+k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
+           const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ scal, int ns, int loss,
+           double f_scale, double* __restrict__ partials, double* bad_points)
+{
+    constexpr int ZS = NC * 3, ZP = ZS + 1;
+    constexpr int NCH = (NC + PT_RC - 1) / PT_RC;        // row chunks per camera block
+    constexpr int NA = PT_RC * NC;                       // accumulators per task
+    extern __shared__ double smem[];
+    const int nS = NC * NC * (A.M * (A.M + 1) / 2);
+    double* s_cam = smem;
+    double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
+    double* s_S = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
+    double* s_rhs = s_S + nS;
+    double* s_Z = s_rhs + ns;
+    __shared__ int s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double reg = scal[SC_REG];
+    load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
+    for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) s_S[t] = 0.0;
+    if (threadIdx.x == 0) s_ticket = 0;
+    __syncthreads();
+    double* zs = s_Z + (size_t)warp * (32 * ZP + PT_RC * 3);          // tail padding: the last chunk may read past row NC-1
+    int nbad = 0;
+    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
+    for (int u = u0 + warp; u < u1; u += nw) {
+        const PUnit un = A.units[u];
+        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
+        const double* rec = s_cam + G.cam * CAMREC_STRIDE;
+        const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
+        const int npair = G.L * (G.L + 1) / 2, ntask = npair * NCH, npass = (ntask + 63) / 64;
+        // few tasks (short tracks): npar groups of lanes take every npar-th track slot of a tile in parallel
+        const int npar = ntask <= 16 ? 32 / ntask : 1;
+        const int par = npar > 1 ? lane / ntask : 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            // tasks of this lane: (position pair ka <= kb, row chunk h)
+            int ka[2], kb[2], hh[2];
+            bool tv[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                int tau = pass * 64 + q * 32 + lane;
+                tv[q] = tau < ntask;
+                if (npar > 1) { tau = lane - par * ntask; tv[q] = q == 0 && par < npar; }
+                const int pr = tv[q] ? tau / NCH : 0;
+                hh[q] = tv[q] ? tau - pr * NCH : 0;
+                int a = 0, rem = pr;
+                while (rem >= G.L - a) { rem -= G.L - a; ++a; }
+                ka[q] = a; kb[q] = a + rem;
+            }
+            double acc[2][NA], accR[NC];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int m = 0; m < NA; ++m) acc[q][m] = 0.0;
+#pragma unroll
+            for (int r = 0; r < NC; ++r) accR[r] = 0.0;
+            for (int tb = 0; tb < un.ntrk; tb += G.T) {
+                const int tt = tb + G.t;
+                const bool on = G.on && tt < un.ntrk;
+                const int nact = min(G.T, un.ntrk - tb);
+                if (on) {
+                    const int i = un.trk0 + tt;
+                    const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
+                    const size_t e3 = (size_t)ns + 3 * (size_t)i;
+                    const double2 ob = A.pts2d[a];
+                    const double wv = A.w[a];
+                    const double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
+                    const double* v = V + 6 * (size_t)i;
+                    double Gm[6], qv[3] = {0.0, 0.0, 0.0};
+                    bool ok = false;
+                    if (pt_free) ok = invert_point_block_d2(v[0], v[1], v[2], v[3], v[4], v[5], dsq[e3], dsq[e3 + 1], dsq[e3 + 2], reg, Gm);
+                    if (!ok) {
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) Gm[m] = 0.0;
+                        if (pt_free && G.k == 0 && pass == 0) ++nbad;
+                    } else {
+                        const double g0 = g[e3], g1 = g[e3 + 1], g2 = g[e3 + 2];
+                        qv[0] = Gm[0] * g0;
+                        qv[1] = Gm[1] * g0 + Gm[2] * g1;
+                        qv[2] = Gm[3] * g0 + Gm[4] * g1 + Gm[5] * g2;
+                    }
+                    ObsEval<MODEL, NC> e;
+                    eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+                    double* z = zs + lane * ZP;
+#pragma unroll
+                    for (int r = 0; r < NC; ++r) {
+                        const double w0 = e.Jc[r] * e.Jp[0] + e.Jc[NC + r] * e.Jp[3];
+                        const double w1 = e.Jc[r] * e.Jp[1] + e.Jc[NC + r] * e.Jp[4];
+                        const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
+                        const double z0 = w0 * Gm[0], z1 = w0 * Gm[1] + w1 * Gm[2], z2 = w0 * Gm[3] + w1 * Gm[4] + w2 * Gm[5];
+                        z[3 * r] = z0; z[3 * r + 1] = z1; z[3 * r + 2] = z2;
+                        if (pass == 0) accR[r] += z0 * qv[0] + z1 * qv[1] + z2 * qv[2];
+                    }
+                }
+                __syncwarp();
+                for (int ts = par; ts < nact; ts += npar) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (!tv[q]) continue;
+                        const double* za = zs + (ts * G.L + ka[q]) * ZP + hh[q] * PT_RC * 3;
+                        const double* zb = zs + (ts * G.L + kb[q]) * ZP;
+                        double Ar[PT_RC * 3];
+#pragma unroll
+                        for (int m = 0; m < PT_RC * 3; ++m) Ar[m] = za[m];
+#pragma unroll
+                        for (int s = 0; s < NC; ++s) {
+                            const double b0 = zb[3 * s], b1 = zb[3 * s + 1], b2 = zb[3 * s + 2];
+#pragma unroll
+                            for (int r = 0; r < PT_RC; ++r)
+                                acc[q][r * NC + s] += Ar[3 * r] * b0 + Ar[3 * r + 1] * b1 + Ar[3 * r + 2] * b2;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (npar > 1) {        // sum over the parallel groups (fixed tree); group 0 flushes
+                for (int off = 1; off < npar; off <<= 1) {
+#pragma unroll
+                    for (int m = 0; m < NA; ++m) {
+                        const double o = __shfl_down_sync(0xffffffffu, acc[0][m], (unsigned)(off * ntask));
+                        if (tv[0] && par + off < npar) acc[0][m] += o;
+                    }
+                }
+                tv[0] = tv[0] && par == 0;
+            }
+            // flush in unit order: the ticket is taken by the first pass and handed on after the last one
+            if (pass == 0) {
+#pragma unroll
+                for (int r = 0; r < NC; ++r) accR[r] = slot_reduce(accR[r], G);
+                ticket_wait(&s_ticket, u - u0);
+                if (G.on && G.t == 0) {
+#pragma unroll
+                    for (int r = 0; r < NC; ++r) s_rhs[G.cam * NC + r] += accR[r];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!tv[q]) continue;
+                const int ja = A.pat_cams[un.pat + ka[q]], jb = A.pat_cams[un.pat + kb[q]];
+                double* dst = s_S + pt_block_offset(ja, jb, A.M, NC) + hh[q] * PT_RC * NC;
+#pragma unroll
+                for (int r = 0; r < PT_RC; ++r) {
+                    if (hh[q] * PT_RC + r >= NC) break;
+#pragma unroll
+                    for (int s = 0; s < NC; ++s) dst[r * NC + s] += acc[q][r * NC + s];
+                }
+            }
+            if (pass == npass - 1) ticket_release(&s_ticket, u - u0);
+            else __syncwarp();
+        }
+    }
+    if (nbad) atomicAdd(bad_points, (double)nbad);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) partials[(size_t)t * A.n_cta + blockIdx.x] = s_S[t];
+}
+
+// Sum of the per-CTA Schur partials -> reduced camera system S (ns x ns column-major, symmetric, both triangles) and its
+// right-hand side:  S_jj' = [j == j'] (U_j + reg D_j^2) - sum,  rhs_j = -g_j + sum.  One warp per value.
+// add_diag: rank 0 only (the all-reduce over ranks then counts U and the damping once).
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_pt_reduce_schur(const double* __restrict__ partials, int n_cta, int M, int n_cam_fix, const double* __restrict__ camsys,
+                  const double* __restrict__ dsq_c, const double* __restrict__ scal, int add_diag, double* __restrict__ S)
+{
+    const int lane = threadIdx.x & 31;
+    const int ns = M * NC, nS = NC * NC * (M * (M + 1) / 2);
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (v >= nS + ns) return;
+    double s = 0.0;
+    for (int b = lane; b < n_cta; b += 32) s += partials[(size_t)v * n_cta + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane != 0) return;
+    const double reg = scal[SC_REG];
+    if (v >= nS) {
+        const int e = v - nS;
+        S[(size_t)ns * ns + e] = (add_diag ? -camsys[(size_t)M * NC * NC + e] : 0.0) + s;
+        return;
+    }
+    int b = v / (NC * NC);
+    const int rs = v - b * NC * NC, r = rs / NC, c = rs - r * NC;
+    int j = 0;
+    while (b >= M - j) { b -= M - j; ++j; }
+    const int jp = j + b;
+    double val = -s;
+    if (j == jp && add_diag) {
+        val += camsys[(size_t)j * NC * NC + r * NC + c];
+        if (r == c) val += (j < n_cam_fix) ? 1.0 : reg * dsq_c[(size_t)j * NC + r];
+    }
+    S[(size_t)(j * NC + r) + (size_t)(jp * NC + c) * ns] = val;
+    if (j != jp) S[(size_t)(jp * NC + c) + (size_t)(j * NC + r) * ns] = val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: back-substitution dp_i = -(V_i + reg D_i^2)^-1 (g_i + W_i^T dc) and the Gram scalars of {t1, delta}
+//   sums: g.delta, |D delta|^2, (J t1).(J delta), |J delta|^2, |t1|^2, t1.delta, |delta|^2
+// shared: s_cam | s_rpc | s_dc[ns] | s_t1c[ns] | s_stage[nwarps][3][32] | s_red
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
+             const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ idsq,
+             const double* __restrict__ dsq_c, const double* __restrict__ idsq_c, double* __restrict__ delta, int ns, int loss,
+             double f_scale, int count_cameras, double* partials, unsigned* counter, double* scal, int fold_ctl)
+{
+    extern __shared__ double smem[];
+    double* s_cam = smem;
+    double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
+    double* s_dc = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
+    double* s_t1c = s_dc + ns;
+    double* s_stage = s_t1c + ns;
+    double* s_red = s_stage + (blockDim.x >> 5) * 3 * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double reg = scal[SC_REG];
+    load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
+    for (int e = threadIdx.x; e < ns; e += blockDim.x) { s_dc[e] = delta[e]; s_t1c[e] = g[e] * idsq_c[e]; }
+    __syncthreads();
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // gd, dd, c12, c22, t11, t1d, tdd
+    if (blockIdx.x == 0 && count_cameras) {
+        for (int e = threadIdx.x; e < ns; e += blockDim.x) {
+            const double d = s_dc[e], t = s_t1c[e];
+            acc[0] += g[e] * d; acc[1] += dsq_c[e] * d * d; acc[4] += t * t; acc[5] += t * d; acc[6] += d * d;
+        }
+    }
+    double* stg = s_stage + warp * 3 * 32;
+    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
+    for (int u = u0 + warp; u < u1; u += nw) {
+        const PUnit un = A.units[u];
+        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
+        const double* rec = s_cam + G.cam * CAMREC_STRIDE;
+        const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
+        const double* dc = s_dc + G.cam * NC;
+        const double* t1c = s_t1c + G.cam * NC;
+        for (int tb = 0; tb < un.ntrk; tb += G.T) {
+            const int tt = tb + G.t;
+            const bool on = G.on && tt < un.ntrk;
+            ObsEval<MODEL, NC> e;
+            double yc0 = 0.0, yc1 = 0.0;
+            size_t e3 = 0;
+            if (on) {
+                const int i = un.trk0 + tt;
+                const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
+                e3 = (size_t)ns + 3 * (size_t)i;
+                const double2 ob = A.pts2d[a];
+                eval_obs<MODEL, NC, true>(rec, rpc_j, x[e3], x[e3 + 1], x[e3 + 2], ob.x, ob.y, A.w[a], loss, f_scale, cam_free,
+                                          pt_free, e);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) { yc0 += e.Jc[q] * dc[q]; yc1 += e.Jc[NC + q] * dc[q]; }
+                stg[lane] = e.Jp[0] * yc0 + e.Jp[3] * yc1;
+                stg[32 + lane] = e.Jp[1] * yc0 + e.Jp[4] * yc1;
+                stg[64 + lane] = e.Jp[2] * yc0 + e.Jp[5] * yc1;
+            }
+            __syncwarp();
+            if (on) {
+                const int i = un.trk0 + tt;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                const int l0 = G.t * G.L;
+                for (int m = 0; m < G.L; ++m) { s0 += stg[l0 + m]; s1 += stg[32 + l0 + m]; s2 += stg[64 + l0 + m]; }
+                const double* v = V + 6 * (size_t)i;
+                const double gp0 = g[e3], gp1 = g[e3 + 1], gp2 = g[e3 + 2];
+                double Gm[6];
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+                if (pt_free && invert_point_block_d2(v[0], v[1], v[2], v[3], v[4], v[5], dsq[e3], dsq[e3 + 1], dsq[e3 + 2], reg, Gm)) {
+                    const double v0 = gp0 + s0, v1 = gp1 + s1, v2 = gp2 + s2;
+                    const double t0 = Gm[0] * v0, t1 = Gm[1] * v0 + Gm[2] * v1, t2 = Gm[3] * v0 + Gm[4] * v1 + Gm[5] * v2;
+                    d0 = -(Gm[0] * t0 + Gm[1] * t1 + Gm[3] * t2);
+                    d1 = -(Gm[2] * t1 + Gm[4] * t2);
+                    d2 = -(Gm[5] * t2);
+                }
+                const double tp0 = gp0 * idsq[e3], tp1 = gp1 * idsq[e3 + 1], tp2 = gp2 * idsq[e3 + 2];
+                if (G.k == 0) {
+                    delta[e3] = d0; delta[e3 + 1] = d1; delta[e3 + 2] = d2;
+                    acc[0] += gp0 * d0 + gp1 * d1 + gp2 * d2;
+                    acc[1] += dsq[e3] * d0 * d0 + dsq[e3 + 1] * d1 * d1 + dsq[e3 + 2] * d2 * d2;
+                    acc[4] += tp0 * tp0 + tp1 * tp1 + tp2 * tp2;
+                    acc[5] += tp0 * d0 + tp1 * d1 + tp2 * d2;
+                    acc[6] += d0 * d0 + d1 * d1 + d2 * d2;
+                }
+                const double jd0 = yc0 + e.Jp[0] * d0 + e.Jp[1] * d1 + e.Jp[2] * d2;
+                const double jd1 = yc1 + e.Jp[3] * d0 + e.Jp[4] * d1 + e.Jp[5] * d2;
+                double jt0 = e.Jp[0] * tp0 + e.Jp[1] * tp1 + e.Jp[2] * tp2;
+                double jt1 = e.Jp[3] * tp0 + e.Jp[4] * tp1 + e.Jp[5] * tp2;
+#pragma unroll
+                for (int q = 0; q < NC; ++q) { jt0 += e.Jc[q] * t1c[q]; jt1 += e.Jc[NC + q] * t1c[q]; }
+                acc[2] += jt0 * jd0 + jt1 * jd1;
+                acc[3] += jd0 * jd0 + jd1 * jd1;
+            }
+            __syncwarp();
+        }
+    }
+    const double tot = cta_reduce_sum<7>(acc, s_red);
+    __shared__ int slots[7];
+    if (threadIdx.x == 0) {
+        slots[0] = SC_P_GD; slots[1] = SC_P_DD; slots[2] = SC_P_C12; slots[3] = SC_P_C22; slots[4] = SC_P_T11; slots[5] = SC_P_T1D;
+        slots[6] = SC_P_TDD;
+    }
+    __syncthreads();
+    const bool last = grid_sum_last<7>(tot, partials, counter, scal, slots);
+    if (last && fold_ctl && threadIdx.x == 0) control_tr2d_gram_dev(scal, -1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary permutations: the caller's order <-> the internal (pattern-major) order
+// ------------------------------------------------------------------------------------------------
+// x_int = [cameras | points of internal track t = points of caller's track new2old[t]]
+__global__ void k_pt_points_in(const double* __restrict__ x_ext, const int* __restrict__ new2old, long long N, int ns,
+                               double* __restrict__ x_int)
+{
+    const long long n3 = 3 * N;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ns + n3; q += (long long)gridDim.x * blockDim.x) {
+        if (q < ns) { x_int[q] = x_ext[q]; continue; }
+        const long long e = q - ns, t = e / 3;
+        x_int[q] = x_ext[ns + 3 * (long long)new2old[t] + (e - 3 * t)];
+    }
+}
+__global__ void k_pt_points_out(const double* __restrict__ x_int, const int* __restrict__ new2old, long long N, int ns,
+                                double* __restrict__ x_ext)
+{
+    const long long n3 = 3 * N;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ns + n3; q += (long long)gridDim.x * blockDim.x) {
+        if (q < ns) { x_ext[q] = x_int[q]; continue; }
+        const long long e = q - ns, t = e / 3;
+        x_ext[ns + 3 * (long long)new2old[t] + (e - 3 * t)] = x_int[q];
+    }
+}
+// per-observation records of `width` doubles: out_ext[new2old[a]] = in_int[a]
+__global__ void k_pt_obs_out(const double* __restrict__ in_int, const int* __restrict__ new2old, long long K, int width,
+                             double* __restrict__ out_ext)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < K * width; q += (long long)gridDim.x * blockDim.x) {
+        const long long a = q / width;
+        out_ext[(long long)new2old[a] * width + (q - a * width)] = in_int[q];
+    }
+}
+__global__ void k_pt_obs_in(const double* __restrict__ in_ext, const int* __restrict__ new2old, long long K, int width,
+                            double* __restrict__ out_int)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < K * width; q += (long long)gridDim.x * blockDim.x) {
+        const long long a = q / width;
+        out_int[q] = in_ext[(long long)new2old[a] * width + (q - a * width)];
+    }
+}
+__global__ void k_pt_fill(double* __restrict__ dst, double v, long long n)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) dst[q] = v;
+}
+
+}  // namespace sba

@@ -3,6 +3,7 @@
 #include "../../sat_bundleadjust_b200/csrc/sba_models.cuh"
 #include "../../sat_bundleadjust_b200/csrc/sba_tr2d.h"
 #include "../../sat_bundleadjust_b200/csrc/sba_index.h"
+#include "../../sat_bundleadjust_b200/csrc/sba_pattern.h"
 
 using namespace sba;
 
@@ -86,6 +87,27 @@ int hh_host_index(const long long* cam_ind, const long long* pts_ind, long long 
     std::copy(h.ch_cam.begin(), h.ch_cam.end(), ch_cam); std::copy(h.ch_beg.begin(), h.ch_beg.end(), ch_beg);
     std::copy(h.ch_end.begin(), h.ch_end.end(), ch_end); std::copy(h.first_chunk.begin(), h.first_chunk.end(), first_chunk);
     std::copy(h.tile_obs.begin(), h.tile_obs.end(), tile_obs);
+    return 0;
+}
+
+
+// pattern-major layout (csrc/sba_pattern.h): sizes first (NULL outputs), then the arrays.
+// sizes = [ok, n_units, n_pat_cams, n_frozen_tracks, unit_tiles, n_runs]; units as 8 ints each
+int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, int N, int n_pts_fix, int n_cta, int warps,
+                      int* sizes, int* trk_new2old, int* obs_new2old, int* track_ptr_new, int* units, int* pat_cams, int* cta_unit0)
+{
+    PatternLayout L;
+    build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, warps, L);
+    sizes[0] = L.ok ? 1 : 0; sizes[1] = (int)L.units.size(); sizes[2] = (int)L.pat_cams.size(); sizes[3] = L.n_frozen_tracks;
+    sizes[4] = L.unit_tiles; sizes[5] = L.n_runs;
+    if (!L.ok || !trk_new2old) return 0;
+    std::copy(L.trk_new2old.begin(), L.trk_new2old.end(), trk_new2old);
+    std::copy(L.obs_new2old.begin(), L.obs_new2old.end(), obs_new2old);
+    std::copy(L.track_ptr.begin(), L.track_ptr.end(), track_ptr_new);
+    static_assert(sizeof(PUnit) == 8 * sizeof(int), "PUnit layout");
+    std::copy((const int*)L.units.data(), (const int*)L.units.data() + 8 * L.units.size(), units);
+    std::copy(L.pat_cams.begin(), L.pat_cams.end(), pat_cams);
+    std::copy(L.cta_unit0.begin(), L.cta_unit0.end(), cta_unit0);
     return 0;
 }
 

@@ -383,3 +383,75 @@ def test_host_index_rejects_bad_input(built):
     assert _host_index([0, 1, 5], [0, 0, 1], 3, 2)[0] == 1          # camera out of range
     assert _host_index([0, 1, 0], [0, 2, 1], 3, 3)[0] == 2          # tracks not sorted
     assert _host_index([0, 1], [0, 7], 3, 3)[0] == 1                # track out of range
+
+
+def _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=0, n_cta=148, warps=16):
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness", "libmodel_harness.so"))
+    ip = ctypes.POINTER(ctypes.c_int)
+    cam = np.ascontiguousarray(cam_ind, dtype=np.int32)
+    tp = np.ascontiguousarray(np.searchsorted(pts_ind, np.arange(N + 1), side="left"), dtype=np.int32)
+    K = cam.size
+    sizes = (ctypes.c_int * 6)()
+    null = ctypes.cast(None, ip)
+    args = [cam.ctypes.data_as(ip), tp.ctypes.data_as(ip), ctypes.c_longlong(K), M, N, n_pts_fix, n_cta, warps, sizes]
+    lib.hh_pattern_layout(*args, *([null] * 6))
+    if not sizes[0]:
+        return None
+    out = {"trk_new2old": np.zeros(N, np.int32), "obs_new2old": np.zeros(K, np.int32), "track_ptr": np.zeros(N + 1, np.int32),
+           "units": np.zeros((sizes[1], 8), np.int32), "pat_cams": np.zeros(sizes[2], np.int32), "cta_unit0": np.zeros(n_cta + 1, np.int32)}
+    lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "pat_cams", "cta_unit0")])
+    out["n_frozen"], out["unit_tiles"], out["n_runs"] = sizes[3], sizes[4], sizes[5]
+    return out
+
+
+@pytest.mark.parametrize("M,N,p_vis,fix", [(10, 100000, 0.5, 0), (10, 5000, 0.5, 37), (22, 3000, 0.3, 0), (3, 50, 0.5, 5), (6, 2000, 0.9, 0)])
+def test_pattern_layout(built, M, N, p_vis, fix):
+    """csrc/sba_pattern.h: the internal order is a permutation that groups tracks by (frozen, camera set); units tile every
+    track with observations exactly once; inside a unit all tracks see the unit's camera list."""
+    rng = np.random.default_rng(M * 100 + N)
+    seen = rng.random((N, M)) < p_vis
+    seen[rng.random(N) < 0.05] = False
+    pts_ind, cam_ind = np.nonzero(seen)
+    K = pts_ind.size
+    lay = _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=fix)
+    assert lay is not None
+    t2o, o2o, tp = lay["trk_new2old"], lay["obs_new2old"], lay["track_ptr"]
+    assert np.array_equal(np.sort(t2o), np.arange(N)) and np.array_equal(np.sort(o2o), np.arange(K))
+    lens_old = np.bincount(pts_ind, minlength=N)
+    assert np.array_equal(np.diff(tp), lens_old[t2o])
+    # observations of an internal track are the caller's observations of that track, cameras ascending
+    tp_old = np.searchsorted(pts_ind, np.arange(N + 1))
+    first = o2o[tp[:-1][lens_old[t2o] > 0]]
+    assert np.array_equal(first, tp_old[t2o][lens_old[t2o] > 0])
+    assert np.all(pts_ind[o2o] == np.repeat(t2o, lens_old[t2o]))
+    # frozen tracks (with observations) come first
+    nf = int(np.sum(lens_old[:fix] > 0))
+    assert lay["n_frozen"] == nf and set(t2o[:nf].tolist()) == set(np.nonzero(lens_old[:fix] > 0)[0].tolist())
+    # units: disjoint, cover all tracks with observations, uniform camera list
+    covered = np.zeros(N, bool)
+    units = lay["units"]
+    for trk0, ntrk, obs0, L, pat, free, _, _ in units.tolist():
+        assert 1 <= L <= 32 and ntrk >= 1 and obs0 == tp[trk0]
+        assert not covered[trk0: trk0 + ntrk].any()
+        covered[trk0: trk0 + ntrk] = True
+        cams = lay["pat_cams"][pat: pat + L]
+        assert np.all(np.diff(cams) > 0)
+        obs = cam_ind[o2o[obs0: obs0 + ntrk * L]].reshape(ntrk, L)
+        assert np.all(obs == cams[None, :])
+        assert np.all((t2o[trk0: trk0 + ntrk] >= fix) == bool(free))
+        assert ntrk <= (32 // L) * lay["unit_tiles"]
+    assert np.array_equal(covered, lens_old[t2o] > 0)
+    cu = lay["cta_unit0"]
+    assert cu[0] == 0 and cu[-1] == len(units) and np.all(np.diff(cu) >= 0)
+    # static balance: no CTA holds more than ~2x its share of tiles (for problems with enough tiles)
+    tiles = np.array([(u[1] + (32 // u[3]) - 1) // (32 // u[3]) for u in units.tolist()])
+    per_cta = np.array([tiles[cu[c]: cu[c + 1]].sum() for c in range(cu.size - 1)])
+    if tiles.sum() > 20 * 148:
+        assert per_cta.max() <= 1.3 * tiles.sum() / 148 + 16
+
+
+def test_pattern_layout_rejects(built):
+    # cameras not ascending inside a track / a track longer than 32 observations -> generic engine
+    assert _pattern_layout([1, 0], [0, 0], 2, 1) is None
+    assert _pattern_layout(np.arange(40), np.zeros(40, int), 40, 1) is None
