@@ -25,9 +25,9 @@ constexpr int PT_MAX_NS = 132;            // reduced camera system that still fi
 constexpr int PT_RC = 3;                  // rows of a camera block per Schur task
 
 struct PatView {
-    const PUnit* units;
+    const PUnit* units;       // assignment for this kernel's CTA shape
+    const int* warp_unit0;    // (n_cta * warps + 1)
     const int* pat_cams;
-    const int* cta_unit0;
     const double2* pts2d;     // internal observation order
     const double* w;
     const double* cam_static; // (M, P) initial camera parameters
@@ -130,7 +130,7 @@ struct LaneGeo {
 __device__ __forceinline__ LaneGeo lane_geometry(const PUnit& u, const int* __restrict__ pat_cams, int lane)
 {
     LaneGeo g;
-    g.L = u.L; g.T = 32 / u.L;
+    g.L = u.L; g.T = min(32 / u.L, PT_MAX_T);
     g.t = lane / u.L; g.k = lane - g.t * u.L;
     g.on = g.t < g.T;
     g.cam = g.on ? pat_cams[u.pat + g.k] : 0;
@@ -150,7 +150,7 @@ __device__ __forceinline__ double slot_reduce(double v, const LaneGeo& g)
 // ordered critical section of a CTA: units flush in unit order
 __device__ __forceinline__ void ticket_wait(volatile int* ticket, int my)
 {
-    if ((threadIdx.x & 31) == 0) while (*ticket != my) { }
+    if ((threadIdx.x & 31) == 0) while (*ticket != my) __nanosleep(40);      // sleeping warps leave the issue slots to the others
     __syncwarp();
 }
 __device__ __forceinline__ void ticket_release(volatile int* ticket, int my)
@@ -164,7 +164,7 @@ __device__ __forceinline__ void ticket_release(volatile int* ticket, int my)
 // K1: trial point + fused residual / Jacobian / block assembly
 //   x_new = x + pa (g idsq) + pb delta  (initial != 0: x_new = x)
 //   outputs: x_new, camrec_new (by CTA 0), V_new, g_new (point part), per-CTA partials of [U | g_c] and of the cost
-// shared: s_cam[M*40] | s_rpc[M*90] | s_acc[M*NV] | s_stage[nwarps][9][32] | s_red[32]
+// shared: s_cam[M*40] | s_rpc[M*90] | s_acc[nwarps][M*NV] | s_stage[nwarps][9][32] | s_red
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int NC>
 __global__ void __launch_bounds__(PT_THREADS, 1)
@@ -178,10 +178,9 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
     double* s_cam = smem;
     double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
     double* s_acc = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
-    double* s_stage = s_acc + A.M * NV;
-    double* s_red = s_stage + (blockDim.x >> 5) * 9 * 32;
-    __shared__ int s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* s_stage = s_acc + nw * A.M * NV;
+    double* s_red = s_stage + nw * 9 * 33;
     const double pa = initial ? 0.0 : scal[SC_PA], pb = initial ? 0.0 : scal[SC_PB];
     // --- prologue: camera records of the trial point (every CTA, same arithmetic; CTA 0 publishes them) ---
     if (threadIdx.x < A.M) {
@@ -206,16 +205,16 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
     }
     if (MODEL == MODEL_RPC)
         for (int t = threadIdx.x; t < A.M * RPC_TAB_STRIDE; t += blockDim.x) s_rpc[t] = A.rpc_tab[t];
-    for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) s_acc[t] = 0.0;
-    if (threadIdx.x == 0) s_ticket = 0;
+    for (int t = threadIdx.x; t < nw * A.M * NV; t += blockDim.x) s_acc[t] = 0.0;
     __syncthreads();
     if (blockIdx.x == 0)
         for (int t = threadIdx.x; t < A.M * CAMREC_STRIDE; t += blockDim.x) camrec_new[t] = s_cam[t];
 
     double cost[1] = {0.0};
-    double* stg = s_stage + warp * 9 * 32;
-    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
-    for (int u = u0 + warp; u < u1; u += nw) {
+    double* stg = s_stage + warp * 9 * 33;           // stride 33: the (track, value) lanes below read conflict-free
+    double* my_acc = s_acc + warp * A.M * NV;            // camera blocks of this warp's units: private, no ordering needed
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
@@ -267,11 +266,11 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
             }
             // per-track sums of the 9 point values: one lane per (track, value)
 #pragma unroll
-            for (int q = 0; q < 9; ++q) stg[q * 32 + lane] = vals[q];
+            for (int q = 0; q < 9; ++q) stg[q * 33 + lane] = vals[q];
             __syncwarp();
             for (int s = lane; s < 9 * nact; s += 32) {
                 const int tr = s / 9, q = s - 9 * tr;
-                const double* src = stg + q * 32 + tr * G.L;
+                const double* src = stg + q * 33 + tr * G.L;
                 double tsum = 0.0;
                 for (int m = 0; m < G.L; ++m) tsum += src[m];
                 const int it = un.trk0 + tb + tr;
@@ -280,19 +279,22 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
             }
             __syncwarp();
         }
-        // flush the camera blocks of the unit: sum over the track slots, then into the CTA's accumulators in unit order
+        // flush the camera blocks of the unit: sum over the track slots, then into the warp's accumulators
 #pragma unroll
         for (int q = 0; q < NV; ++q) acc[q] = slot_reduce(acc[q], G);
-        ticket_wait(&s_ticket, u - u0);
         if (G.on && G.t == 0) {
-            double* dst = s_acc + G.cam * NV;
+            double* dst = my_acc + G.cam * NV;
 #pragma unroll
             for (int q = 0; q < NV; ++q) dst[q] += acc[q];
         }
-        ticket_release(&s_ticket, u - u0);
+        __syncwarp();
     }
     const double ctot = cta_reduce_sum<1>(cost, s_red);       // contains __syncthreads: all flushes are complete
-    for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) partials[(size_t)t * A.n_cta + blockIdx.x] = s_acc[t];
+    for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) {
+        double sum = 0.0;
+        for (int wq = 0; wq < nw; ++wq) sum += s_acc[wq * A.M * NV + t];     // warp order: fixed
+        partials[(size_t)t * A.n_cta + blockIdx.x] = sum;
+    }
     if (threadIdx.x == 0) partials[(size_t)A.M * NV * A.n_cta + blockIdx.x] = ctot;
 }
 
@@ -306,46 +308,58 @@ __device__ __forceinline__ void cam_scale_dev(const double* __restrict__ camsys,
     const int ns = M * NC;
     for (int e = threadIdx.x; e < ns; e += blockDim.x) {
         const int j = e / NC, s = e - j * NC;
-        const double diag = camsys[(size_t)j * NC * NC + s * NC + s];
+        const double diag = __ldcg(camsys + (size_t)j * NC * NC + s * NC + s);
         const double d = first ? (diag == 0.0 ? 1.0 : diag) : fmax(dsq_c_cur[e], diag);
         dsq_c_new[e] = d;
         idsq_c_new[e] = 1.0 / d;
-        g_new[e] = camsys[(size_t)M * NC * NC + e];
+        g_new[e] = __ldcg(camsys + (size_t)M * NC * NC + e);
     }
-    if (threadIdx.x == 0) scal[SC_COST_NEW] = camsys[(size_t)M * NC * NC + ns];
+    if (threadIdx.x == 0) scal[SC_COST_NEW] = __ldcg(camsys + (size_t)M * NC * NC + ns);
 }
 
 template <int NC>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_pt_reduce_assemble(const double* __restrict__ partials, int n_cta, int M, double* __restrict__ camsys, int fold,
                      const double* __restrict__ dsq_c_cur, int first, double* __restrict__ dsq_c_new,
-                     double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal)
+                     double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal, unsigned* counter)
 {
     constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int total = M * NV + 1;
-    for (int v = warp; v < total; v += nw) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (v < total) {
         double s = 0.0;
         for (int b = lane; b < n_cta; b += 32) s += partials[(size_t)v * n_cta + b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane != 0) continue;
-        if (v == M * NV) { camsys[(size_t)M * NC * NC + (size_t)M * NC] = s; continue; }
-        const int j = v / NV, q = v - j * NV;
-        if (q < NU) {
-            int r = 0;
-            while ((r + 1) * (r + 2) / 2 <= q) ++r;
-            const int c = q - r * (r + 1) / 2;
-            camsys[(size_t)j * NC * NC + r * NC + c] = s;
-            camsys[(size_t)j * NC * NC + c * NC + r] = s;
-        } else {
-            camsys[(size_t)M * NC * NC + (size_t)j * NC + (q - NU)] = s;
+        if (lane == 0) {
+            if (v == M * NV) {
+                camsys[(size_t)M * NC * NC + (size_t)M * NC] = s;
+            } else {
+                const int j = v / NV, q = v - j * NV;
+                if (q < NU) {
+                    int r = 0;
+                    while ((r + 1) * (r + 2) / 2 <= q) ++r;
+                    const int c = q - r * (r + 1) / 2;
+                    camsys[(size_t)j * NC * NC + r * NC + c] = s;
+                    camsys[(size_t)j * NC * NC + c * NC + r] = s;
+                } else {
+                    camsys[(size_t)M * NC * NC + (size_t)j * NC + (q - NU)] = s;
+                }
+            }
         }
     }
     if (!fold) return;
-    __threadfence_block();
+    // the last CTA to finish derives the camera scaling from the complete sums
+    __shared__ bool is_last;
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
     cam_scale_dev(camsys, dsq_c_cur, first, M, NC, dsq_c_new, idsq_c_new, g_new, scal);
+    if (threadIdx.x == 0) *counter = 0u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -451,8 +465,8 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
             gmax = fmax(gmax, fabs(gv));
         }
     }
-    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
-    for (int u = u0 + warp; u < u1; u += nw) {
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
@@ -516,15 +530,52 @@ __host__ __device__ inline int pt_block_offset(int j, int jp, int M, int NC)
     return NC * NC * (j * M - j * (j - 1) / 2 + (jp - j));
 }
 
+// tasks of a lane in one pass over a unit: (position pair ka <= kb, row chunk h); few tasks (short tracks): npar groups of
+// lanes take every npar-th track slot of a tile in parallel
+template <int NC>
+struct SchurTasks {
+    static constexpr int NCH = (NC + PT_RC - 1) / PT_RC;
+    int ntask, npass, npar, par;
+    int ka[2], kb[2], hh[2];
+    bool tv[2];
+    __device__ __forceinline__ void unit(int L, int lane)
+    {
+        ntask = L * (L + 1) / 2 * NCH;
+        npass = (ntask + 63) / 64;
+        npar = ntask <= 16 ? 32 / ntask : 1;
+        par = npar > 1 ? lane / ntask : 0;
+    }
+    __device__ __forceinline__ void pass(int L, int lane, int p)
+    {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            int tau = p * 64 + q * 32 + lane;
+            tv[q] = tau < ntask;
+            if (npar > 1) { tau = lane - par * ntask; tv[q] = q == 0 && par < npar; }
+            const int pr = tv[q] ? tau / NCH : 0;
+            hh[q] = tv[q] ? tau - pr * NCH : 0;
+            int a = 0, rem = pr;
+            while (rem >= L - a) { rem -= L - a; ++a; }
+            ka[q] = a; kb[q] = a + rem;
+        }
+    }
+};
+
+// One record per (unit, pass): the lane-private sums of a pass, [2 tasks][NA values][32 lanes] then [NC rhs values][32 lanes]
+// (rows a pass does not use are neither written nor read).  Records are written when a warp leaves a unit and merged into
+// the CTA's shared-memory S after all warps are done, warp by warp in unit order: fixed summation order without any
+// waiting inside the main loop.
+template <int NC> __host__ __device__ constexpr int pt_record_doubles() { return (2 * PT_RC * NC + NC) * 32; }
+
 template <int MODEL, int NC>
 __global__ void __launch_bounds__(PT_THREADS_SCHUR, 1)
 k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
            const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ scal, int ns, int loss,
-           double f_scale, double* __restrict__ partials, double* bad_points)
+           double f_scale, double* __restrict__ records, double* __restrict__ partials, double* bad_points)
 {
     constexpr int ZS = NC * 3, ZP = ZS + 1;
-    constexpr int NCH = (NC + PT_RC - 1) / PT_RC;        // row chunks per camera block
     constexpr int NA = PT_RC * NC;                       // accumulators per task
+    constexpr int REC = pt_record_doubles<NC>();
     extern __shared__ double smem[];
     const int nS = NC * NC * (A.M * (A.M + 1) / 2);
     double* s_cam = smem;
@@ -532,41 +583,24 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
     double* s_S = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
     double* s_rhs = s_S + nS;
     double* s_Z = s_rhs + ns;
-    __shared__ int s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double reg = scal[SC_REG];
     load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
     for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) s_S[t] = 0.0;
-    if (threadIdx.x == 0) s_ticket = 0;
     __syncthreads();
     double* zs = s_Z + (size_t)warp * (32 * ZP + PT_RC * 3);          // tail padding: the last chunk may read past row NC-1
     int nbad = 0;
-    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
-    for (int u = u0 + warp; u < u1; u += nw) {
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    SchurTasks<NC> tk;
+    for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
         const double* rec = s_cam + G.cam * CAMREC_STRIDE;
         const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
-        const int npair = G.L * (G.L + 1) / 2, ntask = npair * NCH, npass = (ntask + 63) / 64;
-        // few tasks (short tracks): npar groups of lanes take every npar-th track slot of a tile in parallel
-        const int npar = ntask <= 16 ? 32 / ntask : 1;
-        const int par = npar > 1 ? lane / ntask : 0;
-        for (int pass = 0; pass < npass; ++pass) {
-            // tasks of this lane: (position pair ka <= kb, row chunk h)
-            int ka[2], kb[2], hh[2];
-            bool tv[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int tau = pass * 64 + q * 32 + lane;
-                tv[q] = tau < ntask;
-                if (npar > 1) { tau = lane - par * ntask; tv[q] = q == 0 && par < npar; }
-                const int pr = tv[q] ? tau / NCH : 0;
-                hh[q] = tv[q] ? tau - pr * NCH : 0;
-                int a = 0, rem = pr;
-                while (rem >= G.L - a) { rem -= G.L - a; ++a; }
-                ka[q] = a; kb[q] = a + rem;
-            }
+        tk.unit(G.L, lane);
+        for (int pass = 0; pass < tk.npass; ++pass) {
+            tk.pass(G.L, lane, pass);
             double acc[2][NA], accR[NC];
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -613,12 +647,12 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                     }
                 }
                 __syncwarp();
-                for (int ts = par; ts < nact; ts += npar) {
+                for (int ts = tk.par; ts < nact; ts += tk.npar) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        if (!tv[q]) continue;
-                        const double* za = zs + (ts * G.L + ka[q]) * ZP + hh[q] * PT_RC * 3;
-                        const double* zb = zs + (ts * G.L + kb[q]) * ZP;
+                        if (!tk.tv[q]) continue;
+                        const double* za = zs + (ts * G.L + tk.ka[q]) * ZP + tk.hh[q] * PT_RC * 3;
+                        const double* zb = zs + (ts * G.L + tk.kb[q]) * ZP;
                         double Ar[PT_RC * 3];
 #pragma unroll
                         for (int m = 0; m < PT_RC * 3; ++m) Ar[m] = za[m];
@@ -633,44 +667,68 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                 }
                 __syncwarp();
             }
-            if (npar > 1) {        // sum over the parallel groups (fixed tree); group 0 flushes
-                for (int off = 1; off < npar; off <<= 1) {
+            if (tk.npar > 1) {        // sum over the parallel groups (fixed tree); group 0 keeps the result
+                for (int off = 1; off < tk.npar; off <<= 1) {
 #pragma unroll
                     for (int m = 0; m < NA; ++m) {
-                        const double o = __shfl_down_sync(0xffffffffu, acc[0][m], (unsigned)(off * ntask));
-                        if (tv[0] && par + off < npar) acc[0][m] += o;
+                        const double o = __shfl_down_sync(0xffffffffu, acc[0][m], (unsigned)(off * tk.ntask));
+                        if (tk.tv[0] && tk.par + off < tk.npar) acc[0][m] += o;
                     }
                 }
-                tv[0] = tv[0] && par == 0;
             }
-            // flush in unit order: the ticket is taken by the first pass and handed on after the last one
-            if (pass == 0) {
-#pragma unroll
-                for (int r = 0; r < NC; ++r) accR[r] = slot_reduce(accR[r], G);
-                ticket_wait(&s_ticket, u - u0);
-                if (G.on && G.t == 0) {
-#pragma unroll
-                    for (int r = 0; r < NC; ++r) s_rhs[G.cam * NC + r] += accR[r];
-                }
-            }
+            // the record of this (unit, pass)
+            double* rp = records + (size_t)(un.rec + pass) * REC;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!tv[q]) continue;
-                const int ja = A.pat_cams[un.pat + ka[q]], jb = A.pat_cams[un.pat + kb[q]];
-                double* dst = s_S + pt_block_offset(ja, jb, A.M, NC) + hh[q] * PT_RC * NC;
+                if (pass * 64 + q * 32 >= tk.ntask) continue;        // warp-uniform: no lane has this task
 #pragma unroll
-                for (int r = 0; r < PT_RC; ++r) {
-                    if (hh[q] * PT_RC + r >= NC) break;
-#pragma unroll
-                    for (int s = 0; s < NC; ++s) dst[r * NC + s] += acc[q][r * NC + s];
-                }
+                for (int m = 0; m < NA; ++m) rp[(q * NA + m) * 32 + lane] = acc[q][m];
             }
-            if (pass == npass - 1) ticket_release(&s_ticket, u - u0);
-            else __syncwarp();
+            if (pass == 0) {
+#pragma unroll
+                for (int r = 0; r < NC; ++r) rp[(2 * NA + r) * 32 + lane] = slot_reduce(accR[r], G);
+            }
         }
     }
     if (nbad) atomicAdd(bad_points, (double)nbad);
+    __threadfence_block();
     __syncthreads();
+    // merge: warp by warp, units and passes in order
+    for (int wq = 0; wq < nw; ++wq) {
+        if (warp == wq) {
+            for (int u = u0; u < u1; ++u) {
+                const PUnit un = A.units[u];
+                const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+                tk.unit(G.L, lane);
+                for (int pass = 0; pass < tk.npass; ++pass) {
+                    tk.pass(G.L, lane, pass);
+                    const double* rp = records + (size_t)(un.rec + pass) * REC;
+                    if (tk.npar > 1) tk.tv[0] = tk.tv[0] && tk.par == 0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (!tk.tv[q]) continue;
+                        double val[NA];
+#pragma unroll
+                        for (int m = 0; m < NA; ++m) val[m] = __ldcg(rp + (q * NA + m) * 32 + lane);
+                        const int ja = A.pat_cams[un.pat + tk.ka[q]], jb = A.pat_cams[un.pat + tk.kb[q]];
+                        double* dst = s_S + pt_block_offset(ja, jb, A.M, NC) + tk.hh[q] * PT_RC * NC;
+#pragma unroll
+                        for (int r = 0; r < PT_RC; ++r) {
+                            if (tk.hh[q] * PT_RC + r >= NC) break;
+#pragma unroll
+                            for (int s = 0; s < NC; ++s) dst[r * NC + s] += val[r * NC + s];
+                        }
+                    }
+                    if (pass == 0 && G.on && G.t == 0) {
+#pragma unroll
+                        for (int r = 0; r < NC; ++r) s_rhs[G.cam * NC + r] += __ldcg(rp + (2 * NA + r) * 32 + lane);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+    }
     for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) partials[(size_t)t * A.n_cta + blockIdx.x] = s_S[t];
 }
 
@@ -743,8 +801,8 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
         }
     }
     double* stg = s_stage + warp * 3 * 32;
-    const int u0 = A.cta_unit0[blockIdx.x], u1 = A.cta_unit0[blockIdx.x + 1];
-    for (int u = u0 + warp; u < u1; u += nw) {
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;

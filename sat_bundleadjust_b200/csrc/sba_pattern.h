@@ -14,10 +14,11 @@
 //
 //   run   = maximal set of tracks with identical (frozen flag, camera set); frozen tracks come first, tracks without
 //           observations last
-//   tile  = floor(32 / L) tracks of a run = one pass of a warp, lane = slot * L + position
-//   unit  = up to `unit_tiles` consecutive tiles of a run = the work item of one warp (static assignment, so that
-//           every reduction has a fixed order and results are reproducible bit for bit)
-//   CTA c owns units [cta_unit0[c], cta_unit0[c+1]); its warps take them round-robin.
+//   tile  = min(floor(32 / L), 16) tracks of a run = one pass of a warp, lane = slot * L + position
+//   unit  = the tiles of ONE run inside the contiguous tile range of one warp (every warp of the persistent grid gets
+//           the same number of tiles; a range usually touches one or two runs).  Register accumulators live for a
+//           whole unit.  The assignment is static, so every reduction has a fixed order and results are reproducible
+//           bit for bit.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -33,7 +34,17 @@ struct PUnit {            // 32 bytes, read by every lane of the warp that owns 
     int L;                // observations per track (1..32)
     int pat;              // offset of the camera list in pat_cams
     int pts_free;         // 0: the points of this run are frozen (the caller's first n_pts_fix tracks)
-    int pad0, pad1;
+    int rec;              // first record of this unit in the Schur record buffer (one record per pass over the unit)
+    int pad;
+};
+
+// static work assignment for kernels launched with `warps` warps per CTA: warp w of CTA c owns the units
+// [warp_unit0[c * warps + w], warp_unit0[c * warps + w + 1])
+struct PatternAssignment {
+    int warps = 0;
+    int n_records = 0;                 // Schur records (sum over units of the passes a unit needs)
+    std::vector<PUnit> units;
+    std::vector<int> warp_unit0;       // (n_cta * warps + 1)
 };
 
 struct PatternLayout {
@@ -42,23 +53,90 @@ struct PatternLayout {
     std::vector<int> trk_new2old;      // (N) internal track -> caller's track (tracks without observations last)
     std::vector<int> obs_new2old;      // (K) internal observation -> caller's observation
     std::vector<int> track_ptr;        // (N+1) internal track offsets
-    std::vector<PUnit> units;
     std::vector<int> pat_cams;
-    std::vector<int> cta_unit0;        // (n_cta + 1)
-    int n_cta = 0, Lmax = 0, n_runs = 0, unit_tiles = 0;
+    PatternAssignment wide, narrow;    // assignments for the two CTA shapes in use (more / fewer warps per CTA)
+    int n_cta = 0, Lmax = 0, n_runs = 0;
     int n_frozen_tracks = 0;           // frozen tracks with observations = internal tracks [0, n_frozen_tracks)
     long long n_tiles = 0;
 };
 
+constexpr int PT_MAX_T = 16;           // track slots per tile (bounds the per-warp staging buffers)
+inline int pattern_tile_tracks(int L) { return std::min(32 / L, PT_MAX_T); }
+
+struct PatternRun { int trk0, ntrk, L, pts_free, pat; long long tile0; };
+
+// passes of the Schur kernel over a unit: a lane holds at most two (camera pair, row chunk) tasks at a time
+inline int pattern_schur_passes(int L, int nc, int rows_per_task)
+{
+    const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
+    return (ntask + 63) / 64;
+}
+
+// relative cost of one tile: uniform for the evaluation kernels (one observation per lane); for the Schur kernel the
+// evaluation (once per pass) plus the product rounds (track slots / parallel groups x tasks per lane)
+inline int pattern_tile_cost(int L, int nc, int rows_per_task, bool schur)
+{
+    if (!schur) return 8;
+    const int T = pattern_tile_tracks(L);
+    const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
+    const int npar = ntask <= 16 ? 32 / ntask : 1;
+    const int rounds = (T + npar - 1) / npar;
+    int cost = 0;
+    for (int left = ntask; left > 0; left -= 64) cost += 8 + rounds * (left > 32 ? 2 : 1) * 3;
+    return cost;
+}
+
+// Cut the tile sequence of the runs into one contiguous range per warp (equal cost); a unit is the part of a warp's
+// range inside one run.
+inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std::vector<int>& track_ptr, int n_cta, int warps,
+                                 int nc, int rows_per_task, bool schur, PatternAssignment& A)
+{
+    A.warps = warps;
+    A.units.clear();
+    A.n_records = 0;
+    const long long nw = (long long)n_cta * warps;
+    A.warp_unit0.assign(nw + 1, 0);
+    // cumulative cost at the start of every run
+    std::vector<long long> cost0(runs.size() + 1, 0);
+    for (size_t r = 0; r < runs.size(); ++r) {
+        const int T = pattern_tile_tracks(runs[r].L);
+        cost0[r + 1] = cost0[r] + (long long)((runs[r].ntrk + T - 1) / T) * pattern_tile_cost(runs[r].L, nc, rows_per_task, schur);
+    }
+    const long long total = cost0.back();
+    size_t r = 0;
+    long long tile = 0;          // next unassigned tile of run r
+    for (long long g = 0; g < nw; ++g) {
+        A.warp_unit0[g] = (int)A.units.size();
+        const long long target = total * (g + 1) / nw;       // this warp takes tiles while the cumulative cost stays <= target
+        while (r < runs.size()) {
+            const PatternRun& R = runs[r];
+            const int T = pattern_tile_tracks(R.L), c = pattern_tile_cost(R.L, nc, rows_per_task, schur);
+            const long long run_tiles = (R.ntrk + T - 1) / T;
+            const long long done = cost0[r] + tile * c;
+            long long take = g == nw - 1 ? run_tiles - tile : std::min(run_tiles - tile, (target - done) / c);
+            if (take <= 0) break;
+            PUnit u;
+            const int s0 = (int)tile * T;
+            u.trk0 = R.trk0 + s0; u.ntrk = (int)std::min<long long>(take * T, R.ntrk - s0); u.obs0 = track_ptr[u.trk0];
+            u.L = R.L; u.pat = R.pat; u.pts_free = R.pts_free; u.rec = A.n_records; u.pad = 0;
+            A.n_records += pattern_schur_passes(R.L, nc, rows_per_task);
+            A.units.push_back(u);
+            tile += take;
+            if (tile == run_tiles) { ++r; tile = 0; } else break;
+        }
+    }
+    A.warp_unit0[nw] = (int)A.units.size();
+}
+
 // cam: (K) camera of every observation, caller's order; track_ptr_old: (N+1) first observation of every track.
 // n_pts_fix: the caller's first n_pts_fix tracks are frozen.
 inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long long K, int M, int N, int n_pts_fix,
-                                 int n_cta, int warps_per_cta, PatternLayout& out)
+                                 int n_cta, int warps_wide, int warps_narrow, int nc, int rows_per_task, PatternLayout& out)
 {
     out = PatternLayout();
     if (M > 64) { out.why = "more than 64 cameras"; return; }
     if (N < 1 || K < 1) { out.why = "empty"; return; }
-    // key = camera bit set (+ frozen flag as bit 64 handled by a separate byte)
+    // key = camera bit set; aux orders frozen tracks first and tracks without observations last
     std::vector<uint64_t> key(N);
     std::vector<unsigned char> aux(N);          // bit 0: free (frozen tracks come first), bit 1: no observations (sorted last)
     int Lmax = 0;
@@ -101,9 +179,8 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
         const int o = order[t], a0 = track_ptr_old[o], L = track_ptr_old[o + 1] - a0, b0 = out.track_ptr[t];
         for (int k = 0; k < L; ++k) out.obs_new2old[b0 + k] = a0 + k;
     }
-    // runs -> tiles
-    struct Run { int trk0, ntrk, L, pts_free; };
-    std::vector<Run> runs;
+    // runs and their tiles
+    std::vector<PatternRun> runs;
     long long tiles = 0;
     for (int t = 0; t < N;) {
         const int o = order[t];
@@ -111,41 +188,19 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
         int e = t + 1;
         while (e < N && key[order[e]] == key[o] && aux[order[e]] == aux[o]) ++e;
         const int L = track_ptr_old[o + 1] - track_ptr_old[o];
-        runs.push_back({t, e - t, L, (aux[o] & 1) ? 1 : 0});
-        const int T = 32 / L;
+        const int pat = (int)out.pat_cams.size();
+        for (int a = track_ptr_old[o]; a < track_ptr_old[o + 1]; ++a) out.pat_cams.push_back(cam[a]);
+        runs.push_back({t, e - t, L, (aux[o] & 1) ? 1 : 0, pat, tiles});
+        const int T = pattern_tile_tracks(L);
         tiles += (e - t + T - 1) / T;
         t = e;
     }
     out.n_runs = (int)runs.size();
     out.n_tiles = tiles;
-    // unit size: ~6 units per warp for balance, at most 16 tiles (flush cost amortised), at least 1
-    long long ut = tiles / ((long long)n_cta * warps_per_cta * 6);
-    out.unit_tiles = (int)std::max<long long>(1, std::min<long long>(16, ut));
-    std::vector<long long> unit_cost;
-    for (const Run& r : runs) {
-        const int pat = (int)out.pat_cams.size();
-        const int o = order[r.trk0];
-        for (int a = track_ptr_old[o]; a < track_ptr_old[o + 1]; ++a) out.pat_cams.push_back(cam[a]);
-        const int T = 32 / r.L, per_unit = T * out.unit_tiles;
-        for (int s = 0; s < r.ntrk; s += per_unit) {
-            PUnit u;
-            u.trk0 = r.trk0 + s; u.ntrk = std::min(per_unit, r.ntrk - s); u.obs0 = out.track_ptr[u.trk0];
-            u.L = r.L; u.pat = pat; u.pts_free = r.pts_free; u.pad0 = u.pad1 = 0;
-            out.units.push_back(u);
-            unit_cost.push_back((u.ntrk + T - 1) / T);
-        }
-    }
-    // contiguous split of the units over the CTAs by cumulative tile count
     out.n_cta = n_cta;
-    out.cta_unit0.assign(n_cta + 1, 0);
-    long long acc = 0;
-    size_t u = 0;
-    for (int c = 0; c < n_cta; ++c) {
-        out.cta_unit0[c] = (int)u;
-        const long long target = tiles * (c + 1) / n_cta;
-        while (u < out.units.size() && (acc + unit_cost[u] <= target || c == n_cta - 1)) { acc += unit_cost[u]; ++u; }
-    }
-    out.cta_unit0[n_cta] = (int)out.units.size();
+    if (runs.empty()) { out.why = "no observations"; return; }
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_wide, nc, rows_per_task, false, out.wide);
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_narrow, nc, rows_per_task, true, out.narrow);
     out.ok = true;
 }
 

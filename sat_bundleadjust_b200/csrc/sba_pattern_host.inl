@@ -6,10 +6,12 @@
 //     K1 trial point: cost AND the blocks of the next iteration (an accepted step costs nothing more)
 // i.e. 6 launches and 4 Jacobian evaluations per observation and iteration, nothing per-observation stored in HBM.
 
-static PatView pat_view(const sba_problem* p)
+static PatView pat_view(const sba_problem* p, bool narrow = false)
 {
     PatView A;
-    A.units = (const PUnit*)p->pt_units; A.pat_cams = p->pt_pat_cams; A.cta_unit0 = p->pt_cta_unit0;
+    A.units = (const PUnit*)(narrow ? p->pt_units_narrow : p->pt_units);
+    A.warp_unit0 = narrow ? p->pt_warp_unit0_narrow : p->pt_warp_unit0;
+    A.pat_cams = p->pt_pat_cams;
     A.pts2d = (const double2*)p->pts2d; A.w = p->w; A.cam_static = p->cam_static; A.rpc_tab = p->rpc_tab;
     A.M = p->M; A.P = p->P; A.n_cam_fix = p->n_cam_fix; A.n_cta = p->pt_n_cta;
     return A;
@@ -24,7 +26,7 @@ static size_t pt_smem_common(const sba_problem* p)
 static size_t pt_smem_assemble(const sba_problem* p)
 {
     const int nv = p->nc * (p->nc + 1) / 2 + p->nc;
-    return (pt_smem_common(p) + (size_t)p->M * nv + (PT_THREADS / 32) * 9 * 32 + PT_RED_DOUBLES) * sizeof(double);
+    return (pt_smem_common(p) + (size_t)(PT_THREADS / 32) * p->M * nv + (PT_THREADS / 32) * 9 * 33 + PT_RED_DOUBLES) * sizeof(double);
 }
 static size_t pt_smem_jvp1(const sba_problem* p)
 {
@@ -100,8 +102,9 @@ static int pt_run_assemble(sba_problem* p, int initial, int first, int loss, dou
         pat_view(p), p->x, p->g, p->idsq, p->idsqc, p->delta, p->scal, initial, ns, loss, f_scale, p->x_new, p->camrec_new,    \
         p->V2, p->g2, p->pt_partials);                                                                                         \
     SBA_TRY(check_launch(p));                                                                                                  \
-    k_pt_reduce_assemble<NC><<<1, 1024, 0, p->stream>>>(p->pt_partials, p->pt_n_cta, p->M, p->camsys2, p->world == 1, p->dsqc, \
-                                                        first, p->dsqc2, p->idsqc2, p->g2, p->scal)
+    k_pt_reduce_assemble<NC><<<(p->M * (NC * (NC + 1) / 2 + NC) + 1 + 7) / 8, 256, 0, p->stream>>>(                          \
+        p->pt_partials, p->pt_n_cta, p->M, p->camsys2, p->world == 1, p->dsqc, first, p->dsqc2, p->idsqc2, p->g2, p->scal,     \
+        p->counters + 4)
     PT_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
@@ -148,7 +151,8 @@ static int pt_run_schur(sba_problem* p, int loss, double f_scale)
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
 #define L(MODEL, NC)                                                                                                        \
     k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                                   \
-        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsq, p->scal, ns, loss, f_scale, p->pt_partials, p->scal + SC_BAD_POINTS); \
+        pat_view(p, true), p->x, p->camrec, p->V, p->g, p->dsq, p->scal, ns, loss, f_scale, p->pt_records, p->pt_partials,    \
+        p->scal + SC_BAD_POINTS);                                                                                            \
     SBA_TRY(check_launch(p));                                                                                                \
     k_pt_reduce_schur<NC><<<(nS + ns + 7) / 8, 256, 0, p->stream>>>(p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, \
                                                                    p->dsqc, p->scal, p->rank == 0, p->S)
@@ -353,12 +357,14 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_upload(p, &p->trk_new2old, lay.trk_new2old, s));
     SBA_TRY(dev_upload(p, &p->obs_new2old, lay.obs_new2old, s));
     SBA_TRY(dev_upload(p, &p->pt_pat_cams, lay.pat_cams, s));
-    SBA_TRY(dev_upload(p, &p->pt_cta_unit0, lay.cta_unit0, s));
-    {
+    SBA_TRY(dev_upload(p, &p->pt_warp_unit0, lay.wide.warp_unit0, s));
+    SBA_TRY(dev_upload(p, &p->pt_warp_unit0_narrow, lay.narrow.warp_unit0, s));
+    for (int k = 0; k < 2; ++k) {
+        const std::vector<PUnit>& hu = k ? lay.narrow.units : lay.wide.units;
         PUnit* du = nullptr;
-        SBA_TRY(dev_alloc(p, &du, lay.units.size()));
-        SBA_CUDA(cudaMemcpyAsync(du, lay.units.data(), lay.units.size() * sizeof(PUnit), cudaMemcpyHostToDevice, s));
-        p->pt_units = du;
+        SBA_TRY(dev_alloc(p, &du, hu.size()));
+        SBA_CUDA(cudaMemcpyAsync(du, hu.data(), hu.size() * sizeof(PUnit), cudaMemcpyHostToDevice, s));
+        (k ? p->pt_units_narrow : p->pt_units) = du;
     }
     // warp tiles of the generic per-track kernels are not used by this engine
     p->n_tiles = 0;
@@ -407,6 +413,7 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
     const size_t nv = (size_t)nc * (nc + 1) / 2 + nc, nS = (size_t)nc * nc * ((size_t)M * (M + 1) / 2);
     SBA_TRY(dev_alloc(p, &p->pt_partials, std::max((size_t)M * nv + 1, nS + ns) * lay.n_cta));
+    SBA_TRY(dev_alloc(p, &p->pt_records, (size_t)std::max(1, lay.narrow.n_records) * (2 * PT_RC * nc + nc) * 32));
     SBA_TRY(dev_alloc(p, &p->red_partials, (size_t)std::max(NUM_SMS * 16, lay.n_cta + 1) * 8));
     SBA_TRY(dev_alloc(p, &p->counters, 16));
     SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));

@@ -399,22 +399,25 @@ def _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=0, n_cta=148, warps=16):
     if not sizes[0]:
         return None
     out = {"trk_new2old": np.zeros(N, np.int32), "obs_new2old": np.zeros(K, np.int32), "track_ptr": np.zeros(N + 1, np.int32),
-           "units": np.zeros((sizes[1], 8), np.int32), "pat_cams": np.zeros(sizes[2], np.int32), "cta_unit0": np.zeros(n_cta + 1, np.int32)}
-    lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "pat_cams", "cta_unit0")])
-    out["n_frozen"], out["unit_tiles"], out["n_runs"] = sizes[3], sizes[4], sizes[5]
+           "units": np.zeros((sizes[1], 8), np.int32), "pat_cams": np.zeros(sizes[2], np.int32),
+           "warp_unit0": np.zeros(n_cta * warps + 1, np.int32)}
+    lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "pat_cams", "warp_unit0")])
+    out["n_frozen"], out["n_tiles"], out["n_runs"] = sizes[3], sizes[4], sizes[5]
     return out
 
 
 @pytest.mark.parametrize("M,N,p_vis,fix", [(10, 100000, 0.5, 0), (10, 5000, 0.5, 37), (22, 3000, 0.3, 0), (3, 50, 0.5, 5), (6, 2000, 0.9, 0)])
 def test_pattern_layout(built, M, N, p_vis, fix):
     """csrc/sba_pattern.h: the internal order is a permutation that groups tracks by (frozen, camera set); units tile every
-    track with observations exactly once; inside a unit all tracks see the unit's camera list."""
+    track with observations exactly once; inside a unit all tracks see the unit's camera list; every warp of the persistent
+    grid owns a contiguous, equally long tile range."""
     rng = np.random.default_rng(M * 100 + N)
     seen = rng.random((N, M)) < p_vis
     seen[rng.random(N) < 0.05] = False
     pts_ind, cam_ind = np.nonzero(seen)
     K = pts_ind.size
-    lay = _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=fix)
+    n_cta, warps = 148, 16
+    lay = _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=fix, n_cta=n_cta, warps=warps)
     assert lay is not None
     t2o, o2o, tp = lay["trk_new2old"], lay["obs_new2old"], lay["track_ptr"]
     assert np.array_equal(np.sort(t2o), np.arange(N)) and np.array_equal(np.sort(o2o), np.arange(K))
@@ -428,10 +431,11 @@ def test_pattern_layout(built, M, N, p_vis, fix):
     # frozen tracks (with observations) come first
     nf = int(np.sum(lens_old[:fix] > 0))
     assert lay["n_frozen"] == nf and set(t2o[:nf].tolist()) == set(np.nonzero(lens_old[:fix] > 0)[0].tolist())
-    # units: disjoint, cover all tracks with observations, uniform camera list
+    # units: disjoint, in track order, cover all tracks with observations, uniform camera list
     covered = np.zeros(N, bool)
     units = lay["units"]
-    for trk0, ntrk, obs0, L, pat, free, _, _ in units.tolist():
+    tiles = []
+    for trk0, ntrk, obs0, L, pat, free, rank, _ in units.tolist():
         assert 1 <= L <= 32 and ntrk >= 1 and obs0 == tp[trk0]
         assert not covered[trk0: trk0 + ntrk].any()
         covered[trk0: trk0 + ntrk] = True
@@ -440,15 +444,19 @@ def test_pattern_layout(built, M, N, p_vis, fix):
         obs = cam_ind[o2o[obs0: obs0 + ntrk * L]].reshape(ntrk, L)
         assert np.all(obs == cams[None, :])
         assert np.all((t2o[trk0: trk0 + ntrk] >= fix) == bool(free))
-        assert ntrk <= (32 // L) * lay["unit_tiles"]
+        T = min(32 // L, 16)
+        tiles.append((ntrk + T - 1) // T)
     assert np.array_equal(covered, lens_old[t2o] > 0)
-    cu = lay["cta_unit0"]
-    assert cu[0] == 0 and cu[-1] == len(units) and np.all(np.diff(cu) >= 0)
-    # static balance: no CTA holds more than ~2x its share of tiles (for problems with enough tiles)
-    tiles = np.array([(u[1] + (32 // u[3]) - 1) // (32 // u[3]) for u in units.tolist()])
-    per_cta = np.array([tiles[cu[c]: cu[c + 1]].sum() for c in range(cu.size - 1)])
-    if tiles.sum() > 20 * 148:
-        assert per_cta.max() <= 1.3 * tiles.sum() / 148 + 16
+    assert np.all(np.diff(units[:, 0]) > 0)
+    tiles = np.array(tiles)
+    assert tiles.sum() == lay["n_tiles"]
+    wu = lay["warp_unit0"]
+    assert wu[0] == 0 and wu[-1] == len(units) and np.all(np.diff(wu) >= 0)
+    per_warp = np.array([tiles[wu[g]: wu[g + 1]].sum() for g in range(n_cta * warps)])
+    if tiles.sum() >= 4 * n_cta * warps:
+        assert per_warp.max() - per_warp.min() <= 2                  # equal tile counts per warp (uniform cost model)
+    passes = (units[:, 3] * (units[:, 3] + 1) // 2 * 2 + 63) // 64      # Schur records: one per pass over a unit (n_params 6: 2 row chunks)
+    assert np.array_equal(units[:, 6], np.concatenate([[0], np.cumsum(passes)[:-1]]))
 
 
 def test_pattern_layout_rejects(built):
