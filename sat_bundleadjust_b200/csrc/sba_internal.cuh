@@ -157,12 +157,13 @@ struct sba_problem {
     std::vector<int> h_trk_new2old, h_obs_new2old;       // host copies (test-only entry points un-permute on the host)
     int *trk_new2old = nullptr, *obs_new2old = nullptr;  // device
     void *pt_units = nullptr, *pt_units_narrow = nullptr;           // device PUnit[]: assignments for the two CTA shapes
-    int *pt_pat_cams = nullptr, *pt_warp_unit0 = nullptr, *pt_warp_unit0_narrow = nullptr;
+    int *pt_warp_unit0 = nullptr, *pt_warp_unit0_narrow = nullptr;
     int pt_n_cta = 0;
     double *V2 = nullptr, *g2 = nullptr, *camsys2 = nullptr;        // second buffer set (trial point)
     double *dsq = nullptr, *idsq = nullptr;                         // (n) squared column scales of the points and their reciprocals
     double *dsqc = nullptr, *dsqc2 = nullptr, *idsqc = nullptr, *idsqc2 = nullptr;   // (ns) the same for the cameras, double-buffered
     double *pt_partials = nullptr;                                  // per-CTA partial sums, [value][cta]
+    double *osc = nullptr, *osc2 = nullptr;                         // (2K) per-observation robust row scales at the current / trial point
     double *pt_records = nullptr;                                   // Schur records, one per (unit, pass)
     double *r_int = nullptr, *e_int = nullptr;                      // (2K), (K) residuals / errors in internal order
 };

@@ -10,7 +10,7 @@
 //                   Z_a Z_b^T of a track accumulated in registers by fixed (camera pair, row chunk) lanes, flushed
 //                   once per unit into the CTA's shared-memory copy of S -- no Z in HBM, no pair lists    (G3)
 //   k_pt_backsub    point steps from the camera step, and the Gram scalars of the 2-D subspace {g, gn}    (G6)
-// Every reduction has a fixed order (static unit -> CTA -> warp assignment, ticketed flushes), so results are
+// Every reduction has a fixed order (static unit -> warp assignment, ordered merges), so results are
 // reproducible bit for bit.  Included by sba_ba.cu only.
 #pragma once
 #include "sba_kernels.cuh"
@@ -27,7 +27,6 @@ constexpr int PT_RC = 3;                  // rows of a camera block per Schur ta
 struct PatView {
     const PUnit* units;       // assignment for this kernel's CTA shape
     const int* warp_unit0;    // (n_cta * warps + 1)
-    const int* pat_cams;
     const double2* pts2d;     // internal observation order
     const double* w;
     const double* cam_static; // (M, P) initial camera parameters
@@ -122,18 +121,25 @@ __device__ __forceinline__ void load_cameras_shared(const PatView& A, const doub
         for (int t = threadIdx.x; t < A.M * RPC_TAB_STRIDE; t += blockDim.x) s_rpc[t] = A.rpc_tab[t];
 }
 
-// lane geometry of a unit
+// k-th camera (k-th set bit) of a unit's camera set
+__device__ __forceinline__ int unit_camera(const PUnit& u, int k)
+{
+    const int nlo = __popc(u.mask_lo);
+    return k < nlo ? (int)__fns(u.mask_lo, 0, k + 1) : 32 + (int)__fns(u.mask_hi, 0, k - nlo + 1);
+}
+
+// lane geometry of a unit: lane = track slot t * L + position k
 struct LaneGeo {
     int L, T, k, t, cam;
     bool on;
 };
-__device__ __forceinline__ LaneGeo lane_geometry(const PUnit& u, const int* __restrict__ pat_cams, int lane)
+__device__ __forceinline__ LaneGeo lane_geometry(const PUnit& u, int lane)
 {
     LaneGeo g;
     g.L = u.L; g.T = min(32 / u.L, PT_MAX_T);
     g.t = lane / u.L; g.k = lane - g.t * u.L;
     g.on = g.t < g.T;
-    g.cam = g.on ? pat_cams[u.pat + g.k] : 0;
+    g.cam = g.on ? unit_camera(u, g.k) : 0;
     return g;
 }
 
@@ -147,17 +153,21 @@ __device__ __forceinline__ double slot_reduce(double v, const LaneGeo& g)
     return v;
 }
 
-// ordered critical section of a CTA: units flush in unit order
-__device__ __forceinline__ void ticket_wait(volatile int* ticket, int my)
+// Jacobian rows of one observation from the geometry alone, scaled by the row scales (weight x robust rescale) that
+// k_pt_assemble stored for this observation at the current point: the passes after the assembly need neither the
+// observed pixel nor the loss.
+template <int MODEL, int NC>
+__device__ __forceinline__ void eval_scaled(const double* __restrict__ rec, const double* __restrict__ rpc_j, double X, double Y,
+                                            double Z, double2 sc, bool cam_free, bool pt_free, ObsEval<MODEL, NC>& e)
 {
-    if ((threadIdx.x & 31) == 0) while (*ticket != my) __nanosleep(40);      // sleeping warps leave the issue slots to the others
-    __syncwarp();
-}
-__device__ __forceinline__ void ticket_release(volatile int* ticket, int my)
-{
-    __threadfence_block();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) *ticket = my + 1;
+    double u, v;
+    full_side<MODEL, NC, true>(rec, rpc_j, X, Y, Z, u, v, e.Jc, e.Jp);
+    const double a0 = cam_free ? sc.x : 0.0, a1 = cam_free ? sc.y : 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { e.Jc[k] *= a0; e.Jc[NC + k] *= a1; }
+    const double b0 = pt_free ? sc.x : 0.0, b1 = pt_free ? sc.y : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { e.Jp[k] *= b0; e.Jp[3 + k] *= b1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
 k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict__ g, const double* __restrict__ idsq,
               const double* __restrict__ idsq_c, const double* __restrict__ delta, const double* __restrict__ scal,
               int initial, int ns, int loss, double f_scale, double* __restrict__ x_new, double* __restrict__ camrec_new,
-              double* __restrict__ V_new, double* __restrict__ g_new, double* __restrict__ partials)
+              double* __restrict__ V_new, double* __restrict__ g_new, double2* __restrict__ osc_new, double* __restrict__ partials)
 {
     constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
     extern __shared__ double smem[];
@@ -216,7 +226,7 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
-        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const LaneGeo G = lane_geometry(un, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
         const double* rec = s_cam + G.cam * CAMREC_STRIDE;
         const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
@@ -244,7 +254,22 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
                 }
                 if (G.k == 0) { x_new[e3] = X; x_new[e3 + 1] = Y; x_new[e3 + 2] = Z; }
                 ObsEval<MODEL, NC> e;
-                eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+                {
+                    // residual, robust cost and row scales (kept for the later passes at this point), then the scaled rows
+                    double u, v;
+                    full_side<MODEL, NC, true>(rec, rpc_j, X, Y, Z, u, v, e.Jc, e.Jp);
+                    double f0 = wv * (u - ob.x), f1 = wv * (v - ob.y), c0, c1;
+                    const double s0 = wv * loss_rescale(loss, f_scale, f0, c0);
+                    const double s1 = wv * loss_rescale(loss, f_scale, f1, c1);
+                    osc_new[a] = make_double2(s0, s1);
+                    e.f0 = f0; e.f1 = f1; e.cost = c0 + c1;
+                    const double a0 = cam_free ? s0 : 0.0, a1 = cam_free ? s1 : 0.0;
+#pragma unroll
+                    for (int q = 0; q < NC; ++q) { e.Jc[q] *= a0; e.Jc[NC + q] *= a1; }
+                    const double b0 = pt_free ? s0 : 0.0, b1 = pt_free ? s1 : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { e.Jp[q] *= b0; e.Jp[3 + q] *= b1; }
+                }
                 cost[0] += e.cost;
                 vals[0] = e.Jp[0] * e.Jp[0] + e.Jp[3] * e.Jp[3];
                 vals[1] = e.Jp[0] * e.Jp[1] + e.Jp[3] * e.Jp[4];
@@ -442,7 +467,7 @@ template <int MODEL, int NC>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
           const double* __restrict__ g, const double* __restrict__ dsq_c, const double* __restrict__ idsq_c,
-          double* __restrict__ dsq, double* __restrict__ idsq, int first, int ns, int loss, double f_scale,
+          double* __restrict__ dsq, double* __restrict__ idsq, const double2* __restrict__ osc, int first, int ns,
           int count_cameras, int rank, double* partials, unsigned* counter, double* scal, int fold_ctl, double delta_arg)
 {
     extern __shared__ double smem[];
@@ -468,7 +493,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
-        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const LaneGeo G = lane_geometry(un, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
         const double* rec = s_cam + G.cam * CAMREC_STRIDE;
         const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
@@ -479,8 +504,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
             const int i = un.trk0 + tt;
             const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
             const size_t e3 = (size_t)ns + 3 * (size_t)i;
-            const double2 ob = A.pts2d[a];
-            const double wv = A.w[a];
+            const double2 sc = osc[a];
             const double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
             const double vd[3] = {V[6 * (size_t)i], V[6 * (size_t)i + 3], V[6 * (size_t)i + 5]};
             double t1p[3], d2[3], gp[3];
@@ -499,7 +523,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
                 gmax = fmax(gmax, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
             }
             ObsEval<MODEL, NC> e;
-            eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+            eval_scaled<MODEL, NC>(rec, rpc_j, X, Y, Z, sc, cam_free, pt_free, e);
             double y0 = e.Jp[0] * t1p[0] + e.Jp[1] * t1p[1] + e.Jp[2] * t1p[2];
             double y1 = e.Jp[3] * t1p[0] + e.Jp[4] * t1p[1] + e.Jp[5] * t1p[2];
 #pragma unroll
@@ -570,8 +594,8 @@ template <int NC> __host__ __device__ constexpr int pt_record_doubles() { return
 template <int MODEL, int NC>
 __global__ void __launch_bounds__(PT_THREADS_SCHUR, 1)
 k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
-           const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ scal, int ns, int loss,
-           double f_scale, double* __restrict__ records, double* __restrict__ partials, double* bad_points)
+           const double* __restrict__ g, const double* __restrict__ dsq, const double2* __restrict__ osc,
+           const double* __restrict__ scal, int ns, double* __restrict__ records, double* __restrict__ partials, double* bad_points)
 {
     constexpr int ZS = NC * 3, ZP = ZS + 1;
     constexpr int NA = PT_RC * NC;                       // accumulators per task
@@ -594,7 +618,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
     SchurTasks<NC> tk;
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
-        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const LaneGeo G = lane_geometry(un, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
         const double* rec = s_cam + G.cam * CAMREC_STRIDE;
         const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
@@ -616,8 +640,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                     const int i = un.trk0 + tt;
                     const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
                     const size_t e3 = (size_t)ns + 3 * (size_t)i;
-                    const double2 ob = A.pts2d[a];
-                    const double wv = A.w[a];
+                    const double2 sc = osc[a];
                     const double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
                     const double* v = V + 6 * (size_t)i;
                     double Gm[6], qv[3] = {0.0, 0.0, 0.0};
@@ -634,7 +657,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                         qv[2] = Gm[3] * g0 + Gm[4] * g1 + Gm[5] * g2;
                     }
                     ObsEval<MODEL, NC> e;
-                    eval_obs<MODEL, NC, true>(rec, rpc_j, X, Y, Z, ob.x, ob.y, wv, loss, f_scale, cam_free, pt_free, e);
+                    eval_scaled<MODEL, NC>(rec, rpc_j, X, Y, Z, sc, cam_free, pt_free, e);
                     double* z = zs + lane * ZP;
 #pragma unroll
                     for (int r = 0; r < NC; ++r) {
@@ -698,7 +721,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
         if (warp == wq) {
             for (int u = u0; u < u1; ++u) {
                 const PUnit un = A.units[u];
-                const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+                const LaneGeo G = lane_geometry(un, lane);
                 tk.unit(G.L, lane);
                 for (int pass = 0; pass < tk.npass; ++pass) {
                     tk.pass(G.L, lane, pass);
@@ -710,7 +733,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                         double val[NA];
 #pragma unroll
                         for (int m = 0; m < NA; ++m) val[m] = __ldcg(rp + (q * NA + m) * 32 + lane);
-                        const int ja = A.pat_cams[un.pat + tk.ka[q]], jb = A.pat_cams[un.pat + tk.kb[q]];
+                        const int ja = unit_camera(un, tk.ka[q]), jb = unit_camera(un, tk.kb[q]);
                         double* dst = s_S + pt_block_offset(ja, jb, A.M, NC) + tk.hh[q] * PT_RC * NC;
 #pragma unroll
                         for (int r = 0; r < PT_RC; ++r) {
@@ -778,8 +801,8 @@ template <int MODEL, int NC>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
              const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ idsq,
-             const double* __restrict__ dsq_c, const double* __restrict__ idsq_c, double* __restrict__ delta, int ns, int loss,
-             double f_scale, int count_cameras, double* partials, unsigned* counter, double* scal, int fold_ctl)
+             const double* __restrict__ dsq_c, const double* __restrict__ idsq_c, const double2* __restrict__ osc,
+             double* __restrict__ delta, int ns, int count_cameras, double* partials, unsigned* counter, double* scal, int fold_ctl)
 {
     extern __shared__ double smem[];
     double* s_cam = smem;
@@ -804,7 +827,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
-        const LaneGeo G = lane_geometry(un, A.pat_cams, lane);
+        const LaneGeo G = lane_geometry(un, lane);
         const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
         const double* rec = s_cam + G.cam * CAMREC_STRIDE;
         const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
@@ -820,9 +843,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
                 const int i = un.trk0 + tt;
                 const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
                 e3 = (size_t)ns + 3 * (size_t)i;
-                const double2 ob = A.pts2d[a];
-                eval_obs<MODEL, NC, true>(rec, rpc_j, x[e3], x[e3 + 1], x[e3 + 2], ob.x, ob.y, A.w[a], loss, f_scale, cam_free,
-                                          pt_free, e);
+                eval_scaled<MODEL, NC>(rec, rpc_j, x[e3], x[e3 + 1], x[e3 + 2], osc[a], cam_free, pt_free, e);
 #pragma unroll
                 for (int q = 0; q < NC; ++q) { yc0 += e.Jc[q] * dc[q]; yc1 += e.Jc[NC + q] * dc[q]; }
                 stg[lane] = e.Jp[0] * yc0 + e.Jp[3] * yc1;

@@ -32,10 +32,10 @@ struct PUnit {            // 32 bytes, read by every lane of the warp that owns 
     int ntrk;             // tracks in the unit
     int obs0;             // first internal observation (= internal track_ptr[trk0])
     int L;                // observations per track (1..32)
-    int pat;              // offset of the camera list in pat_cams
+    unsigned mask_lo;     // camera set of the run, bits 0..31 (position k of a track = k-th set bit) ...
+    unsigned mask_hi;     // ... and bits 32..63
     int pts_free;         // 0: the points of this run are frozen (the caller's first n_pts_fix tracks)
     int rec;              // first record of this unit in the Schur record buffer (one record per pass over the unit)
-    int pad;
 };
 
 // static work assignment for kernels launched with `warps` warps per CTA: warp w of CTA c owns the units
@@ -53,7 +53,6 @@ struct PatternLayout {
     std::vector<int> trk_new2old;      // (N) internal track -> caller's track (tracks without observations last)
     std::vector<int> obs_new2old;      // (K) internal observation -> caller's observation
     std::vector<int> track_ptr;        // (N+1) internal track offsets
-    std::vector<int> pat_cams;
     PatternAssignment wide, narrow;    // assignments for the two CTA shapes in use (more / fewer warps per CTA)
     int n_cta = 0, Lmax = 0, n_runs = 0;
     int n_frozen_tracks = 0;           // frozen tracks with observations = internal tracks [0, n_frozen_tracks)
@@ -63,7 +62,7 @@ struct PatternLayout {
 constexpr int PT_MAX_T = 16;           // track slots per tile (bounds the per-warp staging buffers)
 inline int pattern_tile_tracks(int L) { return std::min(32 / L, PT_MAX_T); }
 
-struct PatternRun { int trk0, ntrk, L, pts_free, pat; long long tile0; };
+struct PatternRun { int trk0, ntrk, L, pts_free; uint64_t mask; long long tile0; };
 
 // passes of the Schur kernel over a unit: a lane holds at most two (camera pair, row chunk) tasks at a time
 inline int pattern_schur_passes(int L, int nc, int rows_per_task)
@@ -118,7 +117,8 @@ inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std:
             PUnit u;
             const int s0 = (int)tile * T;
             u.trk0 = R.trk0 + s0; u.ntrk = (int)std::min<long long>(take * T, R.ntrk - s0); u.obs0 = track_ptr[u.trk0];
-            u.L = R.L; u.pat = R.pat; u.pts_free = R.pts_free; u.rec = A.n_records; u.pad = 0;
+            u.L = R.L; u.mask_lo = (unsigned)(R.mask & 0xffffffffu); u.mask_hi = (unsigned)(R.mask >> 32);
+            u.pts_free = R.pts_free; u.rec = A.n_records;
             A.n_records += pattern_schur_passes(R.L, nc, rows_per_task);
             A.units.push_back(u);
             tile += take;
@@ -188,9 +188,7 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
         int e = t + 1;
         while (e < N && key[order[e]] == key[o] && aux[order[e]] == aux[o]) ++e;
         const int L = track_ptr_old[o + 1] - track_ptr_old[o];
-        const int pat = (int)out.pat_cams.size();
-        for (int a = track_ptr_old[o]; a < track_ptr_old[o + 1]; ++a) out.pat_cams.push_back(cam[a]);
-        runs.push_back({t, e - t, L, (aux[o] & 1) ? 1 : 0, pat, tiles});
+        runs.push_back({t, e - t, L, (aux[o] & 1) ? 1 : 0, key[o], tiles});
         const int T = pattern_tile_tracks(L);
         tiles += (e - t + T - 1) / T;
         t = e;

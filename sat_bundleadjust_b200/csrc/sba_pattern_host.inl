@@ -11,7 +11,6 @@ static PatView pat_view(const sba_problem* p, bool narrow = false)
     PatView A;
     A.units = (const PUnit*)(narrow ? p->pt_units_narrow : p->pt_units);
     A.warp_unit0 = narrow ? p->pt_warp_unit0_narrow : p->pt_warp_unit0;
-    A.pat_cams = p->pt_pat_cams;
     A.pts2d = (const double2*)p->pts2d; A.w = p->w; A.cam_static = p->cam_static; A.rpc_tab = p->rpc_tab;
     A.M = p->M; A.P = p->P; A.n_cam_fix = p->n_cam_fix; A.n_cta = p->pt_n_cta;
     return A;
@@ -25,8 +24,8 @@ static size_t pt_smem_common(const sba_problem* p)
 }
 static size_t pt_smem_assemble(const sba_problem* p)
 {
-    const int nv = p->nc * (p->nc + 1) / 2 + p->nc;
-    return (pt_smem_common(p) + (size_t)(PT_THREADS / 32) * p->M * nv + (PT_THREADS / 32) * 9 * 33 + PT_RED_DOUBLES) * sizeof(double);
+    const int nv = p->nc * (p->nc + 1) / 2 + p->nc, nw = PT_THREADS / 32;
+    return (pt_smem_common(p) + (size_t)nw * p->M * nv + nw * 9 * 33 + PT_RED_DOUBLES) * sizeof(double);
 }
 static size_t pt_smem_jvp1(const sba_problem* p)
 {
@@ -70,7 +69,7 @@ static bool pattern_engine_applicable(const sba_problem* p)
 {
     if (const char* e = getenv("SBA_ENGINE")) if (std::strcmp(e, "generic") == 0) return false;
     if (p->n_common != 0 || p->nc > 6 || p->M * p->nc > PT_MAX_NS || p->M > 64) return false;
-    return pt_smem_schur(p) <= (size_t)220 * 1024 && pt_smem_assemble(p) <= (size_t)220 * 1024;
+    return pt_smem_schur(p) <= (size_t)220 * 1024 && pt_smem_assemble(p) <= (size_t)220 * 1024 && pt_smem_backsub(p) <= (size_t)220 * 1024;
 }
 
 // ---- boundary: caller's order <-> internal order ------------------------------------------------------------------
@@ -100,7 +99,7 @@ static int pt_run_assemble(sba_problem* p, int initial, int first, int loss, dou
 #define L(MODEL, NC)                                                                                                          \
     k_pt_assemble<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_assemble(p), p->stream>>>(                                     \
         pat_view(p), p->x, p->g, p->idsq, p->idsqc, p->delta, p->scal, initial, ns, loss, f_scale, p->x_new, p->camrec_new,    \
-        p->V2, p->g2, p->pt_partials);                                                                                         \
+        p->V2, p->g2, (double2*)p->osc2, p->pt_partials);                                                                      \
     SBA_TRY(check_launch(p));                                                                                                  \
     k_pt_reduce_assemble<NC><<<(p->M * (NC * (NC + 1) / 2 + NC) + 1 + 7) / 8, 256, 0, p->stream>>>(                          \
         p->pt_partials, p->pt_n_cta, p->M, p->camsys2, p->world == 1, p->dsqc, first, p->dsqc2, p->idsqc2, p->g2, p->scal,     \
@@ -121,7 +120,7 @@ static void pt_accept(sba_problem* p)
 {
     std::swap(p->x, p->x_new); std::swap(p->camrec, p->camrec_new);
     std::swap(p->V, p->V2); std::swap(p->g, p->g2); std::swap(p->camsys, p->camsys2);
-    std::swap(p->dsqc, p->dsqc2); std::swap(p->idsqc, p->idsqc2);
+    std::swap(p->dsqc, p->dsqc2); std::swap(p->idsqc, p->idsqc2); std::swap(p->osc, p->osc2);
 }
 
 static int pt_run_jvp1(sba_problem* p, int first, int loss, double f_scale, double delta_arg)
@@ -131,7 +130,7 @@ static int pt_run_jvp1(sba_problem* p, int first, int loss, double f_scale, doub
     const int fold = p->world == 1;
 #define L(MODEL, NC)                                                                                                       \
     k_pt_jvp1<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_jvp1(p), p->stream>>>(                                          \
-        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsqc, p->idsqc, p->dsq, p->idsq, first, ns, loss, f_scale,             \
+        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsqc, p->idsqc, p->dsq, p->idsq, (const double2*)p->osc, first, ns,   \
         p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal, fold, delta_arg)
     PT_DISPATCH(p, L);
 #undef L
@@ -151,7 +150,7 @@ static int pt_run_schur(sba_problem* p, int loss, double f_scale)
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
 #define L(MODEL, NC)                                                                                                        \
     k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                                   \
-        pat_view(p, true), p->x, p->camrec, p->V, p->g, p->dsq, p->scal, ns, loss, f_scale, p->pt_records, p->pt_partials,    \
+        pat_view(p, true), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
         p->scal + SC_BAD_POINTS);                                                                                            \
     SBA_TRY(check_launch(p));                                                                                                \
     k_pt_reduce_schur<NC><<<(nS + ns + 7) / 8, 256, 0, p->stream>>>(p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, \
@@ -169,7 +168,7 @@ static int pt_run_backsub(sba_problem* p, int loss, double f_scale)
     const int fold = p->world == 1;
 #define L(MODEL, NC)                                                                                                      \
     k_pt_backsub<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_backsub(p), p->stream>>>(                                   \
-        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, p->delta, ns, loss, f_scale,        \
+        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
         p->rank == 0, p->red_partials, p->counters + 3, p->scal, fold)
     PT_DISPATCH(p, L);
 #undef L
@@ -356,7 +355,6 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_upload(p, &p->track_ptr, lay.track_ptr, s));
     SBA_TRY(dev_upload(p, &p->trk_new2old, lay.trk_new2old, s));
     SBA_TRY(dev_upload(p, &p->obs_new2old, lay.obs_new2old, s));
-    SBA_TRY(dev_upload(p, &p->pt_pat_cams, lay.pat_cams, s));
     SBA_TRY(dev_upload(p, &p->pt_warp_unit0, lay.wide.warp_unit0, s));
     SBA_TRY(dev_upload(p, &p->pt_warp_unit0_narrow, lay.narrow.warp_unit0, s));
     for (int k = 0; k < 2; ++k) {
@@ -370,6 +368,7 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     p->n_tiles = 0;
     SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
+    SBA_TRY(dev_alloc(p, &p->osc, 2 * (size_t)K)); SBA_TRY(dev_alloc(p, &p->osc2, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->r_int, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->e_int, (size_t)K));
     // observations and weights: uploaded in the caller's order, gathered into the internal order on the device

@@ -92,13 +92,13 @@ int hh_host_index(const long long* cam_ind, const long long* pts_ind, long long 
 
 
 // pattern-major layout (csrc/sba_pattern.h): sizes first (NULL outputs), then the arrays.
-// sizes = [ok, n_units, n_pat_cams, n_frozen_tracks, n_tiles, n_runs]; units (of the `warps`-wide assignment) as 8 ints each
+// sizes = [ok, n_units, 0, n_frozen_tracks, n_tiles, n_runs]; units (of the `warps`-wide assignment) as 8 ints each
 int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, int N, int n_pts_fix, int n_cta, int warps,
-                      int* sizes, int* trk_new2old, int* obs_new2old, int* track_ptr_new, int* units, int* pat_cams, int* warp_unit0)
+                      int* sizes, int* trk_new2old, int* obs_new2old, int* track_ptr_new, int* units, int* warp_unit0)
 {
     PatternLayout L;
     build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, warps, std::max(1, warps - 4), 6, 3, L);
-    sizes[0] = L.ok ? 1 : 0; sizes[1] = (int)L.wide.units.size(); sizes[2] = (int)L.pat_cams.size(); sizes[3] = L.n_frozen_tracks;
+    sizes[0] = L.ok ? 1 : 0; sizes[1] = (int)L.wide.units.size(); sizes[2] = 0; sizes[3] = L.n_frozen_tracks;
     sizes[4] = (int)L.n_tiles; sizes[5] = L.n_runs;
     if (!L.ok || !trk_new2old) return 0;
     std::copy(L.trk_new2old.begin(), L.trk_new2old.end(), trk_new2old);
@@ -106,7 +106,6 @@ int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, 
     std::copy(L.track_ptr.begin(), L.track_ptr.end(), track_ptr_new);
     static_assert(sizeof(PUnit) == 8 * sizeof(int), "PUnit layout");
     std::copy((const int*)L.wide.units.data(), (const int*)L.wide.units.data() + 8 * L.wide.units.size(), units);
-    std::copy(L.pat_cams.begin(), L.pat_cams.end(), pat_cams);
     std::copy(L.wide.warp_unit0.begin(), L.wide.warp_unit0.end(), warp_unit0);
     return 0;
 }

@@ -395,13 +395,12 @@ def _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=0, n_cta=148, warps=16):
     sizes = (ctypes.c_int * 6)()
     null = ctypes.cast(None, ip)
     args = [cam.ctypes.data_as(ip), tp.ctypes.data_as(ip), ctypes.c_longlong(K), M, N, n_pts_fix, n_cta, warps, sizes]
-    lib.hh_pattern_layout(*args, *([null] * 6))
+    lib.hh_pattern_layout(*args, *([null] * 5))
     if not sizes[0]:
         return None
     out = {"trk_new2old": np.zeros(N, np.int32), "obs_new2old": np.zeros(K, np.int32), "track_ptr": np.zeros(N + 1, np.int32),
-           "units": np.zeros((sizes[1], 8), np.int32), "pat_cams": np.zeros(sizes[2], np.int32),
-           "warp_unit0": np.zeros(n_cta * warps + 1, np.int32)}
-    lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "pat_cams", "warp_unit0")])
+           "units": np.zeros((sizes[1], 8), np.int32), "warp_unit0": np.zeros(n_cta * warps + 1, np.int32)}
+    lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "warp_unit0")])
     out["n_frozen"], out["n_tiles"], out["n_runs"] = sizes[3], sizes[4], sizes[5]
     return out
 
@@ -435,12 +434,13 @@ def test_pattern_layout(built, M, N, p_vis, fix):
     covered = np.zeros(N, bool)
     units = lay["units"]
     tiles = []
-    for trk0, ntrk, obs0, L, pat, free, rank, _ in units.tolist():
+    for trk0, ntrk, obs0, L, mlo, mhi, free, rec in units.tolist():
         assert 1 <= L <= 32 and ntrk >= 1 and obs0 == tp[trk0]
         assert not covered[trk0: trk0 + ntrk].any()
         covered[trk0: trk0 + ntrk] = True
-        cams = lay["pat_cams"][pat: pat + L]
-        assert np.all(np.diff(cams) > 0)
+        mask = (mlo & 0xffffffff) | ((mhi & 0xffffffff) << 32)
+        cams = np.array([j for j in range(64) if (mask >> j) & 1])
+        assert cams.size == L
         obs = cam_ind[o2o[obs0: obs0 + ntrk * L]].reshape(ntrk, L)
         assert np.all(obs == cams[None, :])
         assert np.all((t2o[trk0: trk0 + ntrk] >= fix) == bool(free))
@@ -456,7 +456,7 @@ def test_pattern_layout(built, M, N, p_vis, fix):
     if tiles.sum() >= 4 * n_cta * warps:
         assert per_warp.max() - per_warp.min() <= 2                  # equal tile counts per warp (uniform cost model)
     passes = (units[:, 3] * (units[:, 3] + 1) // 2 * 2 + 63) // 64      # Schur records: one per pass over a unit (n_params 6: 2 row chunks)
-    assert np.array_equal(units[:, 6], np.concatenate([[0], np.cumsum(passes)[:-1]]))
+    assert np.array_equal(units[:, 7], np.concatenate([[0], np.cumsum(passes)[:-1]]))
 
 
 def test_pattern_layout_rejects(built):
