@@ -717,7 +717,8 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     stamp("host index pass");
     if (pattern_engine_applicable(p)) {
         PatternLayout lay;
-        build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, PT_RC, lay);
+        build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, PT_RC,
+                             lay);
         stamp("pattern layout");
         if (lay.ok) {
             const int rc = pattern_create(p, d, hidx, lay);

@@ -26,7 +26,7 @@ __device__ __forceinline__ int warp_chol32(double (&a)[CB], int lane, double& in
     for (int c = 0; c < CB; ++c) {
         const double d = __shfl_sync(0xffffffffu, a[c], c);
         if (!(d > 0.0) || !isfinite(d)) return c + 1;
-        const double ip = rsqrt(d);
+        const double ip = fast_rsqrt(d);
         const double l = a[c] * ip;
         a[c] = l;
         if (lane == c) inv = ip;

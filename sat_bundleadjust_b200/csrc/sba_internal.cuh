@@ -156,8 +156,8 @@ struct sba_problem {
     int n_pts_fix_int = 0;                               // frozen tracks in the internal order: tracks [0, n_pts_fix_int)
     std::vector<int> h_trk_new2old, h_obs_new2old;       // host copies (test-only entry points un-permute on the host)
     int *trk_new2old = nullptr, *obs_new2old = nullptr;  // device
-    void *pt_units = nullptr, *pt_units_narrow = nullptr;           // device PUnit[]: assignments for the two CTA shapes
-    int *pt_warp_unit0 = nullptr, *pt_warp_unit0_narrow = nullptr;
+    void* pt_units[3] = {nullptr, nullptr, nullptr};                // device PUnit[]: assignments for the three CTA shapes
+    int* pt_warp_unit0[3] = {nullptr, nullptr, nullptr};
     int pt_n_cta = 0;
     double *V2 = nullptr, *g2 = nullptr, *camsys2 = nullptr;        // second buffer set (trial point)
     double *dsq = nullptr, *idsq = nullptr;                         // (n) squared column scales of the points and their reciprocals

@@ -19,7 +19,8 @@
 namespace sba {
 
 constexpr int PT_CTAS = NUM_SMS;          // one persistent CTA per SM
-constexpr int PT_THREADS = 512;           // assemble / jvp1 / backsub (<= 128 registers)
+constexpr int PT_THREADS = 512;           // assemble (<= 128 registers)
+constexpr int PT_THREADS_LIGHT = 512;     // jvp1 / backsub
 constexpr int PT_THREADS_SCHUR = 384;     // schur (<= 168 registers)
 constexpr int PT_MAX_NS = 132;            // reduced camera system that still fits the shared-memory copy of S
 constexpr int PT_RC = 3;                  // rows of a camera block per Schur task
@@ -32,6 +33,7 @@ struct PatView {
     const double* cam_static; // (M, P) initial camera parameters
     const double* rpc_tab;
     int M, P, n_cam_fix, n_cta;
+    int debug_skip;           // measurement only (SBA_PT_SKIP=1): the warps walk no units, leaving the fixed cost of a pass
 };
 
 __device__ __forceinline__ double step_value2(double x, double t, double d, double pa, double pb)
@@ -153,6 +155,11 @@ __device__ __forceinline__ double slot_reduce(double v, const LaneGeo& g)
     return v;
 }
 
+// The inputs of the NEXT tile of a unit are requested into L1 while the current tile is computed: a warp has only a
+// dozen tiles to walk, so an exposed HBM round trip per tile would dominate the kernel.  Addresses are arithmetic (no
+// index arrays), one prefetch per lane and array; lanes of a track share cache lines.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Jacobian rows of one observation from the geometry alone, scaled by the row scales (weight x robust rescale) that
 // k_pt_assemble stored for this observation at the current point: the passes after the assembly need neither the
 // observed pixel nor the loss.
@@ -223,7 +230,7 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
     double cost[1] = {0.0};
     double* stg = s_stage + warp * 9 * 33;           // stride 33: the (track, value) lanes below read conflict-free
     double* my_acc = s_acc + warp * A.M * NV;            // camera blocks of this warp's units: private, no ordering needed
-    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -237,6 +244,11 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
             const int tt = tb + G.t;
             const bool on = G.on && tt < un.ntrk;
             const int nact = min(G.T, un.ntrk - tb);
+            if (G.on && tt + G.T < un.ntrk) {          // next tile
+                const size_t an = (size_t)un.obs0 + (size_t)(tt + G.T) * G.L + G.k, en = (size_t)ns + 3 * (size_t)(un.trk0 + tt + G.T);
+                prefetch_l1(A.pts2d + an); prefetch_l1(A.w + an); prefetch_l1(x + en);
+                if (!initial) { prefetch_l1(g + en); prefetch_l1(idsq + en); prefetch_l1(delta + en); }
+            }
             double vals[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) vals[q] = 0.0;
@@ -464,7 +476,7 @@ __global__ void k_pt_control_tr2d(double* scal, double delta_arg)
 // shared: s_cam | s_rpc | s_t1c[ns] | s_red
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int NC>
-__global__ void __launch_bounds__(PT_THREADS, 1)
+__global__ void __launch_bounds__(PT_THREADS_LIGHT, 1)
 k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
           const double* __restrict__ g, const double* __restrict__ dsq_c, const double* __restrict__ idsq_c,
           double* __restrict__ dsq, double* __restrict__ idsq, const double2* __restrict__ osc, int first, int ns,
@@ -490,7 +502,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
             gmax = fmax(gmax, fabs(gv));
         }
     }
-    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -501,6 +513,11 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
         for (int tb = 0; tb < un.ntrk; tb += G.T) {
             const int tt = tb + G.t;
             if (!(G.on && tt < un.ntrk)) continue;
+            if (tt + G.T < un.ntrk) {          // next tile
+                const size_t in = (size_t)(un.trk0 + tt + G.T), en = (size_t)ns + 3 * in;
+                prefetch_l1(osc + (size_t)un.obs0 + (size_t)(tt + G.T) * G.L + G.k);
+                prefetch_l1(x + en); prefetch_l1(g + en); prefetch_l1(dsq + en); prefetch_l1(V + 6 * in);
+            }
             const int i = un.trk0 + tt;
             const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
             const size_t e3 = (size_t)ns + 3 * (size_t)i;
@@ -546,8 +563,8 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
 
 // ------------------------------------------------------------------------------------------------
 // K3: point elimination + Schur complement in shared memory
-// shared: s_cam | s_rpc | s_S[NC*NC*M(M+1)/2] | s_rhs[ns] | s_Z[nwarps][32 * ZP]
-// S is stored by upper block rows: block (j, j' >= j) at NC*NC * (j M - j (j-1)/2 + j' - j), row-major NC x NC.
+// shared: s_cam | s_rpc | s_Z[nwarps][32 * ZP]
+// The CTA's partial of S is stored by upper block rows: block (j, j' >= j) at NC*NC * (j M - j (j-1)/2 + j' - j), row-major NC x NC.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline int pt_block_offset(int j, int jp, int M, int NC)
 {
@@ -585,7 +602,7 @@ struct SchurTasks {
     }
 };
 
-// One record per (unit, pass): the lane-private sums of a pass, [2 tasks][NA values][32 lanes] then [NC rhs values][32 lanes]
+// One record per (unit, pass): the lane-private sums of a pass, [2 tasks][32 lanes][NA values] then [NC rhs values][32 lanes]
 // (rows a pass does not use are neither written nor read).  Records are written when a warp leaves a unit and merged into
 // the CTA's shared-memory S after all warps are done, warp by warp in unit order: fixed summation order without any
 // waiting inside the main loop.
@@ -604,17 +621,14 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
     const int nS = NC * NC * (A.M * (A.M + 1) / 2);
     double* s_cam = smem;
     double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
-    double* s_S = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
-    double* s_rhs = s_S + nS;
-    double* s_Z = s_rhs + ns;
+    double* s_Z = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double reg = scal[SC_REG];
     load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
-    for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) s_S[t] = 0.0;
     __syncthreads();
     double* zs = s_Z + (size_t)warp * (32 * ZP + PT_RC * 3);          // tail padding: the last chunk may read past row NC-1
     int nbad = 0;
-    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     SchurTasks<NC> tk;
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
@@ -636,6 +650,11 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                 const int tt = tb + G.t;
                 const bool on = G.on && tt < un.ntrk;
                 const int nact = min(G.T, un.ntrk - tb);
+                if (G.on && tt + G.T < un.ntrk) {          // next tile
+                    const size_t in = (size_t)(un.trk0 + tt + G.T), en = (size_t)ns + 3 * in;
+                    prefetch_l1(osc + (size_t)un.obs0 + (size_t)(tt + G.T) * G.L + G.k);
+                    prefetch_l1(x + en); prefetch_l1(g + en); prefetch_l1(dsq + en); prefetch_l1(V + 6 * in);
+                }
                 if (on) {
                     const int i = un.trk0 + tt;
                     const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
@@ -699,13 +718,17 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                     }
                 }
             }
-            // the record of this (unit, pass)
+            // the record of this (unit, pass): task-major ([q][lane][NA], transposed through the warp's Z area so that the
+            // stores are coalesced and the merge below reads the NA values of a task as one contiguous span), then the rhs rows
             double* rp = records + (size_t)(un.rec + pass) * REC;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 if (pass * 64 + q * 32 >= tk.ntask) continue;        // warp-uniform: no lane has this task
 #pragma unroll
-                for (int m = 0; m < NA; ++m) rp[(q * NA + m) * 32 + lane] = acc[q][m];
+                for (int m = 0; m < NA; ++m) zs[lane * NA + m] = acc[q][m];
+                __syncwarp();
+                for (int e = lane; e < 32 * NA; e += 32) rp[q * 32 * NA + e] = zs[e];
+                __syncwarp();
             }
             if (pass == 0) {
 #pragma unroll
@@ -714,45 +737,83 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
         }
     }
     if (nbad) atomicAdd(bad_points, (double)nbad);
-    __threadfence_block();
+    __threadfence();
     __syncthreads();
-    // merge: warp by warp, units and passes in order
-    for (int wq = 0; wq < nw; ++wq) {
-        if (warp == wq) {
-            for (int u = u0; u < u1; ++u) {
-                const PUnit un = A.units[u];
-                const LaneGeo G = lane_geometry(un, lane);
-                tk.unit(G.L, lane);
-                for (int pass = 0; pass < tk.npass; ++pass) {
-                    tk.pass(G.L, lane, pass);
-                    const double* rp = records + (size_t)(un.rec + pass) * REC;
-                    if (tk.npar > 1) tk.tv[0] = tk.tv[0] && tk.par == 0;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (!tk.tv[q]) continue;
-                        double val[NA];
-#pragma unroll
-                        for (int m = 0; m < NA; ++m) val[m] = __ldcg(rp + (q * NA + m) * 32 + lane);
-                        const int ja = unit_camera(un, tk.ka[q]), jb = unit_camera(un, tk.kb[q]);
-                        double* dst = s_S + pt_block_offset(ja, jb, A.M, NC) + tk.hh[q] * PT_RC * NC;
-#pragma unroll
-                        for (int r = 0; r < PT_RC; ++r) {
-                            if (tk.hh[q] * PT_RC + r >= NC) break;
-#pragma unroll
-                            for (int s = 0; s < NC; ++s) dst[r * NC + s] += val[r * NC + s];
-                        }
-                    }
-                    if (pass == 0 && G.on && G.t == 0) {
-#pragma unroll
-                        for (int r = 0; r < NC; ++r) s_rhs[G.cam * NC + r] += __ldcg(rp + (2 * NA + r) * 32 + lane);
-                    }
-                    __syncwarp();
+    // Merge: every entry of the CTA's partial S (and rhs) is owned by one thread, which adds up the contributions of the
+    // CTA's units in unit order -- parallel over the entries, fixed summation order, no read-modify-write conflicts.  Where a
+    // unit's record holds the entry follows from its camera set: positions ka, kb of the two cameras -> pair -> task -> lane.
+    // The unit descriptors go through shared memory (the Z areas are free now) and the record loads are issued eight units at
+    // a time (units that do not contain the entry read a zero), so the L2 round trips overlap.
+    {
+        constexpr int NCH = SchurTasks<NC>::NCH;
+        constexpr int MU = 4;
+        const int cu0 = A.warp_unit0[blockIdx.x * nw], cu1 = A.warp_unit0[(blockIdx.x + 1) * nw];
+        const int ncu = cu1 - cu0;
+        // per unit: mask (2 ints), L, rec -> 4 ints; capacity of the Z area
+        int* s_units = reinterpret_cast<int*>(s_Z);
+        const int cap = (int)(((size_t)nw * (32 * ZP + PT_RC * 3) * sizeof(double)) / (4 * sizeof(int))) - 1;
+        for (int c0 = 0; c0 < max(ncu, 1); c0 += cap) {        // a CTA without units still writes its (zero) partial
+            const int nc_here = min(cap, ncu - c0);
+            __syncthreads();
+            for (int q = threadIdx.x; q < nc_here; q += blockDim.x) {
+                const PUnit un = A.units[cu0 + c0 + q];
+                s_units[4 * q] = (int)un.mask_lo; s_units[4 * q + 1] = (int)un.mask_hi; s_units[4 * q + 2] = un.L; s_units[4 * q + 3] = un.rec;
+            }
+            if (threadIdx.x == 0) { s_units[4 * nc_here] = 0; }
+            __syncthreads();
+            // one thread per (camera block, row) -- the NC entries of a row are contiguous in a task's record -- and one per
+            // camera for the rhs; MU units at a time: NC * MU independent loads in flight
+            const int nrow = (A.M * (A.M + 1) / 2) * NC;
+            for (int task = threadIdx.x; task < nrow + A.M; task += blockDim.x) {
+                double sum[NC];
+                const bool is_S = task < nrow;
+                int ja = 0, jb = 0, h = 0, mrow = 0;
+                size_t t0;       // first entry of this thread in the partial vector
+                if (is_S) {
+                    int bq = task / NC;
+                    const int r = task - bq * NC;
+                    t0 = (size_t)bq * NC * NC + (size_t)r * NC;
+                    while (bq >= A.M - ja) { bq -= A.M - ja; ++ja; }
+                    jb = ja + bq;
+                    h = r / PT_RC; mrow = (r - h * PT_RC) * NC;
+                } else {
+                    ja = jb = task - nrow;
+                    t0 = (size_t)nS + (size_t)ja * NC;
                 }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) sum[c] = c0 == 0 ? 0.0 : partials[(t0 + c) * A.n_cta + blockIdx.x];
+                for (int q0 = 0; q0 < nc_here; q0 += MU) {
+                    double val[MU][NC];
+#pragma unroll
+                    for (int qq = 0; qq < MU; ++qq) {
+                        const int q = min(q0 + qq, nc_here - 1);
+                        const unsigned long long mask = ((unsigned long long)(unsigned)s_units[4 * q + 1] << 32) | (unsigned)s_units[4 * q];
+                        const int L = s_units[4 * q + 2], rec0 = s_units[4 * q + 3];
+                        const bool has = q0 + qq < nc_here && ((mask >> ja) & 1ull) && ((mask >> jb) & 1ull);
+                        const int ka = __popcll(mask & ((1ull << ja) - 1ull)), kb = __popcll(mask & ((1ull << jb) - 1ull));
+                        const double* src;
+                        int stride;
+                        if (is_S) {
+                            const int tau = (ka * L - ka * (ka - 1) / 2 + (kb - ka)) * NCH + h;
+                            src = records + (size_t)(rec0 + (tau >> 6)) * REC + (((tau >> 5) & 1) * 32 + (tau & 31)) * NA + mrow;
+                            stride = 1;
+                        } else {
+                            src = records + (size_t)rec0 * REC + (2 * NA) * 32 + ka;
+                            stride = 32;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) val[qq][c] = has ? __ldcg(src + c * stride) : 0.0;
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < MU; ++qq)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) sum[c] += val[qq][c];
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) partials[(t0 + c) * A.n_cta + blockIdx.x] = sum[c];
             }
         }
-        __syncthreads();
     }
-    for (int t = threadIdx.x; t < nS + ns; t += blockDim.x) partials[(size_t)t * A.n_cta + blockIdx.x] = s_S[t];
 }
 
 // Sum of the per-CTA Schur partials -> reduced camera system S (ns x ns column-major, symmetric, both triangles) and its
@@ -798,7 +859,7 @@ k_pt_reduce_schur(const double* __restrict__ partials, int n_cta, int M, int n_c
 // shared: s_cam | s_rpc | s_dc[ns] | s_t1c[ns] | s_stage[nwarps][3][32] | s_red
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int NC>
-__global__ void __launch_bounds__(PT_THREADS, 1)
+__global__ void __launch_bounds__(PT_THREADS_LIGHT, 1)
 k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
              const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ idsq,
              const double* __restrict__ dsq_c, const double* __restrict__ idsq_c, const double2* __restrict__ osc,
@@ -824,7 +885,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
         }
     }
     double* stg = s_stage + warp * 3 * 32;
-    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -836,6 +897,11 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
         for (int tb = 0; tb < un.ntrk; tb += G.T) {
             const int tt = tb + G.t;
             const bool on = G.on && tt < un.ntrk;
+            if (G.on && tt + G.T < un.ntrk) {          // next tile
+                const size_t in = (size_t)(un.trk0 + tt + G.T), en = (size_t)ns + 3 * in;
+                prefetch_l1(osc + (size_t)un.obs0 + (size_t)(tt + G.T) * G.L + G.k);
+                prefetch_l1(x + en); prefetch_l1(g + en); prefetch_l1(dsq + en); prefetch_l1(idsq + en); prefetch_l1(V + 6 * in);
+            }
             ObsEval<MODEL, NC> e;
             double yc0 = 0.0, yc1 = 0.0;
             size_t e3 = 0;

@@ -53,7 +53,7 @@ struct PatternLayout {
     std::vector<int> trk_new2old;      // (N) internal track -> caller's track (tracks without observations last)
     std::vector<int> obs_new2old;      // (K) internal observation -> caller's observation
     std::vector<int> track_ptr;        // (N+1) internal track offsets
-    PatternAssignment wide, narrow;    // assignments for the two CTA shapes in use (more / fewer warps per CTA)
+    PatternAssignment light, wide, narrow;   // assignments for the CTA shapes in use (24 / 16 / 12 warps per CTA)
     int n_cta = 0, Lmax = 0, n_runs = 0;
     int n_frozen_tracks = 0;           // frozen tracks with observations = internal tracks [0, n_frozen_tracks)
     long long n_tiles = 0;
@@ -131,7 +131,8 @@ inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std:
 // cam: (K) camera of every observation, caller's order; track_ptr_old: (N+1) first observation of every track.
 // n_pts_fix: the caller's first n_pts_fix tracks are frozen.
 inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long long K, int M, int N, int n_pts_fix,
-                                 int n_cta, int warps_wide, int warps_narrow, int nc, int rows_per_task, PatternLayout& out)
+                                 int n_cta, int warps_light, int warps_wide, int warps_narrow, int nc, int rows_per_task,
+                                 PatternLayout& out)
 {
     out = PatternLayout();
     if (M > 64) { out.why = "more than 64 cameras"; return; }
@@ -197,6 +198,7 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     out.n_tiles = tiles;
     out.n_cta = n_cta;
     if (runs.empty()) { out.why = "no observations"; return; }
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_light, nc, rows_per_task, false, out.light);
     assign_pattern_units(runs, out.track_ptr, n_cta, warps_wide, nc, rows_per_task, false, out.wide);
     assign_pattern_units(runs, out.track_ptr, n_cta, warps_narrow, nc, rows_per_task, true, out.narrow);
     out.ok = true;

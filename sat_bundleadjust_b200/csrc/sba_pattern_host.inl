@@ -6,13 +6,16 @@
 //     K1 trial point: cost AND the blocks of the next iteration (an accepted step costs nothing more)
 // i.e. 6 launches and 4 Jacobian evaluations per observation and iteration, nothing per-observation stored in HBM.
 
-static PatView pat_view(const sba_problem* p, bool narrow = false)
+// shape: 0 = light (jvp1, backsub), 1 = wide (assemble), 2 = narrow (schur)
+static PatView pat_view(const sba_problem* p, int shape)
 {
     PatView A;
-    A.units = (const PUnit*)(narrow ? p->pt_units_narrow : p->pt_units);
-    A.warp_unit0 = narrow ? p->pt_warp_unit0_narrow : p->pt_warp_unit0;
+    A.units = (const PUnit*)p->pt_units[shape];
+    A.warp_unit0 = p->pt_warp_unit0[shape];
     A.pts2d = (const double2*)p->pts2d; A.w = p->w; A.cam_static = p->cam_static; A.rpc_tab = p->rpc_tab;
     A.M = p->M; A.P = p->P; A.n_cam_fix = p->n_cam_fix; A.n_cta = p->pt_n_cta;
+    static const bool skip = getenv("SBA_PT_SKIP") != nullptr;
+    A.debug_skip = skip ? 1 : 0;
     return A;
 }
 
@@ -33,12 +36,11 @@ static size_t pt_smem_jvp1(const sba_problem* p)
 }
 static size_t pt_smem_schur(const sba_problem* p)
 {
-    const int ns = p->M * p->nc, nS = p->nc * p->nc * (p->M * (p->M + 1) / 2);
-    return (pt_smem_common(p) + (size_t)nS + ns + (size_t)(PT_THREADS_SCHUR / 32) * (32 * (p->nc * 3 + 1) + PT_RC * 3)) * sizeof(double);
+    return (pt_smem_common(p) + (size_t)(PT_THREADS_SCHUR / 32) * (32 * (p->nc * 3 + 1) + PT_RC * 3)) * sizeof(double);
 }
 static size_t pt_smem_backsub(const sba_problem* p)
 {
-    return (pt_smem_common(p) + 2 * (size_t)p->M * p->nc + (PT_THREADS / 32) * 3 * 32 + PT_RED_DOUBLES) * sizeof(double);
+    return (pt_smem_common(p) + 2 * (size_t)p->M * p->nc + (PT_THREADS_LIGHT / 32) * 3 * 32 + PT_RED_DOUBLES) * sizeof(double);
 }
 
 #define PT_DISPATCH(p, MACRO)                                                           \
@@ -98,7 +100,7 @@ static int pt_run_assemble(sba_problem* p, int initial, int first, int loss, dou
     const size_t cs_count = (size_t)ns * p->nc + ns + 1;
 #define L(MODEL, NC)                                                                                                          \
     k_pt_assemble<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_assemble(p), p->stream>>>(                                     \
-        pat_view(p), p->x, p->g, p->idsq, p->idsqc, p->delta, p->scal, initial, ns, loss, f_scale, p->x_new, p->camrec_new,    \
+        pat_view(p, 1), p->x, p->g, p->idsq, p->idsqc, p->delta, p->scal, initial, ns, loss, f_scale, p->x_new, p->camrec_new,    \
         p->V2, p->g2, (double2*)p->osc2, p->pt_partials);                                                                      \
     SBA_TRY(check_launch(p));                                                                                                  \
     k_pt_reduce_assemble<NC><<<(p->M * (NC * (NC + 1) / 2 + NC) + 1 + 7) / 8, 256, 0, p->stream>>>(                          \
@@ -129,8 +131,8 @@ static int pt_run_jvp1(sba_problem* p, int first, int loss, double f_scale, doub
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_GMAX_SLOTS, 0, 16 * sizeof(double), p->stream));
     const int fold = p->world == 1;
 #define L(MODEL, NC)                                                                                                       \
-    k_pt_jvp1<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_jvp1(p), p->stream>>>(                                          \
-        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsqc, p->idsqc, p->dsq, p->idsq, (const double2*)p->osc, first, ns,   \
+    k_pt_jvp1<MODEL, NC><<<p->pt_n_cta, PT_THREADS_LIGHT, pt_smem_jvp1(p), p->stream>>>(                                    \
+        pat_view(p, 0), p->x, p->camrec, p->V, p->g, p->dsqc, p->idsqc, p->dsq, p->idsq, (const double2*)p->osc, first, ns,   \
         p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal, fold, delta_arg)
     PT_DISPATCH(p, L);
 #undef L
@@ -150,7 +152,7 @@ static int pt_run_schur(sba_problem* p, int loss, double f_scale)
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
 #define L(MODEL, NC)                                                                                                        \
     k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                                   \
-        pat_view(p, true), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
+        pat_view(p, 2), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
         p->scal + SC_BAD_POINTS);                                                                                            \
     SBA_TRY(check_launch(p));                                                                                                \
     k_pt_reduce_schur<NC><<<(nS + ns + 7) / 8, 256, 0, p->stream>>>(p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, \
@@ -167,8 +169,8 @@ static int pt_run_backsub(sba_problem* p, int loss, double f_scale)
     const int ns = p->M * p->nc;
     const int fold = p->world == 1;
 #define L(MODEL, NC)                                                                                                      \
-    k_pt_backsub<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_backsub(p), p->stream>>>(                                   \
-        pat_view(p), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
+    k_pt_backsub<MODEL, NC><<<p->pt_n_cta, PT_THREADS_LIGHT, pt_smem_backsub(p), p->stream>>>(                             \
+        pat_view(p, 0), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
         p->rank == 0, p->red_partials, p->counters + 3, p->scal, fold)
     PT_DISPATCH(p, L);
 #undef L
@@ -355,14 +357,13 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_upload(p, &p->track_ptr, lay.track_ptr, s));
     SBA_TRY(dev_upload(p, &p->trk_new2old, lay.trk_new2old, s));
     SBA_TRY(dev_upload(p, &p->obs_new2old, lay.obs_new2old, s));
-    SBA_TRY(dev_upload(p, &p->pt_warp_unit0, lay.wide.warp_unit0, s));
-    SBA_TRY(dev_upload(p, &p->pt_warp_unit0_narrow, lay.narrow.warp_unit0, s));
-    for (int k = 0; k < 2; ++k) {
-        const std::vector<PUnit>& hu = k ? lay.narrow.units : lay.wide.units;
+    for (int k = 0; k < 3; ++k) {
+        const PatternAssignment& as = k == 0 ? lay.light : (k == 1 ? lay.wide : lay.narrow);
+        SBA_TRY(dev_upload(p, &p->pt_warp_unit0[k], as.warp_unit0, s));
         PUnit* du = nullptr;
-        SBA_TRY(dev_alloc(p, &du, hu.size()));
-        SBA_CUDA(cudaMemcpyAsync(du, hu.data(), hu.size() * sizeof(PUnit), cudaMemcpyHostToDevice, s));
-        (k ? p->pt_units_narrow : p->pt_units) = du;
+        SBA_TRY(dev_alloc(p, &du, as.units.size()));
+        SBA_CUDA(cudaMemcpyAsync(du, as.units.data(), as.units.size() * sizeof(PUnit), cudaMemcpyHostToDevice, s));
+        p->pt_units[k] = du;
     }
     // warp tiles of the generic per-track kernels are not used by this engine
     p->n_tiles = 0;

@@ -97,7 +97,7 @@ int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, 
                       int* sizes, int* trk_new2old, int* obs_new2old, int* track_ptr_new, int* units, int* warp_unit0)
 {
     PatternLayout L;
-    build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, warps, std::max(1, warps - 4), 6, 3, L);
+    build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, warps + 8, warps, std::max(1, warps - 4), 6, 3, L);
     sizes[0] = L.ok ? 1 : 0; sizes[1] = (int)L.wide.units.size(); sizes[2] = 0; sizes[3] = L.n_frozen_tracks;
     sizes[4] = (int)L.n_tiles; sizes[5] = L.n_runs;
     if (!L.ok || !trk_new2old) return 0;
