@@ -5,9 +5,11 @@ Benchmark of the bundle-adjustment hot path (see DESIGN.md "Measurement").
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|1m|small|cfg3|cfg3a|cfg4s]
 
 One JSON line on stdout (rank 0).  A "step" is one trust-region (Levenberg-Marquardt) iteration of the
-BASELINE.json config-2 problem: synthetic 10-view perspective BA, 1e5 tracks / ~5e5 observations,
-soft_l1 loss, correction_params R+T.  At N > 1 every rank gets its own 1e5 tracks (weak scaling, the
-10 cameras are shared) and the per-iteration exchange is the SUM all-reduce of the partial camera system.
+workload the metric is quoted on ("LM iters/s and Jacobian obs/s at 1M obs"): BASELINE config 2 at twice its
+track count -- synthetic 10-view perspective BA, 2e5 tracks / ~1e6 observations, soft_l1 loss,
+correction_params R+T (`--workload 1m`, the default; `cfg2` is config 2 itself and is reported next to it under
+"secondary" at N = 1).  At N > 1 every rank gets its own 2e5 tracks (weak scaling, the 10 cameras are shared)
+and the per-iteration exchange is the SUM all-reduce of the partial camera system.
 
   value   = observations x iterations / second, device time (CUDA events) summed over exactly K
             iterations, inputs resident in HBM, L2 overwritten between iterations, max over ranks
@@ -37,7 +39,9 @@ WORKLOADS = {
     "cfg2": (10, 100000, 0.5, "perspective", ["R", "T"],
              "BASELINE config 2: synthetic 10-view perspective BA, 1e5 tracks / ~5e5 observations, soft_l1, R+T"),
     "1m": (10, 200000, 0.5, "perspective", ["R", "T"],
-           "config 2 doubled: 10-view perspective BA, 2e5 tracks / ~1e6 observations, soft_l1, R+T"),
+           "the metric's size: BASELINE config 2 at 2e5 tracks -- 10-view perspective BA, ~1e6 observations, soft_l1, R+T"),
+    "5m": (10, 1000000, 0.5, "perspective", ["R", "T"],
+           "10-view perspective BA, 1e6 tracks / ~5e6 observations, soft_l1, R+T (HBM-resident working set >> L2)"),
     "small": (6, 4000, 0.5, "perspective", ["R", "T"], "smoke-size: 6 views, 4e3 tracks"),
     # BASELINE configs 3 and 4 per GPU (parity / scaling cases, not the bench line): 8 x 125k tracks = 1e6 tracks, ~5e6 obs
     "cfg3": (50, 125000, 0.1, "perspective", ["R", "T"],
@@ -61,22 +65,32 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(phase, workload):
-    """(dram__bytes_read.sum + dram__bytes_write.sum per launch, source, FP64 pipe utilisation) of the phase's main kernel, from the committed summary of one
-    `ncu --set full` capture of this workload (profiles/r01_ncu_full_selected_metrics.csv); None when there is none."""
-    main_kernel = {"schur": "k_schur<", "assemble": "k_assemble_points<", "point_prep": "k_point_prep<", "backsub": "k_backsub<",
-                   "cholesky": "k_chol_fused<", "scale_jvp": "k_jvp<1, 6, 1>", "subspace": "k_jvp<1, 6, 2>",
-                   "step_eval": "k_residual<"}.get(phase)
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_selected_metrics.csv")
-    if workload != "cfg2" or main_kernel is None or not os.path.exists(path):
-        return None, None, None
+# phase -> (main kernel of the phase, as named in the ncu summaries) for the two engines of libsba_b200.so
+PHASE_KERNELS = {
+    "pattern": {"assemble_trial": "k_pt_assemble<", "jvp_damping": "k_pt_jvp1<", "eliminate_schur": "k_pt_schur<",
+                "cholesky": "k_chol_fused<", "backsub_gram": "k_pt_backsub<"},
+    "generic": {"schur": "k_schur<", "assemble": "k_assemble_points<", "point_prep": "k_point_prep<", "backsub": "k_backsub<",
+                "cholesky": "k_chol_fused<", "scale_jvp": "k_jvp<1, 6, 1>", "subspace": "k_jvp<1, 6, 2>", "step_eval": "k_residual<"},
+}
+# C-ABI phase slots -> names used for the pattern engine (K1 doubles as trial evaluation and assembly: "step_eval" slot)
+PATTERN_PHASES = {"scale_jvp": "jvp_damping", "schur": "eliminate_schur", "cholesky": "cholesky", "backsub": "backsub_gram",
+                  "step_eval": "assemble_trial"}
+
+
+def ncu_summary(engine, phase, workload):
+    """Row of the committed ncu summary (one `ncu --set full --clock-control none` capture per kernel of this workload,
+    profiles/r02_ncu_<workload>_selected_metrics.csv, written by tools/summarize_profiles.py) for the phase's main kernel."""
+    kern = PHASE_KERNELS[engine].get(phase)
+    name = "r02_ncu_%s_selected_metrics.csv" % workload if engine == "pattern" else "r01_ncu_full_selected_metrics.csv"
+    path = os.path.join(ROOT, "profiles", name)
+    if kern is None or not os.path.exists(path) or (engine == "generic" and workload != "cfg2"):
+        return None, None
     import csv
     with open(path) as f:
         for row in csv.DictReader(f):
-            if row["kernel"].startswith(main_kernel):
-                src = "profiles/r01_ncu_full_selected_metrics.csv (%s, one ncu --set full capture, cold L2)" % row["kernel"]
-                return (float(row["dram rd MB"]) + float(row["dram wr MB"])) * 1e6, src, float(row["fp64 pipe %"]) / 100.0
-    return None, None, None
+            if row["kernel"].startswith(kern):
+                return row, "profiles/%s (%s, one ncu --set full capture, cold L2)" % (name, row["kernel"])
+    return None, None
 
 
 class ClockSampler:
@@ -133,18 +147,36 @@ def build_problem(workload, world):
     return synth.scene_to_params(scene, corr)
 
 
-def algorithmic_bytes(K, N, M, c):
-    """SURVEY.md section 8d, int32 indices + FP64 values, J never materialised (per LM iteration pass)."""
+def algorithmic_bytes(K, N, M, c, engine):
+    """int32 indices + FP64 values, J and W never materialised, camera tables once (per pass)."""
+    n = M * c + 3 * N
+    if engine == "pattern":
+        return {
+            "assemble_trial": 48 * K + 96 * N + 4 * M * c * (c + 3),    # B_asm: one fused residual + Jacobian + assembly pass (G1 + G2)
+            "jvp_damping": 48 * K + 48 * N + 5 * 8 * n,                 # one J*v pass + the scale update
+            "eliminate_schur": 48 * K + 120 * N + 8 * (M * c) ** 2,     # observations, x, V, g, D of the points in; S out (G3)
+            "backsub_gram": 32 * K + 120 * N,                           # B_back (G6)
+            "cholesky": 8 * (M * c) ** 2,
+        }
     return {
         "assemble": 48 * K + 96 * N + 4 * M * c * (c + 3),          # G2: one fused residual+Jacobian+assembly pass
         "step_eval": 48 * K + 24 * N + 8 * 16 * M,                  # G1: one residual pass (no r written)
-        "scale_jvp": 48 * K + 48 * N + 5 * 8 * (M * c + 3 * N),     # vector update + one J*v pass
-        "subspace": 48 * K + 48 * N + 9 * 8 * (M * c + 3 * N),      # vector work + one J*[v1 v2] pass
+        "scale_jvp": 48 * K + 48 * N + 5 * 8 * n,                   # vector update + one J*v pass
+        "subspace": 48 * K + 48 * N + 9 * 8 * n,                    # vector work + one J*[v1 v2] pass
         "point_prep": 48 * K + 24 * N + 48 * N + 48 * N + 72 * N + 24 * c * K,   # + Z write (non-algorithmic 24cK)
         "schur": 24 * c * K + 8 * (M * c) ** 2,                     # read Z once + write S
         "backsub": 24 * c * K + 72 * N + 24 * N + 4 * K,
         "cholesky": 8 * (M * c) ** 2,
     }
+
+
+def fp64_peak():
+    """Measured FP64 FMA peak of this pool's B200 (tools/fp64_peak.cu, committed result profiles/r02_fp64_peak.json)."""
+    path = os.path.join(ROOT, "profiles", "r02_fp64_peak.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["dfma_tflops"]), "measured (profiles/r02_fp64_peak.json, DFMA stream)"
+    return 37.2, "nominal (148 SMs x 64 FMA/clk x 1.965 GHz)"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -216,7 +248,8 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOADS[args.workload][5], "n_obs": int(q.n_obs), "n_tracks": int(q.n_pts),
                    "n_cam": int(q.n_cam), "loss": LS["loss"]},
         "lm_iters_per_s": 1.0 / sec_it,
-        "cpu_baseline": {"value": value, "unit": "obs*it/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample + "; numpy/scipy free to use all host threads (the path is mostly serial)"},
+        "cpu_baseline": {"value": value, "unit": "obs*it/s", "cores": 1, "kind": "port",
+                         "sample": sample + "; numpy / scipy.sparse run this path on one thread (%d host cores present)" % (os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": "obs*it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -227,25 +260,16 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def run_b200_arm(args):
+def measure_workload(workload, K, W, world, rank, local_rank, with_e2e=True, with_clocks=True):
+    """Device-timed iterations (+ phases), the fused Jacobian/assembly pass alone and the end-to-end call for one workload.
+    Returns a dict of raw measurements on every rank (max over ranks already taken)."""
     import torch
     import torch.distributed as dist
     from sat_bundleadjust_b200 import ba_core
     from sat_bundleadjust_b200 import dist as sdist
     from sat_bundleadjust_b200.solver import DeviceProblem, initial_vars
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    W, K = args.warmup, args.steps
-    p = build_problem(args.workload, world)
+    p = build_problem(workload, world)
     ranges = sdist.shard_ranges(p.pts_ind, p.n_pts, world)
     ncv = p.n_cam * p.n_params
     x0 = initial_vars(p)
@@ -271,23 +295,24 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # untimed: one short solve so that every kernel is loaded and the NCCL communicator is warm
+    # untimed: one short solve so that every kernel is loaded and the exchange buffers are mapped
     prob.solve_device(x_dev.data_ptr(), out_dev.data_ptr(), None, ftol=0.0, xtol=0.0, gtol=0.0, max_nfev=10 ** 6,
                       max_iterations=2, **LS)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
     # exactly K timed iterations; long runs are cut into solves of <= SEG timed iterations that each restart from
     # x0 (with W untimed iterations first), so that every timed iteration is a productive pre-convergence one
     SEG = 25
 
     def timed_run(no_phase_timing):
-        left, acc = K, None
+        left, acc, per_it = K, None, []
         while left > 0:
             k = min(SEG, left)
             part = prob.solve_device(x_dev.data_ptr(), out_dev.data_ptr(), None, ftol=0.0, xtol=0.0, gtol=0.0,
                                      max_nfev=10 ** 6, max_iterations=W + k, timed_from=W, l2_flush_bytes=L2_FLUSH_BYTES,
                                      no_phase_timing=no_phase_timing, **LS)
             assert part["timed_iterations"] == k, part
+            per_it.append(part["iter_ms"] / k)
             if acc is None:
                 acc = part
             else:
@@ -297,22 +322,24 @@ def run_b200_arm(args):
                 for ph in acc["phase_ms"]:
                     acc["phase_ms"][ph] += part["phase_ms"][ph]
             left -= k
+        acc["segment_ms_per_iteration"] = per_it
         return acc
 
     # the headline: whole iterations only (one CUDA-event pair per iteration); then the same K iterations again with the
-    # per-phase events on (~16 more event records per iteration, which themselves cost ~1 us each on the stream)
+    # per-phase events on (more event records per iteration, which themselves cost ~1 us each on the stream)
     info = timed_run(1)
     barrier()
     info_ph = timed_run(0)
-    info["phase_ms"] = info_ph["phase_ms"]
-    iter_ms_with_phase_events = info_ph["iter_ms"]
     barrier()
-    t = torch.tensor([info["iter_ms"]] + [info["phase_ms"][k] for k in info["phase_ms"]], dtype=torch.float64, device="cuda")
+    keys = list(info_ph["phase_ms"].keys())
+    t = torch.tensor([info["iter_ms"], info_ph["iter_ms"]] + [info_ph["phase_ms"][k] for k in keys], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t = t.cpu().numpy()
-    iter_ms = float(t[0])
-    phase_ms = {k: float(v) / K for k, v in zip(info["phase_ms"].keys(), t[1:])}
+    engine = prob.engine
+    phase_ms = {k: float(v) / K for k, v in zip(keys, t[2:])}
+    if engine == "pattern":
+        phase_ms = {PATTERN_PHASES[k]: v for k, v in phase_ms.items() if k in PATTERN_PHASES}
 
     # Jacobian pass alone (fused residual + analytic Jacobian + robust weights + block assembly), L2-cold
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
@@ -325,88 +352,141 @@ def run_b200_arm(args):
     jac = torch.tensor([float(np.mean(jac_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(jac, op=dist.ReduceOp.MAX)
-    jac_ms_mean = float(jac.item())
-    clocks = sampler.stop() if sampler else None
+    out = {"p": p, "engine": engine, "iter_ms": float(t[0]), "iter_ms_with_phase_events": float(t[1]), "phase_ms": phase_ms,
+           "jac_ms": float(jac.item()), "gpu_launches": int(info["gpu_launches"]), "n_obs_local": prob.n_obs,
+           "n_pts_local": prob.n_pts, "n_vars_local": prob.n_vars, "segments": info["segment_ms_per_iteration"],
+           "clocks": sampler.stop() if sampler else None}
+    if world > 1:
+        dist.barrier()      # peers may still be reading this rank's exchange buffer
+    prob.close()
+    del flush, x_dev, out_dev
 
-    # end to end through the public API (host buffers in and out; rank 0's wall clock, all ranks take part):
-    # one untimed call (like the W warm-up steps: first-use allocations), then the mean of E2E_CALLS timed calls
-    E2E_CALLS = 3
-    ls = dict(LS, max_iter=300, verbose=0)
+    if with_e2e:
+        # end to end through the public API (host buffers in and out; rank 0's wall clock, all ranks take part): the first call of
+        # the process (first-use allocations: device slabs, pinned scalars) is reported on its own, then the mean of E2E_CALLS calls
+        E2E_CALLS = 3
+        ls = dict(LS, max_iter=300, verbose=0)
 
-    def e2e_call():
-        if world > 1:
-            return sdist.run_ba_optimization_distributed(p, ls)[5]
-        return ba_core.run_ba_optimization(p, ls, False, False, return_info=True)[5]
+        def e2e_call():
+            if world > 1:
+                return sdist.run_ba_optimization_distributed(p, ls)[5]
+            return ba_core.run_ba_optimization(p, ls, False, False, return_info=True)[5]
 
-    e2e_call()
-    walls = []
-    for _ in range(E2E_CALLS):
-        barrier()
-        t0 = time.perf_counter()
-        info_e = e2e_call()
-        torch.cuda.synchronize()
-        walls.append(time.perf_counter() - t0)
-    wall = float(np.mean(walls))
-    Kobs = int(p.n_obs)
-    n_loc = prob.n_vars
-    # per call: int32 cam / track index + camera-major permutation (12 B), observation (16 B) and weight (8 B) per observation,
-    # track offsets, x0 and the camera table in; x and the two per-observation error vectors out
-    h2d = 36 * prob.n_obs + 4 * (prob.n_pts + 1) + 8 * n_loc + 8 * p.cam_params.size
-    d2h = 8 * n_loc + 2 * 8 * prob.n_obs
-    e2e = {"value": Kobs * info_e["iterations"] / wall, "unit": "obs*it/s",
-           "h2d_bytes_per_step": int(h2d / max(1, info_e["iterations"])),
-           "d2h_bytes_per_step": int(d2h / max(1, info_e["iterations"])),
-           "wall_s": wall, "wall_s_calls": walls, "calls": E2E_CALLS, "warmup_calls": 1,
-           "iterations": info_e["iterations"], "nfev": info_e["nfev"], "status": info_e["status"],
-           "cost": info_e["cost"], "device_ms": info_e["solve_ms"], "wall_breakdown_s": info_e.get("wall_s"),
-           "call": "ba_core.run_ba_optimization(p, {'loss': 'soft_l1', 'f_scale': 1.0, 'max_iter': 300})"}
+        walls = []
+        for _ in range(1 + E2E_CALLS):
+            barrier()
+            t0 = time.perf_counter()
+            info_e = e2e_call()
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        wall = float(np.mean(walls[1:]))
+        Kobs = int(p.n_obs)
+        n_loc = out["n_vars_local"]
+        # per call: int32 camera / track index + internal permutation (12 B), observation (16 B) and weight (8 B) per observation,
+        # track offsets, x0 and the camera table in; x and the two per-observation error vectors out
+        h2d = 36 * out["n_obs_local"] + 4 * (out["n_pts_local"] + 1) + 8 * n_loc + 8 * p.cam_params.size
+        d2h = 8 * n_loc + 2 * 8 * out["n_obs_local"]
+        out["e2e"] = {"value": Kobs * info_e["iterations"] / wall, "unit": "obs*it/s",
+                      "h2d_bytes_per_step": int(h2d / max(1, info_e["iterations"])),
+                      "d2h_bytes_per_step": int(d2h / max(1, info_e["iterations"])),
+                      "wall_s": wall, "wall_s_calls": walls[1:], "calls": E2E_CALLS, "first_call_wall_s": walls[0],
+                      "first_call_value": Kobs * info_e["iterations"] / walls[0],
+                      "iterations": info_e["iterations"], "nfev": info_e["nfev"], "status": info_e["status"],
+                      "cost": info_e["cost"], "device_ms": info_e["solve_ms"], "wall_breakdown_s": info_e.get("wall_s"),
+                      "call": "ba_core.run_ba_optimization(p, {'loss': 'soft_l1', 'f_scale': 1.0, 'max_iter': 300})"}
+    return out
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, K = args.warmup, args.steps
+    m = measure_workload(args.workload, K, W, world, rank, local_rank)
+    second = None
+    if world == 1 and not args.no_secondary and args.workload != "cfg2":
+        second = measure_workload("cfg2", K, W, world, rank, local_rank, with_e2e=True, with_clocks=False)
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        M, c = p.n_cam, p.n_params
-        K_loc, N_loc = prob.n_obs, prob.n_pts
-        ab = algorithmic_bytes(K_loc, N_loc, M, c)
-        dominant = max(phase_ms, key=lambda k: phase_ms[k])
-        traffic, traffic_src, fp64_frac = ncu_traffic(dominant, args.workload)
-        roof_all = {k: {"ms": phase_ms[k], "algorithmic_bytes": ab[k],
-                        "achieved_GBps": ab[k] / (phase_ms[k] * 1e-3) / 1e9 if phase_ms[k] > 0 else None}
+        f64_peak, f64_src = fp64_peak()
+        p = m["p"]
+        M, c, Kobs = p.n_cam, p.n_params, int(p.n_obs)
+        K_loc, N_loc = m["n_obs_local"], m["n_pts_local"]
+        engine, phase_ms, iter_ms, jac_ms = m["engine"], m["phase_ms"], m["iter_ms"], m["jac_ms"]
+        ab = algorithmic_bytes(K_loc, N_loc, M, c, engine)
+        asm_key = "assemble_trial" if engine == "pattern" else "assemble"
+        # the dominant kernel of the iteration (the dense Cholesky is one CTA of latency, not a streaming kernel)
+        dominant = max((k for k in phase_ms if k != "cholesky"), key=lambda k: phase_ms[k])
+        row, row_src = ncu_summary(engine, dominant, args.workload)
+        traffic = (float(row["dram rd MB"]) + float(row["dram wr MB"])) * 1e6 if row else None
+        fp64_frac = float(row["fp64 pipe %"]) / 100.0 if row else None
+        # FP64 work of the dominant kernel: thread-level FP64 instructions counted by ncu for one launch (FMA = 2 flop)
+        flop = float(row["fp64 Gflop"]) * 1e9 if row and row.get("fp64 Gflop") else None
+        roof_all = {k: {"ms": phase_ms[k], "algorithmic_bytes": ab.get(k),
+                        "achieved_GBps": ab[k] / (phase_ms[k] * 1e-3) / 1e9 if phase_ms[k] > 0 and k in ab else None}
                     for k in phase_ms}
         ach = ab[dominant] / (phase_ms[dominant] * 1e-3) / 1e9
-        jac_ach = ab["assemble"] / (jac_ms_mean * 1e-3) / 1e9
+        jac_ach = ab[asm_key] / (jac_ms * 1e-3) / 1e9
+        seg = np.array(m["segments"])
         line = {
             "metric": "lm_observation_iterations_per_s", "value": Kobs * K / (iter_ms * 1e-3), "unit": "obs*it/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": iter_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][5], "n_obs": Kobs, "n_tracks": int(p.n_pts), "n_cam": int(M),
-                       "n_params_per_cam": int(c), "loss": LS["loss"], "tracks_per_gpu": int(N_loc),
+                       "n_params_per_cam": int(c), "loss": LS["loss"], "tracks_per_gpu": int(N_loc), "engine": engine,
                        "parallelism": "tracks sharded over %d GPU(s), cameras replicated" % world,
-                       "exchange": ("none" if world == 1 else os.environ.get("SBA_COMM", "peer") + " (per iteration: [U|g_c], [S|rhs], 5 scalar groups)"),
+                       "exchange": ("none" if world == 1 else os.environ.get("SBA_COMM", "peer") +
+                                    (" (per iteration: [U|g_c|cost], 5 scalars, [S|rhs], 7 scalars)" if engine == "pattern"
+                                     else " (per iteration: [U|g_c], [S|rhs], 5 scalar groups)")),
                        "l2": "256 MiB scratch overwritten between timed iterations (outside the event pairs)"},
             "lm_iters_per_s": K / (iter_ms * 1e-3),
-            "jacobian_obs_per_s": Kobs / (jac_ms_mean * 1e-3),
-            "jacobian_pass_ms": jac_ms_mean,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(info["gpu_launches"]),
-            "roofline": {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         # the other roofline of this FP64 path: share of the FP64 pipe's issue slots the kernel used (ncu)
+            "ms_per_step_segments": {"mean": float(seg.mean()), "min": float(seg.min()), "max": float(seg.max()), "n": int(seg.size)},
+            "jacobian_obs_per_s": Kobs / (jac_ms * 1e-3),
+            "jacobian_pass_ms": jac_ms,
+            "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
+            "roofline": {"kernel": dominant + " (" + PHASE_KERNELS[engine].get(dominant, "?").rstrip("<") + ")", "bound": "hbm",
+                         "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": row_src, "peak_source": peak_src,
+                         # the roofline that actually binds this FP64 path: FP64 pipe issue slots used (ncu), and the counted FP64
+                         # work of one launch over the live kernel time against the measured DFMA peak
                          "fp64_pipe_frac": fp64_frac,
-                         "jacobian_assembly": {"achieved": jac_ach, "frac": jac_ach / peak, "ms": jac_ms_mean,
-                                               "algorithmic_bytes": ab["assemble"]}},
+                         "fp64": ({"flop_per_launch": flop, "achieved_tflops": flop / (phase_ms[dominant] * 1e-3) / 1e12,
+                                   "peak_tflops": f64_peak, "frac": flop / (phase_ms[dominant] * 1e-3) / 1e12 / f64_peak,
+                                   "peak_source": f64_src} if flop else None),
+                         "jacobian_assembly": {"achieved": jac_ach, "frac": jac_ach / peak, "ms": jac_ms,
+                                               "algorithmic_bytes": ab[asm_key]}},
             "phases_ms_per_iteration": phase_ms, "phases": roof_all,
-            "ms_per_step_with_phase_events": iter_ms_with_phase_events / K,
+            "ms_per_step_with_phase_events": m["iter_ms_with_phase_events"] / K,
         }
+        if second is not None:
+            q = second["p"]
+            line["secondary"] = [{"workload": WORKLOADS["cfg2"][5], "n_obs": int(q.n_obs), "engine": second["engine"],
+                                  "value": int(q.n_obs) * K / (second["iter_ms"] * 1e-3), "unit": "obs*it/s",
+                                  "ms_per_step": second["iter_ms"] / K, "phases_ms_per_iteration": second["phase_ms"],
+                                  "jacobian_pass_ms": second["jac_ms"], "e2e": second["e2e"]}]
         if world == 1 and not args.no_cpu_baseline:
-            q = p
-            sec_it, done, _ = cpu_reference_iterations(q, 3, 1)
+            # bounded sample (~20 s of CPU work): 2 TRF iterations after 1 warm-up iteration on the first half of the tracks
+            q = subsample_tracks(p, 0.5) if p.n_obs > 600000 else p
+            sec_it, done, _ = cpu_reference_iterations(q, 2, 1)
             line["cpu_baseline"] = {"value": q.n_obs / sec_it, "unit": "obs*it/s", "cores": 1, "kind": "port",
-                                    "lm_iters_per_s": 1.0 / sec_it,
-                                    "sample": "3 TRF iterations (after 1 warm-up iteration) of scipy least_squares (2-point "
-                                              "sparse differences + LSMR) on the full workload; the path is single-threaded "
-                                              "numpy / scipy.sparse (%d host cores present)" % (os.cpu_count() or 1)}
+                                    "lm_iters_per_s_at_sample_size": 1.0 / sec_it,
+                                    "sample": "%d TRF iterations (after 1 warm-up iteration) of scipy least_squares (2-point sparse "
+                                              "differences + LSMR) on %s; obs x it/s is size-normalised; the path is single-threaded "
+                                              "numpy / scipy.sparse (%d host cores present)"
+                                              % (done, "the first half of the tracks (%d observations)" % q.n_obs if q is not p
+                                                 else "the full workload", os.cpu_count() or 1)}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()      # peers may still be reading this rank's exchange buffer
-    prob.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -424,7 +504,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 line reported under \"secondary\" (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

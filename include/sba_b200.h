@@ -98,6 +98,8 @@ typedef struct sba_solve_info {
     double phase_ms[8];       /* the same, split by phase (SBA_PH_*) */
     int32_t explicit_subspace_passes; /* iterations that ran the explicit J*[t1 t2] pass (= all of them: the algebraic
                                          shortcut through the normal equations cancels catastrophically) */
+    int32_t pcg_solves;       /* reduced camera systems solved by block-Jacobi PCG (0 on the dense Cholesky path) ... */
+    int32_t pcg_iterations;   /* ... and the CG iterations they took in total */
 } sba_solve_info;
 
 /* Optional hook for the multi-GPU exchange step: must SUM `count` doubles at device pointer `buf`
@@ -123,6 +125,10 @@ int sba_comm_export(sba_problem *p, void *handle_out_64_bytes);
 int sba_comm_import(sba_problem *p, const void *handles_world_x_64_bytes);
 /* number of variables n = n_cam * n_params + 3 * n_pts */
 int64_t sba_problem_num_vars(const sba_problem *p);
+/* Which of the two device engines serves this problem (diagnostics / measurement): 1 = pattern-major (reduced camera
+ * system of at most 132 unknowns, n_params <= 6: fused passes, nothing per-observation stored), 0 = generic (static pair
+ * lists, any size up to 4096 camera unknowns).  SBA_ENGINE=generic in the environment forces 0. */
+int sba_problem_engine(const sba_problem *p);
 
 /* Replaces ba_core.fun(v, p) (ba_core.py:157-183): x (n) -> weighted residuals r (2K), interleaved.
  * Also returns 0.5*sum(rho(r)) for the given loss in *cost (may be NULL). */

@@ -45,7 +45,8 @@ class SolveInfo(ctypes.Structure):
                 ("iterations", ctypes.c_int32), ("cost_init", ctypes.c_double), ("cost", ctypes.c_double),
                 ("optimality", ctypes.c_double), ("solve_ms", ctypes.c_double), ("chol_retries", ctypes.c_int32),
                 ("gpu_launches", ctypes.c_int32), ("timed_iterations", ctypes.c_int32), ("iter_ms", ctypes.c_double),
-                ("phase_ms", ctypes.c_double * 8), ("explicit_subspace_passes", ctypes.c_int32)]
+                ("phase_ms", ctypes.c_double * 8), ("explicit_subspace_passes", ctypes.c_int32),
+                ("pcg_solves", ctypes.c_int32), ("pcg_iterations", ctypes.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -61,7 +62,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 # every symbol include/sba_b200.h declares
 EXPORTED_SYMBOLS = [
     "sba_last_error", "sba_version", "sba_problem_create", "sba_problem_destroy", "sba_release_cached_memory", "sba_problem_set_allreduce",
-    "sba_problem_num_vars", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve", "sba_solve_errors",
+    "sba_problem_num_vars", "sba_problem_engine", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve", "sba_solve_errors",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",
@@ -89,6 +90,7 @@ def load():
     lib.sba_comm_import.argtypes = [vp, ctypes.c_char_p]
     lib.sba_problem_num_vars.argtypes = [vp]
     lib.sba_problem_num_vars.restype = ctypes.c_int64
+    lib.sba_problem_engine.argtypes = [vp]
     lib.sba_residuals.argtypes = [vp, c_double_p, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p]
     lib.sba_jacobian_blocks.argtypes = [vp, c_double_p, c_double_p, c_double_p]
     lib.sba_normal_blocks.argtypes = [vp, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_double_p, c_double_p]

@@ -27,6 +27,7 @@
 #include "sba_index.h"
 #include "sba_kernels.cuh"
 #include "sba_pattern.cuh"
+#include "sba_pcg.cuh"
 #include "sba_tr2d.h"
 
 namespace sba {
@@ -351,6 +352,68 @@ static int run_jvp(sba_problem* p, int loss, double f_scale, int nvec, Slots out
     return check_launch(p);
 }
 
+// G5: the camera step from block-Jacobi PCG on the reduced camera system, matrix-free (sba_pcg.cuh).  Needs Z, F, q of
+// k_point_prep.  Tolerance: |r|_{M^-1} <= pcg_tol |r0|_{M^-1}; the trust-region step only uses the result as the second
+// direction of its 2-D subspace (scipy solves the same system with LSMR to 1e-6), so an inexact solve costs convergence
+// speed, never correctness.
+static int run_pcg(sba_problem* p)
+{
+    const int ns = p->M * p->nc, nc = p->nc;
+    const int nv = nc * (nc + 1) / 2 + nc;
+    double* cg = p->pcg_vec + 5 * (size_t)ns;
+    const int grid_t = (p->n_tiles + WPB - 1) / WPB;
+#define PCG_NC(MACRO)                                              \
+    switch (nc) {                                                  \
+    case 3: MACRO(3); break;                                       \
+    case 5: MACRO(5); break;                                       \
+    case 6: MACRO(6); break;                                       \
+    case 8: MACRO(8); break;                                       \
+    default: MACRO(11); break;                                     \
+    }
+#define L(NC) k_pcg_diag<NC><<<p->chunks.n, TPB, 0, p->stream>>>(p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->Z, p->q, p->cam_partials)
+    PCG_NC(L);
+#undef L
+    SBA_TRY(check_launch(p));
+    k_pcg_sum<<<p->M, 128, 0, p->stream>>>(p->cam_partials, p->cam_ptr, nv, cg, 0, p->pcg_diag);
+    SBA_TRY(check_launch(p));
+    SBA_TRY(allreduce_any(p, p->pcg_diag, (long long)p->M * nv));
+#define L(NC) k_pcg_init<NC><<<1, 1024, 0, p->stream>>>(p->pcg_diag, p->camsys, p->sinv, p->scal, p->M, p->n_cam_fix, p->pcg_L, p->pcg_vec, p->scal + SC_CHOL_FAIL)
+    PCG_NC(L);
+#undef L
+    SBA_TRY(check_launch(p));
+    const int max_it = p->pcg_max_it;
+    int it = 0;
+    while (it < max_it) {
+        const int batch = std::min(8, max_it - it);
+        for (int b = 0; b < batch; ++b) {
+#define L(NC)                                                                                                                  \
+    k_pcg_tracks<NC><<<grid_t, TPB, 0, p->stream>>>(obs_arrays(p), p->Z, p->pcg_vec + 3 * (size_t)ns, cg, p->pcg_s);             \
+    k_pcg_cameras<NC><<<p->chunks.n, TPB, 0, p->stream>>>(p->chunks.beg, p->chunks.end, p->cm_obs, p->cm_pts, p->Z, p->pcg_s, cg, \
+                                                          p->cam_partials)
+            PCG_NC(L);
+#undef L
+            SBA_TRY(check_launch(p)); p->launches++;
+            k_pcg_sum<<<p->M, 128, 0, p->stream>>>(p->cam_partials, p->cam_ptr, nc, cg, 1, p->pcg_w);
+            SBA_TRY(check_launch(p));
+            SBA_TRY(allreduce_any(p, p->pcg_w, (long long)ns));
+#define L(NC) k_pcg_update<NC><<<1, 1024, 0, p->stream>>>(p->pcg_w, p->camsys, p->sinv, p->scal, p->pcg_L, p->M, p->n_cam_fix, p->pcg_tol, max_it, p->pcg_vec)
+            PCG_NC(L);
+#undef L
+            SBA_TRY(check_launch(p));
+        }
+        it += batch;
+        // the host only looks at the flag between batches (converged launches inside a batch return at once)
+        SBA_CUDA(cudaMemcpyAsync(p->h_scal + SC_COUNT, cg, PCG_SCAL * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        SBA_CUDA(cudaStreamSynchronize(p->stream));
+        if (p->h_scal[SC_COUNT + 2] != 0.0) break;
+    }
+    p->pcg_iterations += (long long)p->h_scal[SC_COUNT + 3];
+    p->pcg_solves += 1;
+    SBA_CUDA(cudaMemcpyAsync(p->delta, p->pcg_vec, (size_t)ns * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+#undef PCG_NC
+    return SBA_OK;
+}
+
 // Schur complement + Cholesky solve + back-substitution for a given damping `reg`
 static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, PhaseTimer& tm, bool stop_after_schur = false)
 {
@@ -369,6 +432,12 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
         SBA_TRY(check_launch(p));
     }
     tm.end();
+    if (p->use_pcg) {
+        if (stop_after_schur) { set_error("the reduced camera system is not formed on the PCG path"); return SBA_E_INVALID; }
+        tm.begin(SBA_PH_SCHUR);
+        SBA_TRY(run_pcg(p));
+        tm.end();
+    } else {
     tm.begin(SBA_PH_SCHUR);
     {
 #define SCHUR_ARGS                                                                                                     \
@@ -413,6 +482,7 @@ static int run_gauss_newton_step(sba_problem* p, int loss, double f_scale, Phase
                                   p->stream, false));
     p->launches++;
     tm.end();
+    }
     tm.begin(SBA_PH_BACKSUB);
     {
         const int grid = (p->n_tiles + WPB - 1) / WPB;
@@ -448,6 +518,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     std::memset(info, 0, sizeof(*info));
     if (o->max_nfev < 1) { set_error("max_nfev must be >= 1"); return SBA_E_INVALID; }
     p->launches = 0;
+    p->pcg_iterations = 0; p->pcg_solves = 0;
     SBA_CUDA(cudaMemsetAsync(p->scal, 0, SC_COUNT * sizeof(double), p->stream));
     SBA_CUDA(cudaEventRecord(p->ev0, p->stream));
 
@@ -600,6 +671,7 @@ static int solve_on_device(sba_problem* p, const sba_solve_opts* o, sba_solve_in
     info->cost = cost; info->optimality = g_norm; info->solve_ms = ms; info->chol_retries = chol_retries;
     info->gpu_launches = p->launches;
     info->explicit_subspace_passes = iteration;
+    info->pcg_solves = (int)p->pcg_solves; info->pcg_iterations = (int)p->pcg_iterations;
     tm.resolve(info);
     it_tm.resolve(info);
     return SBA_OK;
@@ -708,14 +780,15 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     };
     // --- indices: int64 -> int32, track offsets, camera-major order, chunks, warp tiles (host, O(K), a few threads) ---
     HostIndex hidx;
-    const int irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx);
+    const bool try_pattern = pattern_engine_applicable(p);
+    int irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx, try_pattern);
     if (irc == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
     if (irc == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
     std::vector<int>&cam = hidx.cam, &pts = hidx.pts, &track_ptr = hidx.track_ptr, &cm_obs = hidx.cm_obs;
     std::vector<int>&ch_cam = hidx.ch_cam, &ch_beg = hidx.ch_beg, &ch_end = hidx.ch_end, &first_chunk = hidx.first_chunk;
     std::vector<int>& tile_obs = hidx.tile_obs;
     stamp("host index pass");
-    if (pattern_engine_applicable(p)) {
+    if (try_pattern) {
         PatternLayout lay;
         build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, PT_RC,
                              lay);
@@ -726,6 +799,8 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
             return rc;
         }
         if (timing) fprintf(stderr, "[sba create] pattern engine not applicable: %s\n", lay.why.c_str());
+        irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx);       // the generic engine needs the camera-major tables too
+        if (irc) { set_error("cam_ind / pts_ind invalid"); return SBA_E_INVALID; }
     }
     p->chunks.n = (int)ch_cam.size();
     p->chunks.h_cam = ch_cam;
@@ -772,13 +847,17 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     k_gather_camera_major<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cm_obs, p->pts_ind, (const double2*)p->pts2d, p->w, K,
                                                                        p->cm_pts, (double2*)p->cm_pts2d, p->cm_w);
     SBA_CUDA(cudaGetLastError());
-    SBA_TRY(dev_alloc(p, &p->obs_of, (size_t)M * N));
-    SBA_CUDA(cudaMemsetAsync(p->obs_of, 0xFF, (size_t)M * N * sizeof(int), s));
-    k_fill_obs_of<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cam_ind, p->pts_ind, K, N, p->obs_of);
-    SBA_CUDA(cudaGetLastError());
+    if (!p->use_pcg) {
+        SBA_TRY(dev_alloc(p, &p->obs_of, (size_t)M * N));
+        SBA_CUDA(cudaMemsetAsync(p->obs_of, 0xFF, (size_t)M * N * sizeof(int), s));
+        k_fill_obs_of<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->cam_ind, p->pts_ind, K, N, p->obs_of);
+        SBA_CUDA(cudaGetLastError());
+    }
     stamp("uploads + obs_of");
-    // --- static pair lists of the Schur complement: count, scan on the host, fill ---
-    {
+    // --- static pair lists of the Schur complement: count, scan on the host, fill (dense path only) ---
+    if (p->use_pcg) {
+        p->n_schur_items = 0; p->n_schur_blocks = 0; p->n_pairs = 0;
+    } else {
         const int n_items = item_base.back();
         int *d_counts = nullptr, *d_off = nullptr;
         SBA_TRY(dev_alloc(p, &d_counts, (size_t)n_items));
@@ -839,13 +918,21 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     SBA_TRY(dev_alloc(p, &p->camsys_local, ns * nc + ns));
     if (p->world > 1) SBA_TRY(dev_alloc(p, &p->camsys, ns * nc + ns));
     else p->camsys = p->camsys_local;
-    SBA_TRY(dev_alloc(p, &p->S, ns * ns + ns));
-    SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
+    if (p->use_pcg) {
+        const size_t nvc = (size_t)nc * (nc + 1) / 2 + nc;
+        SBA_TRY(dev_alloc(p, &p->pcg_vec, 5 * ns + PCG_SCAL)); SBA_TRY(dev_alloc(p, &p->pcg_diag, (size_t)M * nvc));
+        SBA_TRY(dev_alloc(p, &p->pcg_L, ns * nc)); SBA_TRY(dev_alloc(p, &p->pcg_w, ns)); SBA_TRY(dev_alloc(p, &p->pcg_s, 3 * (size_t)N));
+        SBA_CUDA(cudaMemsetAsync(p->pcg_vec, 0, (5 * ns + PCG_SCAL) * sizeof(double), s));
+        SBA_CUDA(cudaMemsetAsync(p->pcg_s, 0, 3 * (size_t)N * sizeof(double), s));
+    } else {
+        SBA_TRY(dev_alloc(p, &p->S, ns * ns + ns));
+        SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
+    }
     SBA_TRY(dev_alloc(p, &p->cvec, (size_t)3 * ns));
     const size_t nv_cam = (size_t)nc * (nc + 1) / 2 + nc;
     SBA_TRY(dev_alloc(p, &p->cam_partials, (size_t)p->chunks.n * nv_cam));
-    SBA_TRY(dev_alloc(p, &p->schur_partials, (size_t)p->n_schur_items * (nc * nc + nc)));
-    SBA_CUDA(cudaMemsetAsync(p->schur_partials, 0, (size_t)p->n_schur_items * (nc * nc + nc) * sizeof(double), s));
+    SBA_TRY(dev_alloc(p, &p->schur_partials, (size_t)std::max(p->n_schur_items, 1) * (nc * nc + nc)));
+    SBA_CUDA(cudaMemsetAsync(p->schur_partials, 0, (size_t)std::max(p->n_schur_items, 1) * (nc * nc + nc) * sizeof(double), s));
     SBA_TRY(dev_alloc(p, &p->red_partials, (size_t)std::max(NUM_SMS * 16, (p->n_tiles + WPB - 1) / WPB + 1) * 8));
     SBA_TRY(dev_alloc(p, &p->counters, 16));
     SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));
@@ -855,7 +942,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         std::lock_guard<std::mutex> lock(g_pool_mutex);
         if (!g_pinned_pool.empty()) { p->h_scal = g_pinned_pool.back(); g_pinned_pool.pop_back(); }
     }
-    if (!p->h_scal) SBA_CUDA(cudaMallocHost((void**)&p->h_scal, SC_COUNT * sizeof(double)));
+    if (!p->h_scal) SBA_CUDA(cudaMallocHost((void**)&p->h_scal, H_SCAL_COUNT * sizeof(double)));
     SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
     SBA_CUDA(cudaEventCreate(&p->ev0));
@@ -885,8 +972,19 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
         return SBA_E_INVALID;
     }
     if (d->world_size < 1 || d->world_size > 16 || d->rank < 0 || d->rank >= d->world_size) { set_error("bad rank / world_size"); return SBA_E_INVALID; }
-    if ((double)d->n_cam * d->n_pts > 1.5e9) { set_error("n_cam * n_pts too large for the dense (camera, track) table; use the matrix-free path"); return SBA_E_INVALID; }
-    if ((int64_t)d->n_cam * d->n_params > 4096) { set_error("reduced camera system larger than 4096: use the matrix-free path"); return SBA_E_INVALID; }
+    // Solver of the reduced camera system: dense Cholesky up to PCG_ABOVE unknowns, matrix-free block-Jacobi PCG beyond
+    // (SBA_SOLVER=pcg | dense overrides).  The dense path also needs a (camera, track) look-up table of n_cam * n_pts ints.
+    constexpr int64_t PCG_ABOVE = 1200, PCG_MAX_NS = 65536;
+    const int64_t ns_all = (int64_t)d->n_cam * d->n_params;
+    bool use_pcg = ns_all > PCG_ABOVE || (double)d->n_cam * d->n_pts > 1.5e9;
+    if (const char* e = getenv("SBA_SOLVER")) {
+        if (std::strcmp(e, "pcg") == 0) use_pcg = true;
+        if (std::strcmp(e, "dense") == 0) use_pcg = false;
+    }
+    if (use_pcg && d->n_common > 0) use_pcg = false;      // the shared-calibration border is only folded on the dense path
+    if (!use_pcg && (double)d->n_cam * d->n_pts > 1.5e9) { set_error("unsupported size: n_cam * n_pts > 1.5e9 needs the PCG path (no shared calibration, SBA_SOLVER unset)"); return SBA_E_INVALID; }
+    if (!use_pcg && ns_all > 4096) { set_error("unsupported size: more than 4096 camera unknowns need the PCG path (no shared calibration, SBA_SOLVER unset)"); return SBA_E_INVALID; }
+    if (ns_all > PCG_MAX_NS) { set_error("unsupported size: more than 65536 camera unknowns"); return SBA_E_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("no CUDA device: sat_bundleadjust_b200 has no CPU fallback");
@@ -897,6 +995,8 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
     p->n_cam_fix = d->n_cam_fix; p->n_pts_fix = d->n_pts_fix; p->rpc_f32 = d->rpc_float32;
     p->rank = d->rank; p->world = d->world_size;
     p->n_common = d->n_common;
+    p->use_pcg = use_pcg;
+    if (const char* e = getenv("SBA_PCG_TOL")) p->pcg_tol = atof(e);
     p->n = (int64_t)p->M * p->nc + 3 * (int64_t)p->N;
     p->stream = (cudaStream_t)stream;
     cudaGetDevice(&p->device);
@@ -915,6 +1015,7 @@ extern "C" int sba_problem_set_allreduce(sba_problem* p, sba_allreduce_fn fn, vo
 }
 
 extern "C" int64_t sba_problem_num_vars(const sba_problem* p) { return p ? p->n : -1; }
+extern "C" int sba_problem_engine(const sba_problem* p) { return p ? p->engine : -1; }
 
 // Multi-GPU exchange over peer memory: every rank exports the IPC handle of its symmetric buffer ...
 extern "C" int sba_comm_export(sba_problem* p, void* handle_out)
@@ -993,6 +1094,10 @@ extern "C" int sba_jacobian_blocks(sba_problem* p, const double* x, double* Jc, 
     if (dJc) cudaFree(dJc);
     if (dJp) cudaFree(dJp);
     if (p->engine == 1) {          // test-only entry point: un-permute on the host
+        if (p->h_obs_new2old.empty()) {
+            p->h_obs_new2old.resize((size_t)p->K);
+            SBA_CUDA(cudaMemcpy(p->h_obs_new2old.data(), p->obs_new2old, (size_t)p->K * sizeof(int), cudaMemcpyDeviceToHost));
+        }
         auto unperm = [&](double* buf, size_t width) {
             std::vector<double> tmp(buf, buf + (size_t)p->K * width);
             for (int64_t a = 0; a < p->K; ++a)

@@ -21,8 +21,9 @@ struct HostIndex {
 };
 
 // returns 0, 1 (index out of range) or 2 (pts_ind decreasing)
+// tracks_only: stop after the int32 copies and the track offsets (the pattern engine needs nothing else)
 inline int build_host_index(const int64_t* cam_ind, const int64_t* pts_ind, int64_t K, int M, int N, int chunk, int max_threads,
-                            HostIndex& h)
+                            HostIndex& h, bool tracks_only = false)
 {
     h.cam.assign(K, 0); h.pts.assign(K, 0); h.track_ptr.assign(N + 1, 0); h.cam_cnt.assign(M + 1, 0);
     const int hw = (int)std::thread::hardware_concurrency();
@@ -54,6 +55,7 @@ inline int build_host_index(const int64_t* cam_ind, const int64_t* pts_ind, int6
     for (int t = 0; t < nthr; ++t) if (thr_err[t]) return thr_err[t];
     h.track_ptr[N] = (int)K;
     for (int i = N - 1; i >= 0; --i) if (!seen[i]) h.track_ptr[i] = h.track_ptr[i + 1];
+    if (tracks_only) return 0;
     for (int j = 0; j < M; ++j) {
         int tot = 0;
         for (int t = 0; t < nthr; ++t) { const int c = thr_cnt[t][j]; thr_cnt[t][j] = tot; tot += c; }   // thread t's start inside camera j

@@ -74,6 +74,7 @@ enum Scal {
     SC_PA, SC_PB,
     SC_COUNT
 };
+constexpr int H_SCAL_COUNT = SC_COUNT + 8;      // pinned host mirror: the scalar block + the CG state of the PCG path
 
 struct ChunkTable {          // camera-major work items
     int n = 0;
@@ -150,6 +151,13 @@ struct sba_problem {
     size_t arena_left = 0;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+
+    // ---- G5: matrix-free PCG on the reduced camera system (csrc/sba_pcg.cuh), generic engine only ----
+    bool use_pcg = false;
+    double pcg_tol = 1e-8;
+    int pcg_max_it = 500;
+    long long pcg_iterations = 0, pcg_solves = 0;       // totals of the last solve (diagnostics)
+    double *pcg_vec = nullptr, *pcg_diag = nullptr, *pcg_L = nullptr, *pcg_w = nullptr, *pcg_s = nullptr;
 
     // ---- pattern engine (csrc/sba_pattern.h): internal track order = tracks grouped by visibility pattern ----
     int engine = 0;                                      // 0: generic (pair lists), 1: pattern-major

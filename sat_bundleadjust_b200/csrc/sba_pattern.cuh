@@ -1006,6 +1006,16 @@ __global__ void k_pt_obs_in(const double* __restrict__ in_ext, const int* __rest
         out_int[q] = in_ext[(long long)new2old[a] * width + (q - a * width)];
     }
 }
+// internal per-observation index arrays from the track permutation (one thread per internal track)
+__global__ void k_pt_build_obs(const int* __restrict__ trk_new2old, const int* __restrict__ track_ptr_old,
+                               const int* __restrict__ track_ptr_new, const int* __restrict__ cam_ext, int N,
+                               int* __restrict__ obs_new2old, int* __restrict__ cam_int, int* __restrict__ pts_int)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) {
+        const int o = trk_new2old[t], a0 = track_ptr_old[o], L = track_ptr_old[o + 1] - a0, b0 = track_ptr_new[t];
+        for (int k = 0; k < L; ++k) { obs_new2old[b0 + k] = a0 + k; cam_int[b0 + k] = cam_ext[a0 + k]; pts_int[b0 + k] = t; }
+    }
+}
 __global__ void k_pt_fill(double* __restrict__ dst, double v, long long n)
 {
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) dst[q] = v;

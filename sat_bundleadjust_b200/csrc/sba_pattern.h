@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace sba {
@@ -51,7 +52,6 @@ struct PatternLayout {
     bool ok = false;
     std::string why;                   // why the layout does not apply (generic engine is used instead)
     std::vector<int> trk_new2old;      // (N) internal track -> caller's track (tracks without observations last)
-    std::vector<int> obs_new2old;      // (K) internal observation -> caller's observation
     std::vector<int> track_ptr;        // (N+1) internal track offsets
     PatternAssignment light, wide, narrow;   // assignments for the CTA shapes in use (24 / 16 / 12 warps per CTA)
     int n_cta = 0, Lmax = 0, n_runs = 0;
@@ -137,23 +137,40 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     out = PatternLayout();
     if (M > 64) { out.why = "more than 64 cameras"; return; }
     if (N < 1 || K < 1) { out.why = "empty"; return; }
-    // key = camera bit set; aux orders frozen tracks first and tracks without observations last
+    // key = camera bit set; aux orders frozen tracks first and tracks without observations last (a few threads: O(K))
     std::vector<uint64_t> key(N);
     std::vector<unsigned char> aux(N);          // bit 0: free (frozen tracks come first), bit 1: no observations (sorted last)
-    int Lmax = 0;
-    for (int i = 0; i < N; ++i) {
-        const int a0 = track_ptr_old[i], a1 = track_ptr_old[i + 1];
-        uint64_t m = 0;
-        int prev = -1;
-        for (int a = a0; a < a1; ++a) {
-            if (cam[a] <= prev) { out.why = "cameras not strictly ascending inside a track"; return; }
-            prev = cam[a];
-            m |= (uint64_t)1 << cam[a];
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int nthr = std::max(1, std::min({8, hw > 0 ? hw : 1, N / 16384 + 1}));
+    std::vector<int> t_lmax(nthr, 0), t_frozen(nthr, 0), t_bad(nthr, 0);
+    auto scan = [&](int th) {
+        const int i0 = (int)((long long)N * th / nthr), i1 = (int)((long long)N * (th + 1) / nthr);
+        for (int i = i0; i < i1; ++i) {
+            const int a0 = track_ptr_old[i], a1 = track_ptr_old[i + 1];
+            uint64_t m = 0;
+            int prev = -1;
+            for (int a = a0; a < a1; ++a) {
+                if (cam[a] <= prev) { t_bad[th] = 1; return; }
+                prev = cam[a];
+                m |= (uint64_t)1 << cam[a];
+            }
+            key[i] = m;
+            aux[i] = (unsigned char)((i < n_pts_fix ? 0 : 1) | (a1 == a0 ? 2 : 0));
+            if (i < n_pts_fix && a1 > a0) t_frozen[th]++;
+            t_lmax[th] = std::max(t_lmax[th], a1 - a0);
         }
-        key[i] = m;
-        aux[i] = (unsigned char)((i < n_pts_fix ? 0 : 1) | (a1 == a0 ? 2 : 0));
-        if (i < n_pts_fix && a1 > a0) out.n_frozen_tracks++;
-        Lmax = std::max(Lmax, a1 - a0);
+    };
+    if (nthr == 1) scan(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int th = 0; th < nthr; ++th) pool.emplace_back(scan, th);
+        for (auto& t : pool) t.join();
+    }
+    int Lmax = 0;
+    for (int th = 0; th < nthr; ++th) {
+        if (t_bad[th]) { out.why = "cameras not strictly ascending inside a track"; return; }
+        Lmax = std::max(Lmax, t_lmax[th]);
+        out.n_frozen_tracks += t_frozen[th];
     }
     if (Lmax > 32) { out.why = "a track has more than 32 observations"; return; }
     out.Lmax = Lmax;
@@ -175,11 +192,6 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     out.trk_new2old = order;
     out.track_ptr.assign(N + 1, 0);
     for (int t = 0; t < N; ++t) out.track_ptr[t + 1] = out.track_ptr[t] + (track_ptr_old[order[t] + 1] - track_ptr_old[order[t]]);
-    out.obs_new2old.resize((size_t)K);
-    for (int t = 0; t < N; ++t) {
-        const int o = order[t], a0 = track_ptr_old[o], L = track_ptr_old[o + 1] - a0, b0 = out.track_ptr[t];
-        for (int k = 0; k < L; ++k) out.obs_new2old[b0 + k] = a0 + k;
-    }
     // runs and their tiles
     std::vector<PatternRun> runs;
     long long tiles = 0;

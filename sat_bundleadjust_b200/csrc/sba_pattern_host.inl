@@ -344,19 +344,22 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     const int64_t K = p->K;
     cudaStream_t s = p->stream;
     p->engine = 1;
+    p->use_pcg = false;
     p->pt_n_cta = lay.n_cta;
     p->n_pts_fix_int = lay.n_frozen_tracks;
     p->h_trk_new2old = lay.trk_new2old;
-    p->h_obs_new2old = lay.obs_new2old;
-    // internal-order indices for the generic per-observation kernels (residual output, Jacobian blocks)
-    std::vector<int> cam_int((size_t)K), pts_int((size_t)K);
-    for (int t = 0; t < N; ++t)
-        for (int b = lay.track_ptr[t]; b < lay.track_ptr[t + 1]; ++b) { cam_int[b] = hidx.cam[lay.obs_new2old[b]]; pts_int[b] = t; }
-    SBA_TRY(dev_upload(p, &p->cam_ind, cam_int, s));
-    SBA_TRY(dev_upload(p, &p->pts_ind, pts_int, s));
+    // internal-order indices for the generic per-observation kernels (residual output, Jacobian blocks) and the observation
+    // permutation are derived on the device from the track permutation
+    int *d_cam_ext = nullptr, *d_tp_old = nullptr;
+    SBA_TRY(dev_upload(p, &d_cam_ext, hidx.cam, s));
+    SBA_TRY(dev_upload(p, &d_tp_old, hidx.track_ptr, s));
+    SBA_TRY(dev_alloc(p, &p->cam_ind, (size_t)K)); SBA_TRY(dev_alloc(p, &p->pts_ind, (size_t)K));
+    SBA_TRY(dev_alloc(p, &p->obs_new2old, (size_t)K));
     SBA_TRY(dev_upload(p, &p->track_ptr, lay.track_ptr, s));
     SBA_TRY(dev_upload(p, &p->trk_new2old, lay.trk_new2old, s));
-    SBA_TRY(dev_upload(p, &p->obs_new2old, lay.obs_new2old, s));
+    k_pt_build_obs<<<grid_for(N, 256, NUM_SMS * 8), 256, 0, s>>>(p->trk_new2old, d_tp_old, p->track_ptr, d_cam_ext, N, p->obs_new2old,
+                                                                p->cam_ind, p->pts_ind);
+    SBA_CUDA(cudaGetLastError());
     for (int k = 0; k < 3; ++k) {
         const PatternAssignment& as = k == 0 ? lay.light : (k == 1 ? lay.wide : lay.narrow);
         SBA_TRY(dev_upload(p, &p->pt_warp_unit0[k], as.warp_unit0, s));
@@ -423,7 +426,7 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
         std::lock_guard<std::mutex> lock(g_pool_mutex);
         if (!g_pinned_pool.empty()) { p->h_scal = g_pinned_pool.back(); g_pinned_pool.pop_back(); }
     }
-    if (!p->h_scal) SBA_CUDA(cudaMallocHost((void**)&p->h_scal, SC_COUNT * sizeof(double)));
+    if (!p->h_scal) SBA_CUDA(cudaMallocHost((void**)&p->h_scal, H_SCAL_COUNT * sizeof(double)));
     SBA_CUDA(cudaEventCreate(&p->ev0));
     SBA_CUDA(cudaEventCreate(&p->ev1));
     SBA_TRY(pt_set_smem_attributes(p));

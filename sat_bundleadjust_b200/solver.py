@@ -91,6 +91,7 @@ class DeviceProblem:
         self.handle = ctypes.c_void_p()
         check(self.lib.sba_problem_create(ctypes.byref(self.handle), ctypes.byref(d), ctypes.c_void_p(stream)))
         self.n_vars_device = int(self.lib.sba_problem_num_vars(self.handle))
+        self.engine = "pattern" if self.lib.sba_problem_engine(self.handle) == 1 else "generic"
         # length of the caller's vector (the reference's params_opt layout); the device keeps n_params slots per camera
         self.n_vars = self.n_vars_device - (self.n_cam - 1) * self.n_common
         self._cb = None

@@ -102,7 +102,8 @@ int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, 
     sizes[4] = (int)L.n_tiles; sizes[5] = L.n_runs;
     if (!L.ok || !trk_new2old) return 0;
     std::copy(L.trk_new2old.begin(), L.trk_new2old.end(), trk_new2old);
-    std::copy(L.obs_new2old.begin(), L.obs_new2old.end(), obs_new2old);
+    for (int t = 0; t < N; ++t)          // the observation permutation the device derives (k_pt_build_obs)
+        for (int k = 0, a0 = track_ptr[L.trk_new2old[t]], b0 = L.track_ptr[t]; k < L.track_ptr[t + 1] - b0; ++k) obs_new2old[b0 + k] = a0 + k;
     std::copy(L.track_ptr.begin(), L.track_ptr.end(), track_ptr_new);
     static_assert(sizeof(PUnit) == 8 * sizeof(int), "PUnit layout");
     std::copy((const int*)L.wide.units.data(), (const int*)L.wide.units.data() + 8 * L.wide.units.size(), units);

@@ -21,6 +21,22 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    if "--tight" in sys.argv:
+        # BASELINE config 2 size, tight tolerances: the sharded solve and the single-GPU solve reach the same minimum
+        sc = synth.make_scene(n_cam=10, n_tracks=100000, p_vis=0.5, cam_model="perspective", seed=0)
+        p = synth.scene_to_params(sc, ["R", "T"])
+        ls = {"loss": "soft_l1", "f_scale": 1.0, "ftol": 1e-14, "xtol": 0.0, "max_iter": 3000, "verbose": 0}
+        v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
+        if rank == 0:
+            from oracle import ba_oracle
+            s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+            c_dist = ba_oracle.robust_cost(ba_oracle.residuals(v1.copy(), p), "soft_l1", 1.0)
+            c_one = ba_oracle.robust_cost(ba_oracle.residuals(s1.copy(), p), "soft_l1", 1.0)
+            rel = abs(c_dist - c_one) / c_one
+            print("tight %d obs: dist cost %.12e (oracle %.12e) nfev %d status %d | single cost %.12e (oracle %.12e) nfev %d status %d | rel %.2e"
+                  % (p.n_obs, info["cost"], c_dist, nfev, info["status"], info1["cost"], c_one, nfev1, info1["status"], rel), flush=True)
+            ok = ok and rel < 1e-8 and info["status"] > 0 and abs(c_dist - info["cost"]) < 1e-9 * c_dist
+            ok = ok and abs(np.sqrt(np.mean(e1 ** 2)) - np.sqrt(np.mean(f1 ** 2))) < 1e-6
     for model, corr, ntr, loss in (("perspective", ["R", "T"], 20000, "soft_l1"), ("affine", ["R"], 5000, "linear")):
         sc = synth.make_scene(n_cam=8, n_tracks=ntr, p_vis=0.5, cam_model=model, seed=3)
         p = synth.scene_to_params(sc, corr, n_cam_fix=1, n_pts_fix=10)

@@ -77,7 +77,58 @@ def full_table():
     return "\n".join(out)
 
 
+def full_table_r02(rep, out_csv):
+    """Round 2: selected metrics of one `ncu --set full --clock-control none` capture per kernel -> profiles/<out_csv>
+    (read by bench.py for `roofline.traffic`, `fp64_pipe_frac` and the counted FP64 work) and a markdown table."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    h = rows[0]
+    col = {k: i for i, k in enumerate(h)}
+    stalls = [k for k in h if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
+    sel = [("time us", "gpu__time_duration.sum"), ("dram rd MB", "dram__bytes_read.sum"), ("dram wr MB", "dram__bytes_write.sum"),
+           ("regs", "launch__registers_per_thread"), ("grid", "launch__grid_size"), ("block", "launch__block_size"),
+           ("fp64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+           ("issue active %", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("warp instr", "smsp__inst_executed.sum"),
+           ("L1 hit %", "l1tex__t_sector_hit_rate.pct"), ("L2 hit %", "lts__t_sector_hit_rate.pct")]
+    fl = ["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+          "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+    seen, table = set(), []
+    for r in rows[2:]:
+        name = short(r[col["Kernel Name"]])
+        if name in seen:
+            continue
+        seen.add(name)
+        vals = [r[col[m]] if m in col else "" for _, m in sel]
+        try:
+            gflop = (2 * float(r[col[fl[0]]]) + float(r[col[fl[1]]]) + float(r[col[fl[2]]])) / 1e9
+        except (KeyError, ValueError):
+            gflop = ""
+        st = sorted(((float(r[col[s]] or 0), s[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for s in stalls),
+                    reverse=True)[:4]
+        table.append((name, vals + [gflop], ", ".join("%s %.1f" % (n, v) for v, n in st)))
+    names = [a for a, _ in sel] + ["fp64 Gflop"]
+    with open(os.path.join(PROF, out_csv), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel"] + names + ["top stalls (warp cycles per issue)"])
+        for name, vals, st in table:
+            w.writerow([name] + vals + [st])
+    out = ["| kernel | " + " | ".join(names) + " | top stalls (cycles per issue) |", "|---|" + "---:|" * len(names) + "---|"]
+    for name, vals, st in table:
+        fmt = []
+        for v in vals:
+            try:
+                fmt.append("%.4g" % float(v))
+            except ValueError:
+                fmt.append(str(v))
+        out.append("| `%s` | " % name + " | ".join(fmt) + " | " + st + " |")
+    return "\n".join(out)
+
+
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "r02":
+        print(full_table_r02(sys.argv[2], sys.argv[3]))
+        sys.exit(0)
     d = json.load(open(os.path.join(OUT, "r01_bench_n1.json")))
     shutil.copy(os.path.join(OUT, "r01_bench_n1.json"), os.path.join(PROF, "r01_bench_n1.json"))
     print("### launch list\n")
