@@ -123,6 +123,9 @@ int sba_problem_set_allreduce(sba_problem *p, sba_allreduce_fn fn, void *user);
  * When imported, the solver uses it instead of the hook.  The problems of all ranks must be destroyed collectively. */
 int sba_comm_export(sba_problem *p, void *handle_out_64_bytes);
 int sba_comm_import(sba_problem *p, const void *handles_world_x_64_bytes);
+/* Attach to the exchange buffers this process already shares with the same peers (kept across problems: mapping them
+ * costs ~15 ms).  Returns 1 when attached, 0 when the export / gather / import sequence is needed. */
+int sba_comm_try_reuse(sba_problem *p);
 /* number of variables n = n_cam * n_params + 3 * n_pts */
 int64_t sba_problem_num_vars(const sba_problem *p);
 /* Which of the two device engines serves this problem (diagnostics / measurement): 1 = pattern-major (reduced camera
@@ -155,6 +158,9 @@ int sba_solve(sba_problem *p, const double *x0, const sba_solve_opts *opts, doub
 /* sba_solve plus the two per-observation reprojection-error vectors the reference's driver returns
  * (compute_reprojection_error, ba_core.py:304-305,335-349), computed on the device: err_init (K) at x0 and err (K) at the
  * solution; either may be NULL.  Saves the 2 x 2K residual read-backs and the host-side norms of the end-to-end call. */
+/* The same with device pointers (caller's layouts): nothing but the steering scalars crosses PCIe. */
+int sba_solve_errors_device(sba_problem *p, const double *x0_dev, const sba_solve_opts *opts, double *x_dev,
+                            double *err_init_dev, double *err_dev, sba_solve_info *info);
 int sba_solve_errors(sba_problem *p, const double *x0, const sba_solve_opts *opts, double *x, double *err_init, double *err,
                      sba_solve_info *info);
 

@@ -66,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",
-    "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import",
+    "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import", "sba_comm_try_reuse", "sba_solve_errors_device",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def load():
     lib.sba_problem_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     lib.sba_comm_export.argtypes = [vp, ctypes.c_char_p]
     lib.sba_comm_import.argtypes = [vp, ctypes.c_char_p]
+    lib.sba_comm_try_reuse.argtypes = [vp]
+    lib.sba_solve_errors_device.argtypes = [vp, vp, ctypes.POINTER(SolveOpts), vp, vp, vp, ctypes.POINTER(SolveInfo)]
     lib.sba_problem_num_vars.argtypes = [vp]
     lib.sba_problem_num_vars.restype = ctypes.c_int64
     lib.sba_problem_engine.argtypes = [vp]

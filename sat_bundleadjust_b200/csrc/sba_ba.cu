@@ -55,6 +55,32 @@ static std::mutex g_pool_mutex;
 static std::vector<Slab> g_slab_pool;
 static std::vector<double*> g_pinned_pool;          // pinned scalar blocks (SC_COUNT doubles)
 static size_t g_pool_bytes = 0;
+
+// Symmetric exchange buffer of the multi-GPU solve: one per process, kept (with its CUDA IPC mappings of the peers' buffers)
+// across problems -- opening the handles costs ~15 ms per call, more than a third of a solve at the bench size.
+struct CommGlobal {
+    void* buf = nullptr;
+    void* peer[16] = {nullptr};
+    long long cap = 0;                 // doubles per parity
+    unsigned long long seq = 0;        // exchange counter, the same on every rank
+    int world = 0, rank = -1, device = -1;
+    bool ready = false;
+};
+static CommGlobal g_comm;
+static void comm_release()
+{
+    if (!g_comm.buf) return;
+    for (int r = 0; r < g_comm.world; ++r)
+        if (g_comm.ready && r != g_comm.rank && g_comm.peer[r]) cudaIpcCloseMemHandle(g_comm.peer[r]);
+    cudaFree(g_comm.buf);
+    g_comm = CommGlobal();
+}
+static long long comm_needed(const sba_problem* p)
+{
+    const long long ns = (long long)p->M * p->nc;
+    const long long dense = p->use_pcg ? 0 : ns * ns + ns;
+    return std::max<long long>({dense, ns * p->nc + ns + 1, (long long)p->M * (p->nc * (p->nc + 1) / 2 + p->nc), (long long)SC_COUNT, 1LL << 16});
+}
 constexpr size_t SLAB_POOL_MAX = (size_t)16 << 30;
 
 static void* pool_take(size_t want, int device, size_t* got)
@@ -289,7 +315,7 @@ static int allreduce_any(sba_problem* p, double* buf, long long count)
             c.flag[r] = (unsigned long long*)((double*)p->comm_peer[r] + 2 * p->comm_cap);
         }
         c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
-        const unsigned long long seq = ++p->comm_seq;
+        const unsigned long long seq = ++g_comm.seq;
         const int grid = grid_for(count, 256, 16);
         if (p->comm_split) {        // SBA_COMM_SPLIT=1: the two-launch form (push, then pull)
             k_comm_push<<<grid, 256, 0, p->stream>>>(c, buf, count, seq, p->counters + 8);
@@ -738,6 +764,7 @@ extern "C" int sba_release_cached_memory(void)
     for (const Slab& c : g_slab_pool) { cudaSetDevice(c.device); cudaFree(c.ptr); }
     for (double* h : g_pinned_pool) cudaFreeHost(h);
     g_slab_pool.clear(); g_pinned_pool.clear(); g_pool_bytes = 0;
+    comm_release();
     cudaSetDevice(dev);
     return SBA_OK;
 }
@@ -749,9 +776,7 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     if (p->stream2) cudaStreamSynchronize(p->stream2);
     cudaStreamSynchronize(p->stream);               // nothing of this problem may still be running on the slabs
     for (size_t i = 0; i < p->arena_chunks.size(); ++i) pool_give(p->arena_chunks[i], p->arena_chunk_bytes[i], p->device);
-    for (int r = 0; r < p->world; ++r)
-        if (p->comm_ready && r != p->rank && p->comm_peer[r]) cudaIpcCloseMemHandle(p->comm_peer[r]);
-    if (p->comm_buf) cudaFree(p->comm_buf);
+    // the exchange buffer and its peer mappings belong to the process (g_comm), not to the problem
     if (p->h_scal) { std::lock_guard<std::mutex> lock(g_pool_mutex); g_pinned_pool.push_back(p->h_scal); }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1022,15 +1047,15 @@ extern "C" int sba_comm_export(sba_problem* p, void* handle_out)
 {
     if (!p || !handle_out) { set_error("null argument"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
-    if (!p->comm_buf) {
-        const long long ns = (long long)p->M * p->nc;
-        p->comm_cap = std::max<long long>(ns * ns + ns, std::max<long long>(ns * p->nc + ns, SC_COUNT));
-        const size_t bytes = (size_t)(2 * p->comm_cap) * sizeof(double) + 2 * COMM_MAX_RANKS * sizeof(unsigned long long);
-        SBA_CUDA(cudaMalloc(&p->comm_buf, bytes));
-        SBA_CUDA(cudaMemset(p->comm_buf, 0, bytes));
-    }
+    comm_release();                            // a fresh exchange group: drop whatever an earlier group left
+    g_comm.cap = comm_needed(p);
+    const size_t bytes = (size_t)(2 * g_comm.cap) * sizeof(double) + 2 * COMM_MAX_RANKS * sizeof(unsigned long long);
+    SBA_CUDA(cudaMalloc(&g_comm.buf, bytes));
+    SBA_CUDA(cudaMemset(g_comm.buf, 0, bytes));
+    g_comm.world = p->world; g_comm.rank = p->rank; g_comm.device = p->device;
+    p->comm_buf = g_comm.buf; p->comm_cap = g_comm.cap;
     cudaIpcMemHandle_t h;
-    SBA_CUDA(cudaIpcGetMemHandle(&h, p->comm_buf));
+    SBA_CUDA(cudaIpcGetMemHandle(&h, g_comm.buf));
     std::memcpy(handle_out, &h, sizeof(h));
     return SBA_OK;
 }
@@ -1038,17 +1063,32 @@ extern "C" int sba_comm_export(sba_problem* p, void* handle_out)
 // ... and maps the buffers of all ranks (handles: world x 64 bytes, in rank order; its own entry is skipped)
 extern "C" int sba_comm_import(sba_problem* p, const void* handles)
 {
-    if (!p || !handles || !p->comm_buf) { set_error("sba_comm_export must be called first"); return SBA_E_INVALID; }
+    if (!p || !handles || !g_comm.buf || p->comm_buf != g_comm.buf) { set_error("sba_comm_export must be called first"); return SBA_E_INVALID; }
     SBA_CUDA(cudaSetDevice(p->device));
     for (int r = 0; r < p->world; ++r) {
-        if (r == p->rank) { p->comm_peer[r] = p->comm_buf; continue; }
+        if (r == p->rank) { g_comm.peer[r] = g_comm.buf; continue; }
         cudaIpcMemHandle_t h;
         std::memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
-        SBA_CUDA(cudaIpcOpenMemHandle(&p->comm_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+        SBA_CUDA(cudaIpcOpenMemHandle(&g_comm.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
     }
+    g_comm.ready = true;
+    g_comm.seq = 0;
+    for (int r = 0; r < p->world; ++r) p->comm_peer[r] = g_comm.peer[r];
     p->comm_ready = true;
-    p->comm_seq = 0;
     return SBA_OK;
+}
+
+// Attach a new problem to the exchange buffers this process already shares with the same peers (same world, rank, device;
+// large enough).  Returns 1 when attached, 0 when sba_comm_export / sba_comm_import are needed.  All ranks of a group run the
+// same sequence of problems, so they agree on the answer.
+extern "C" int sba_comm_try_reuse(sba_problem* p)
+{
+    if (!p || !g_comm.ready || g_comm.world != p->world || g_comm.rank != p->rank || g_comm.device != p->device) return 0;
+    if (g_comm.cap < comm_needed(p)) return 0;
+    p->comm_buf = g_comm.buf; p->comm_cap = g_comm.cap;
+    for (int r = 0; r < p->world; ++r) p->comm_peer[r] = g_comm.peer[r];
+    p->comm_ready = true;
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1248,6 +1288,24 @@ extern "C" int sba_tr2d(const double B[4], const double g[2], double Delta, doub
 
 // sba_solve plus the two per-observation error vectors the reference's driver returns (ba_core.py:304-305), computed
 // on the device: err_init at x0, err at the solution (K doubles each, either may be NULL).
+// sba_solve_device plus the two per-observation error vectors (device pointers, caller's order; any may be NULL)
+extern "C" int sba_solve_errors_device(sba_problem* p, const double* x0_dev, const sba_solve_opts* opts, double* x_dev,
+                                       double* err_init_dev, double* err_dev, sba_solve_info* info)
+{
+    if (!p || !x0_dev || !opts || !info) { set_error("null argument"); return SBA_E_INVALID; }
+    SBA_CUDA(cudaSetDevice(p->device));
+    if (err_init_dev) {
+        SBA_TRY(vars_in(p, x0_dev, p->x_new));
+        SBA_TRY(run_prepare(p, p->x_new, p->camrec_new));
+        SBA_TRY(residuals_ext(p, p->x_new, p->camrec_new, SBA_LOSS_LINEAR, 1.0, p->r_out, SC_SCRATCH, p->rpc_f32));
+        SBA_TRY(reproj_errors_ext(p, p->r_out, err_init_dev));
+    }
+    SBA_TRY(sba_solve_device(p, x0_dev, opts, x_dev, err_dev ? p->r_out : nullptr, info));
+    if (err_dev) SBA_TRY(reproj_errors_ext(p, p->r_out, err_dev));
+    SBA_CUDA(cudaStreamSynchronize(p->stream));
+    return SBA_OK;
+}
+
 extern "C" int sba_solve_errors(sba_problem* p, const double* x0, const sba_solve_opts* opts, double* x, double* err_init,
                                 double* err, sba_solve_info* info)
 {

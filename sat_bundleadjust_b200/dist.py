@@ -21,10 +21,11 @@ def shard_ranges(pts_ind, n_pts, world_size):
     """
     Cut the track range [0, n_pts) into `world_size` contiguous pieces holding ~equal numbers of
     observations.  Returns a list of (t0, t1).  Deterministic; every rank computes the same cuts.
+    When there are fewer tracks with work than ranks the trailing ranges are empty.
     """
     pts_ind = np.asarray(pts_ind)
     K = pts_ind.size
-    track_ptr = np.searchsorted(pts_ind, np.arange(n_pts + 1), side="left")      # first observation of each track
+    track_ptr = np.concatenate([[0], np.cumsum(np.bincount(pts_ind, minlength=n_pts))])     # first observation of each track
     cuts = [0]
     for r in range(1, world_size):
         target = (K * r) // world_size
@@ -53,27 +54,60 @@ class _CudaView:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
+_PINNED = {}
+
+
+def _pinned(n):
+    """Page-locked host staging buffer of >= n doubles, kept for the life of the process (allocating one costs milliseconds)."""
+    import torch
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(int(n * 1.25) + 1024, dtype=torch.float64, pin_memory=True)
+        _PINNED["buf"] = buf
+    return buf[:n]
+
+
 def run_ba_optimization_distributed(p, ls_params=None, group=None):
     """
     Multi-GPU counterpart of ba_core.run_ba_optimization, to be called by every rank of an initialised
     torch.distributed NCCL process group (one process per GPU).  Every rank passes the same `p`.
     Returns (vars_init, vars_ba, err_init, err_ba, nfev, info) with the global vectors on every rank.
+
+    Each rank uploads only its own shard, the per-iteration exchanges run over NVLink peer memory, and the results
+    (x, err_init, err of every shard) are all-gathered on the device and brought back with one copy into pinned memory.
     """
-    from .solver import n_common_params
-    if n_common_params(p):
-        raise NotImplementedError("COMMON_K is not supported by the distributed driver")
+    import time
+
     import torch
     import torch.distributed as dist
 
     from . import ba_core
-    from .solver import DeviceProblem, initial_vars
+    from ._lib import SbaError
+    from .solver import DeviceProblem, initial_vars, n_common_params
 
+    if n_common_params(p):
+        raise NotImplementedError("COMMON_K is not supported by the distributed driver")
+    t_start = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     cfg = ba_core.init_optimization_config(ls_params)
-    ranges = shard_ranges(p.pts_ind, p.n_pts, world)
+    cache = getattr(p, "_sba_shard_cache", None)
+    if cache is None or cache[0] != (world, p.n_pts, p.pts_ind.size):
+        ranges = shard_ranges(p.pts_ind, p.n_pts, world)
+        a = [tuple(int(v) for v in np.searchsorted(p.pts_ind, [t0, t1])) for t0, t1 in ranges]
+        try:
+            p._sba_shard_cache = ((world, p.n_pts, p.pts_ind.size), ranges, a)
+        except AttributeError:
+            pass
+    else:
+        ranges, a = cache[1], cache[2]
+    if any(a1 == a0 for a0, a1 in a):
+        raise ValueError("fewer tracks with observations than ranks: use a smaller process group")
     ncv = p.n_cam * p.n_params
     x0 = initial_vars(p)
     stream = torch.cuda.current_stream().cuda_stream
+    n_loc = [ncv + 3 * (t1 - t0) for t0, t1 in ranges]
+    k_loc = [a1 - a0 for a0, a1 in a]
+    longest = max(n + 2 * k for n, k in zip(n_loc, k_loc))
 
     def hook(ptr, count):
         t = torch.as_tensor(_CudaView(ptr, count), device="cuda")
@@ -84,25 +118,45 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         dist.all_gather_object(out, obj, group=group)
         return out
 
+    t_prep = time.perf_counter()
+    failure = None
+    buf = torch.zeros(longest, dtype=torch.float64, device="cuda")
+    info = None
     with DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank]) as prob:
+        t_create = time.perf_counter()
         prob.set_allreduce(hook)                       # NCCL fall-back for exchanges that do not fit the peer buffer
         if os.environ.get("SBA_COMM", "peer") == "peer":
             prob.connect_peers(gather_obj)
-        xl0 = local_vars(x0, ncv, ranges[rank])
-        xl, e0, e1, info = prob.solve_with_errors(xl0, loss=cfg["loss"], f_scale=cfg["f_scale"], ftol=cfg["ftol"],
-                                                  xtol=cfg["xtol"], max_nfev=cfg["max_iter"])
+        t_connect = time.perf_counter()
+        xl0 = torch.from_numpy(prob._vars(local_vars(x0, ncv, ranges[rank]))).cuda()
+        nl, kl = n_loc[rank], k_loc[rank]
+        base = buf.data_ptr()
+        try:
+            info = prob.solve_errors_device(xl0.data_ptr(), base, base + 8 * nl, base + 8 * (nl + kl), loss=cfg["loss"],
+                                            f_scale=cfg["f_scale"], ftol=cfg["ftol"], xtol=cfg["xtol"], max_nfev=cfg["max_iter"])
+        except SbaError as exc:                        # raised after the barrier below, so that no peer is left spinning
+            failure = exc
+        t_solve = time.perf_counter()
         dist.barrier(group=group)                      # peers keep reading each other's buffers until everybody is done
-    # one all-gather of [x_local | err_init | err] per rank (variable length -> padded to the longest shard)
-    a = [np.searchsorted(p.pts_ind, [t0, t1]) for t0, t1 in ranges]
-    n_loc = [ncv + 3 * (t1 - t0) for t0, t1 in ranges]
-    k_loc = [int(a1 - a0) for a0, a1 in a]
-    longest = max(n + 2 * k for n, k in zip(n_loc, k_loc))
-    buf = torch.zeros(longest, dtype=torch.float64, device="cuda")
-    buf[: n_loc[rank] + 2 * k_loc[rank]] = torch.from_numpy(np.concatenate([xl, e0, e1])).cuda()
+    t_close = time.perf_counter()
+    # every rank learns whether any rank failed, and all raise together
+    flag = torch.tensor([1.0 if failure is not None else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
+    if flag.item() > 0:
+        if failure is not None and "not finite" in str(failure):
+            raise ValueError("Residuals are not finite in the initial point.") from failure
+        raise failure if failure is not None else SbaError("the solve failed on another rank")
+    # one all-gather of [x_local | err_init | err] per rank (variable length -> padded to the longest shard), one D2H copy
     out = torch.empty((world, longest), dtype=torch.float64, device="cuda")
     dist.all_gather_into_tensor(out, buf, group=group)
-    out = out.cpu().numpy()
-    x = merge_vars([out[r, : n_loc[r]] for r in range(world)], ncv)
-    err0 = np.concatenate([out[r, n_loc[r]: n_loc[r] + k_loc[r]] for r in range(world)])
-    err1 = np.concatenate([out[r, n_loc[r] + k_loc[r]: n_loc[r] + 2 * k_loc[r]] for r in range(world)])
+    host = _pinned(world * longest)
+    host.copy_(out.view(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    h = host.numpy().reshape(world, longest)
+    x = merge_vars([h[r, : n_loc[r]] for r in range(world)], ncv)
+    err0 = np.concatenate([h[r, n_loc[r]: n_loc[r] + k_loc[r]] for r in range(world)])
+    err1 = np.concatenate([h[r, n_loc[r] + k_loc[r]: n_loc[r] + 2 * k_loc[r]] for r in range(world)])
+    t_end = time.perf_counter()
+    info["wall_s"] = {"prepare": t_prep - t_start, "create": t_create - t_prep, "connect": t_connect - t_create,
+                      "solve": t_solve - t_connect, "close": t_close - t_solve, "gather": t_end - t_close}
     return x0, x, err0, err1, info["nfev"], info

@@ -223,6 +223,15 @@ class DeviceProblem:
                                         ctypes.c_void_p(r_ptr) if r_ptr else None, ctypes.byref(info)))
         return info.as_dict()
 
+    def solve_errors_device(self, x0_ptr, x_ptr, err_init_ptr, err_ptr, **kw):
+        """solve_with_errors with device pointers (caller's layouts)."""
+        info = SolveInfo()
+        opts = self.make_opts(**kw)
+        vp = ctypes.c_void_p
+        check(self.lib.sba_solve_errors_device(self.handle, vp(x0_ptr), ctypes.byref(opts), vp(x_ptr), vp(err_init_ptr), vp(err_ptr),
+                                               ctypes.byref(info)))
+        return info.as_dict()
+
     def assemble_device(self, x_ptr, loss="linear", f_scale=1.0):
         ms = ctypes.c_float()
         check(self.lib.sba_assemble_device(self.handle, ctypes.c_void_p(x_ptr), LOSS_IDS[loss], f_scale, ctypes.byref(ms)))
@@ -234,6 +243,8 @@ class DeviceProblem:
         as device-side one-shot kernels.  `all_gather_object(obj) -> list` must return every rank's object in rank order
         (e.g. a wrapper of torch.distributed.all_gather_object).
         """
+        if self.lib.sba_comm_try_reuse(self.handle) == 1:      # the process already shares buffers with these peers
+            return
         mine = ctypes.create_string_buffer(64)
         check(self.lib.sba_comm_export(self.handle, mine))
         handles = all_gather_object(bytes(mine.raw))
