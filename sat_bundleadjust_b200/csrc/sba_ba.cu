@@ -315,6 +315,10 @@ static int allreduce_any(sba_problem* p, double* buf, long long count)
             c.flag[r] = (unsigned long long*)((double*)p->comm_peer[r] + 2 * p->comm_cap);
         }
         c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
+        // 60 s by default (SBA_COMM_TIMEOUT_S): ranks make a host round trip per trial step, so ordinary skew (a busy host, first-touch
+        // IPC mapping, verbose output) must not be mistaken for a lost peer
+        static const double timeout_s = getenv("SBA_COMM_TIMEOUT_S") ? atof(getenv("SBA_COMM_TIMEOUT_S")) : 60.0;
+        c.timeout_cycles = (long long)(timeout_s * 1.9e9);
         const unsigned long long seq = ++g_comm.seq;
         const int grid = grid_for(count, 256, 16);
         if (p->comm_split) {        // SBA_COMM_SPLIT=1: the two-launch form (push, then pull)

@@ -22,6 +22,7 @@ struct CommView {            // passed to the kernels by value
     double* data[COMM_MAX_RANKS];                 // data[r]: base of rank r's buffer (own buffer for r == me)
     unsigned long long* flag[COMM_MAX_RANKS];     // flag[r]: flags of rank r
     long long cap;                                // doubles per parity
+    long long timeout_cycles;                     // a peer that has not arrived after this many clocks is reported, not waited for
     int me, world;
 };
 
@@ -72,7 +73,7 @@ k_comm_pull(CommView c, double* __restrict__ dst, long long count, unsigned long
         const unsigned long long* f = c.flag[c.me] + parity * COMM_MAX_RANKS + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > 4000000000LL) { ok = 0; break; }     // ~2 s: a peer is gone; report instead of hanging
+            if (clock64() - t0 > c.timeout_cycles) { ok = 0; break; }  // a peer is gone: report instead of hanging
         }
     }
     __syncthreads();
@@ -113,7 +114,7 @@ k_comm_allreduce(CommView c, double* __restrict__ buf, long long count, unsigned
         const unsigned long long* f = c.flag[c.me] + parity * COMM_MAX_RANKS + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > 4000000000LL) { ok = 0; break; }     // ~2 s: a peer is gone; report instead of hanging
+            if (clock64() - t0 > c.timeout_cycles) { ok = 0; break; }  // a peer is gone: report instead of hanging
         }
     }
     __syncthreads();

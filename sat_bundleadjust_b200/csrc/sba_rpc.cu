@@ -284,7 +284,12 @@ extern "C" void stereo_corresp_to_lonlatalt(double* lonlatalt, float* err, float
                                             void* rpc_a, void* rpc_b)
 {
     const int rc = sba_stereo_corresp_to_lonlatalt(lonlatalt, err, kp_a, kp_b, n_kp, rpc_a, rpc_b);
-    if (rc != SBA_OK) fprintf(stderr, "stereo_corresp_to_lonlatalt (sba_b200): %s\n", sba_last_error());
+    if (rc != SBA_OK) {
+        // the reference's signature has no way to report failure: never leave plausible-looking zeros behind
+        fprintf(stderr, "stereo_corresp_to_lonlatalt (sba_b200): %s\n", sba_last_error());
+        if (lonlatalt && err)
+            for (int i = 0; i < n_kp; ++i) { lonlatalt[3 * i] = lonlatalt[3 * i + 1] = lonlatalt[3 * i + 2] = NAN; err[i] = NAN; }
+    }
 }
 
 extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info)

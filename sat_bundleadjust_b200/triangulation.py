@@ -51,13 +51,16 @@ def stereo_corresp_to_xyz(rpc1, rpc2, pts1, pts2, out_crs=None):
     lib = _lib.load()
     s1, s2 = RPCStruct(rpc1, delta=0.1), RPCStruct(rpc2, delta=0.1)
     n = pts1.shape[0]
-    lib.stereo_corresp_to_lonlatalt.argtypes = (ndpointer(dtype=c_double, shape=(n, 3)), ndpointer(dtype=c_float, shape=(n, 1)),
-                                                ndpointer(dtype=c_float, shape=(n, 2)), ndpointer(dtype=c_float, shape=(n, 2)),
-                                                c_int, POINTER(RPCStruct), POINTER(RPCStruct))
+    # The package's own binding goes through the status-returning entry point: a missing device, an out-of-memory condition or
+    # any CUDA error raises SbaError instead of handing zero-filled points to the caller.  (The void symbol
+    # `stereo_corresp_to_lonlatalt` with the reference's exact signature stays exported for the reference's unmodified ctypes
+    # stub; it fills its outputs with NaN on failure.)
     lonlatalt = np.zeros((n, 3), dtype="float64")
     err = np.zeros((n, 1), dtype="float32")
-    lib.stereo_corresp_to_lonlatalt(lonlatalt, err, np.ascontiguousarray(pts1, dtype="float32"),
-                                    np.ascontiguousarray(pts2, dtype="float32"), n, byref(s1), byref(s2))
+    k1, k2 = np.ascontiguousarray(pts1, dtype="float32"), np.ascontiguousarray(pts2, dtype="float32")
+    _lib.check(lib.sba_stereo_corresp_to_lonlatalt(lonlatalt.ctypes.data_as(_lib.c_double_p), err.ctypes.data_as(_lib.c_float_p),
+                                                   k1.ctypes.data_as(_lib.c_float_p), k2.ctypes.data_as(_lib.c_float_p), n,
+                                                   byref(s1), byref(s2)))
     return lonlatalt, err
 
 
