@@ -53,6 +53,7 @@ WORKLOADS = {
     "cfg4s": (300, 100000, 0.02, "perspective", ["R", "T"],
               "BASELINE config 4 reduced: 300-view perspective BA, 1e5 tracks / ~6e5 observations per GPU (1800 x 1800 reduced system)"),
 }
+RPC_WORKLOAD = "rpc"         # BASELINE config 5: RPC refit + batched RPC projection / localisation / triangulation, 300 cameras
 LS = {"loss": "soft_l1", "f_scale": 1.0}
 L2_FLUSH_BYTES = 256 << 20      # > 126 MB L2
 
@@ -493,6 +494,130 @@ def run_b200_arm(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 5: the RPC side of the path (G7-G10): projection, localisation, triangulation, refit
+# ---------------------------------------------------------------------------------------------------
+def run_rpc_workload(args):
+    """`--workload rpc`: 300 cameras (the two reference test RPCs with jittered offsets), a 100 x 100 x 10 lon/lat/alt grid
+    per camera for projection / localisation, 1e5 matches per camera pair for triangulation, 10 x 10 x 10 samples per camera
+    for the refit.  --impl reference times the CPU side only: the reference's compiled C (oracle/_ref/disp_to_h.so) when it is
+    there, else the pinned C port, and the oracle's weighted_lsq, on bounded samples."""
+    import ctypes
+    import numpy as np
+    from oracle import rpc_ctypes, rpc_oracle, rpcfit_oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    G = np.load(os.path.join(ROOT, "tests", "golden", "rpc_golden.npz"))
+    F = np.load(os.path.join(ROOT, "tests", "golden", "rpcfit_golden.npz"))
+    n_cam, reps = 300, max(1, args.steps // 4)
+    rng = np.random.default_rng(0)
+    base = [G["rpc_a"], G["rpc_b"]]
+    tables = np.stack([base[j % 2].copy() for j in range(2 * n_cam)])
+    tables[:, 0] += rng.uniform(-5, 5, 2 * n_cam)         # row / col offsets jittered: 600 distinct cameras
+    tables[:, 1] += rng.uniform(-5, 5, 2 * n_cam)
+    ra = base[0]
+    gl = np.stack(np.meshgrid(np.linspace(-0.9, 0.9, 100), np.linspace(-0.9, 0.9, 100), np.linspace(-0.9, 0.9, 10), indexing="ij"), -1).reshape(-1, 3)
+    lon, lat, alt = ra[3] + gl[:, 0] * ra[8], ra[2] + gl[:, 1] * ra[7], ra[4] + gl[:, 2] * ra[9]
+    n = lon.size
+    # CPU side: reference C where it compiled, else the pinned port
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "disp_to_h.so"))
+    clib = rpc_ctypes.load_ref() if have_ref else rpc_ctypes.load_port()
+    kind = "reference" if have_ref else "port"
+    from tests_util_shim import rpc_from_array
+    ma, mb = rpc_from_array(base[0]), rpc_from_array(base[1])
+    ns = 20000                                              # bounded CPU samples
+    lla_s = np.stack([lon[:ns], lat[:ns], alt[:ns]], 1)
+    t0 = time.perf_counter()
+    cr = rpc_ctypes.ref_project(clib, ma, lla_s[:4000]) if have_ref else rpc_ctypes.port_project(clib, ma, lla_s)
+    n_proj = cr.shape[0]
+    t_proj = time.perf_counter() - t0
+    col_a, row_a = ma.projection(lon, lat, alt)
+    col_b, row_b = mb.projection(lon, lat, alt)
+    t0 = time.perf_counter()
+    _ = rpc_ctypes.triangulate(clib, ma, mb, np.stack([col_a[:ns], row_a[:ns]], 1), np.stack([col_b[:ns], row_b[:ns]], 1), 0.1, ref=have_ref)
+    t_tri = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    nfit = 6
+    for k in range(nfit):
+        rpcfit_oracle.weighted_lsq(F["case%d/target" % k], F["case%d/input_locs" % k])
+    t_fit = (time.perf_counter() - t0) / nfit
+    cpu = {"projection": n_proj / t_proj, "triangulation": ns / t_tri, "refit": 1.0 / t_fit}
+    if args.impl == "reference":
+        line = {"impl": "reference", "metric": "rpc_triangulated_matches_per_s", "value": cpu["triangulation"], "unit": "matches/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tri, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: RPC triangulation / projection / refit, CPU side on bounded samples"},
+                "cpu_baseline": {"value": cpu["triangulation"], "unit": "matches/s", "cores": 1, "kind": kind,
+                                 "sample": "%d matches through stereo_corresp_to_lonlatalt of %s" % (ns, "oracle/_ref/disp_to_h.so (the reference's C, compiled in place)" if have_ref else "the pinned C port"),
+                                 "projection_points_per_s": cpu["projection"], "refit_cameras_per_s": cpu["refit"]},
+                "e2e": {"value": cpu["triangulation"], "unit": "matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from sat_bundleadjust_b200 import _lib, ba_rpcfit
+    lib = _lib.load()
+    dp = _lib.dptr
+    ms = ctypes.c_double()
+
+    def thr(kind_id, a, b, c, d, delta, out_w):
+        out = np.empty(out_w * n)
+        _lib.check(lib.sba_rpc_throughput(kind_id, dp(tables), n_cam, dp(a), dp(b), dp(c), dp(d) if d is not None else None, n, delta, reps,
+                                          dp(out), ctypes.byref(ms)))
+        return ms.value, out
+    f64 = _lib.f64
+    ms_proj, o = thr(0, f64(lon), f64(lat), f64(alt), None, 1.0, 2)
+    last = rpc_from_array(tables[n_cam - 1])
+    assert np.abs(o[:n] - last.projection(lon, lat, alt)[0]).max() < 1e-6
+    ms_loc, o = thr(1, f64(col_a), f64(row_a), f64(alt), None, 1.0, 2)
+    ms_tri, o = thr(2, f64(col_a), f64(row_a), f64(col_b), f64(row_b), 0.1, 3)
+    # refit: 300 cameras x 1000 samples through the public batched call (host buffers in and out)
+    tg = np.stack([F["case%d/target" % (k % int(F["n_cases"]))] for k in range(n_cam)])
+    lc = np.stack([F["case%d/input_locs" % (k % int(F["n_cases"]))] for k in range(n_cam)])
+    ba_rpcfit.weighted_lsq_batch(tg[:4], lc[:4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ba_rpcfit.weighted_lsq_batch(tg, lc)
+    t_fit_gpu = time.perf_counter() - t0
+    # end to end through the host-pointer API (the reference-facing calls): projection of every camera's grid, host buffers
+    colo, rowo = np.empty(n), np.empty(n)
+    t0 = time.perf_counter()
+    for j in range(0, n_cam, 10):
+        _lib.check(lib.sba_rpc_projection(dp(tables[j]), dp(f64(lon)), dp(f64(lat)), dp(f64(alt)), n, dp(colo), dp(rowo)))
+    e2e_proj = (n_cam // 10) * n / (time.perf_counter() - t0)
+    f64_peak, f64_src = fp64_peak()
+    peak, peak_src = load_peaks()
+    pts = n_cam * n
+    # flop per point counted from the formulas: 4 cubics x (19 add + 36 mul) + normalisation / de-normalisation 3 x 2 + 2 x 2 + 2 div
+    flop_proj = 4 * 55 + 12
+    ops = {
+        "projection": {"value": pts / (ms_proj * 1e-3), "unit": "points/s", "ms": ms_proj, "cpu_baseline": cpu["projection"],
+                       "hbm_frac": 40 * pts / (ms_proj * 1e-3) / 1e9 / peak, "fp64_frac": flop_proj * pts / (ms_proj * 1e-3) / 1e12 / f64_peak},
+        "localization": {"value": pts / (ms_loc * 1e-3), "unit": "points/s", "ms": ms_loc},
+        "triangulation": {"value": pts / (ms_tri * 1e-3), "unit": "matches/s", "ms": ms_tri, "cpu_baseline": cpu["triangulation"]},
+        "refit": {"value": n_cam / t_fit_gpu, "unit": "cameras/s", "ms": 1e3 * t_fit_gpu, "cpu_baseline": cpu["refit"],
+                  "note": "wall clock of ba_rpcfit.weighted_lsq_batch, host buffers in and out, 1000 samples per camera"},
+    }
+    line = {"metric": "rpc_triangulated_matches_per_s", "value": ops["triangulation"]["value"], "unit": "matches/s", "n_gpus": 1,
+            "steps": reps, "warmup": 1, "ms_per_step": ms_tri, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: 300 cameras, 100 x 100 x 10 grid per camera (projection, localisation), 1e5 matches per pair "
+                                   "(triangulation), 1000 samples per camera (refit)", "n_cam": n_cam, "points_per_camera": int(n)},
+            "operations": ops,
+            "roofline": {"kernel": "k_rpc_projection", "bound": "hbm", "achieved": 40 * pts / (ms_proj * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ops["projection"]["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                         "fp64": {"flop_per_point": flop_proj, "achieved_tflops": flop_proj * pts / (ms_proj * 1e-3) / 1e12, "peak_tflops": f64_peak,
+                                  "frac": ops["projection"]["fp64_frac"], "peak_source": f64_src}},
+            "cpu_baseline": {"value": cpu["triangulation"], "unit": "matches/s", "cores": 1, "kind": kind,
+                             "sample": "%d matches (triangulation), %d points (projection), %d refits on one core" % (ns, n_proj, nfit)},
+            "e2e": {"value": e2e_proj, "unit": "points/s", "h2d_bytes_per_step": 24 * int(n), "d2h_bytes_per_step": 16 * int(n),
+                    "call": "sba_rpc_projection (host buffers), 30 cameras x 1e5 points"},
+            "gpu_launches": int(3 * n_cam * (reps + 1) + n_cam // 10 + 2)}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     # stdout carries exactly one JSON line: everything else that libraries print there (e.g. NCCL's version banner)
     # is sent to stderr by swapping the file descriptors for the duration of the run
@@ -504,12 +629,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="1m", choices=sorted(WORKLOADS) + [RPC_WORKLOAD])
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 line reported under \"secondary\" (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
-    rc = run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args)
+    if args.workload == RPC_WORKLOAD:
+        rc = run_rpc_workload(args)
+    else:
+        rc = run_reference_arm(args) if args.impl == "reference" else run_b200_arm(args)
     sys.stdout.flush()
     return rc
 

@@ -188,6 +188,10 @@ int sba_rpc_projection_ecef(const double *rpc, const double *xyz, int64_t n, dou
 /* c/rpc.c:378-439 eval_rpc (iterative) / rpcm localization: (col,row,alt) -> (lon,lat); delta = first probe */
 int sba_rpc_localization(const double *rpc, const double *col, const double *row, const double *alt, int64_t n,
                          double delta, double *lon, double *lat);
+/* Measurement only (bench.py --workload rpc): device-resident time per pass of the batched RPC kernels over n_cam cameras x n
+ * points (kind 0 projection, 1 localisation, 2 triangulation between tables 2j and 2j+1), inputs uploaded once. */
+int sba_rpc_throughput(int32_t kind, const double *tables_n_cam_x_90, int32_t n_cam, const double *a, const double *b,
+                       const double *c, const double *d, int64_t n, double delta, int32_t reps, double *out, double *ms);
 
 /* The reference's one native entry point, same signature and struct layout (c/disp_to_h.c:40-42,
  * c/rpc.h:14-32): two-view RPC triangulation of n_kp matches.  rpc_a / rpc_b point to `struct rpc`

@@ -8,6 +8,7 @@
 // rounding; only the execution is different: coefficients staged once per block in shared memory,
 // one match per thread, arrays of structure-of-arrays inputs read coalesced.
 #include "sba_internal.cuh"
+#include <vector>
 
 namespace sba {
 
@@ -290,6 +291,59 @@ extern "C" void stereo_corresp_to_lonlatalt(double* lonlatalt, float* err, float
         if (lonlatalt && err)
             for (int i = 0; i < n_kp; ++i) { lonlatalt[3 * i] = lonlatalt[3 * i + 1] = lonlatalt[3 * i + 2] = NAN; err[i] = NAN; }
     }
+}
+
+// Measurement entry point (bench.py --workload rpc): device-resident throughput of the batched RPC kernels over n_cam cameras
+// x n points, inputs uploaded once, `reps` timed repetitions of one launch per camera (CUDA events).
+//   kind 0: projection  (a, b, c) = (lon, lat, alt) -> (col, row)
+//   kind 1: localisation (a, b, c) = (col, row, alt) -> (lon, lat)
+//   kind 2: triangulation of n matches between tables 2j and 2j+1 (kp_a = (a, b), kp_b = (c, d) as doubles, cast to float)
+// out (2n or 3n doubles, may be NULL) receives the result of the last camera / pair for a spot check.
+extern "C" int sba_rpc_throughput(int32_t kind, const double* tables, int32_t n_cam, const double* a, const double* b,
+                                  const double* c, const double* d, int64_t n, double delta, int32_t reps, double* out, double* ms)
+{
+    if (!tables || !a || !b || !c || n < 1 || n_cam < 1 || reps < 1 || !ms || kind < 0 || kind > 2) { set_error("bad argument"); return SBA_E_INVALID; }
+    SBA_TRY(require_device());
+    const int n_str = kind == 2 ? 2 * n_cam : n_cam;
+    std::vector<double> hs((size_t)n_str * R_STRUCT_DOUBLES);
+    for (int j = 0; j < n_str; ++j) table_to_struct(tables + (size_t)j * 90, delta, hs.data() + (size_t)j * R_STRUCT_DOUBLES);
+    DevBuf ds, in, o, kf, ef;
+    SBA_TRY(ds.alloc(hs.size() * sizeof(double))); SBA_TRY(in.alloc(4 * n * sizeof(double))); SBA_TRY(o.alloc(3 * n * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(ds.p, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>(), a, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + n, b, n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + 2 * n, c, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (kind == 2) {
+        if (!d) { set_error("bad argument"); return SBA_E_INVALID; }
+        std::vector<float> kp(4 * (size_t)n);
+        for (int64_t i = 0; i < n; ++i) { kp[2 * i] = (float)a[i]; kp[2 * i + 1] = (float)b[i]; kp[2 * n + 2 * i] = (float)c[i]; kp[2 * n + 2 * i + 1] = (float)d[i]; }
+        SBA_TRY(kf.alloc(kp.size() * sizeof(float))); SBA_TRY(ef.alloc(n * sizeof(float)));
+        SBA_CUDA(cudaMemcpy(kf.p, kp.data(), kp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    cudaEvent_t e0, e1;
+    SBA_CUDA(cudaEventCreate(&e0)); SBA_CUDA(cudaEventCreate(&e1));
+    auto pass = [&]() {
+        for (int j = 0; j < n_cam; ++j) {
+            const double* sj = ds.as<double>() + (size_t)(kind == 2 ? 2 * j : j) * R_STRUCT_DOUBLES;
+            double* x = in.as<double>();
+            if (kind == 0) k_rpc_projection<<<grid_n(n, 256), 256>>>(sj, x, x + n, x + 2 * n, n, o.as<double>(), o.as<double>() + n);
+            else if (kind == 1) k_rpc_localization<<<grid_n(n, 256), 256>>>(sj, x, x + n, x + 2 * n, n, o.as<double>(), o.as<double>() + n);
+            else k_rpc_triangulate<<<grid_n(n, 128), 128>>>(sj, sj + R_STRUCT_DOUBLES, kf.as<float2>(), kf.as<float2>() + n, n, o.as<double>(), ef.as<float>());
+        }
+    };
+    pass();                                     // warm-up
+    SBA_CUDA(cudaDeviceSynchronize());
+    SBA_CUDA(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) pass();
+    SBA_CUDA(cudaEventRecord(e1));
+    SBA_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    SBA_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    SBA_CUDA(cudaGetLastError());
+    *ms = (double)t / reps;
+    if (out) SBA_CUDA(cudaMemcpy(out, o.p, (kind == 2 ? 3 : 2) * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return SBA_OK;
 }
 
 extern "C" int sba_cholesky_solve(double* A, double* b, int32_t n, int32_t* info)

@@ -238,7 +238,11 @@ k_rpcfit(const double* __restrict__ target, const double* __restrict__ locs, int
         rmse_prev = rmse;
         rmse = sqrt(0.5 * (sq[0] / N + sq[1] / N));
         n_iter = pass;
-        if (pass > 0 && fabs(rmse_prev - rmse) < tol) break;
+        // At least two re-weighted passes (when max_iter allows): the first, unregularised system is numerically singular
+        // (condition number ~4e16), so the RMSE the first pass is compared with is arbitrary -- the reference's own inaccurate
+        // inverse makes it run 2-3 passes -- and the fitted function still moves by pixels BETWEEN the samples from pass 1 to
+        // pass 2 (by < 5e-2 px afterwards; tests/test_rpcfit.py measures both on a held-out grid).
+        if (pass >= (max_iter < 2 ? max_iter : 2) && pass > 0 && fabs(rmse_prev - rmse) < tol) break;
     }
     if (tid < 90) {
         double v;

@@ -62,6 +62,58 @@ def test_reference_fit_is_ill_conditioned():
     assert np.abs(a - b).max() > 1e-6 * np.abs(a).max()
 
 
+def test_reference_fit_noise_on_a_held_out_grid():
+    """
+    How much "the same RPC" can mean.  The reference's fit against the same algorithm, same number of passes, with accurate
+    linear solves (oracle.weighted_lsq_accurate): the fitted FUNCTIONS differ by 4e-4 .. 5e-2 px on a dense held-out grid.  That
+    is the reference's own numerical noise (np.linalg.inv at condition numbers 4e16 / 6e11), so no other implementation can be
+    closer to it than this; the GPU test below uses it as its bar.
+    """
+    worst = 0.0
+    for k in range(NCASES):
+        t, x = F["case%d/target" % k], F["case%d/input_locs" % k]
+        ref, n_it, _ = rpcfit_oracle.weighted_lsq(t, x, return_iters=True)
+        acc = rpcfit_oracle.weighted_lsq_accurate(t, x, n_it)
+        g = rpcfit_oracle.held_out_grid(x)
+        d = np.abs(np.stack(acc.projection(g[:, 0], g[:, 1], g[:, 2]), 1) - np.stack(ref.projection(g[:, 0], g[:, 1], g[:, 2]), 1)).max()
+        worst = max(worst, d)
+    assert 1e-3 < worst < 0.1, worst
+
+
+@pytest.mark.gpu
+def test_gpu_fit_function_parity_on_a_held_out_grid(built):
+    """
+    GPU-fitted RPC against the reference-fitted RPC as FUNCTIONS (what "same RPC out" means downstream), on a dense held-out
+    lon/lat/alt grid inside the sample hull:
+      * default stopping rule: within the reference's own numerical noise (see the test above): measured 4e-4 .. 4.9e-2 px, case
+        by case the same figures as the accurate CPU restatement shows against the reference; bar 6e-2 px;
+      * pass count forced equal to the reference's and accurate arithmetic on both sides (GPU vs oracle.weighted_lsq_accurate):
+        the two well-conditioned implementations of the same algorithm agree to 1e-3 px (measured); bar 2e-3 px.
+    """
+    from sat_bundleadjust_b200 import ba_rpcfit
+    targets = np.stack([F["case%d/target" % k] for k in range(NCASES)])
+    locs = np.stack([F["case%d/input_locs" % k] for k in range(NCASES)])
+    models, iters, _ = ba_rpcfit.weighted_lsq_batch(targets, locs)
+    d_ref, d_acc = [], []
+    for k in range(NCASES):
+        g = rpcfit_oracle.held_out_grid(locs[k])
+        ref = util.rpc_from_array(F["case%d/ref_rpc" % k])
+        want = np.stack(ref.projection(g[:, 0], g[:, 1], g[:, 2]), 1)
+        got = np.stack(models[k].projection(g[:, 0], g[:, 1], g[:, 2]), 1)
+        d_ref.append(np.abs(got - want).max())
+        _, n_it, _ = rpcfit_oracle.weighted_lsq(targets[k], locs[k], return_iters=True)
+        forced, it_f, _ = ba_rpcfit.weighted_lsq_batch(targets[k][None], locs[k][None], tol=0.0, max_iter=n_it)
+        assert it_f[0] == n_it
+        acc = rpcfit_oracle.weighted_lsq_accurate(targets[k], locs[k], n_it)
+        a = np.stack(acc.projection(g[:, 0], g[:, 1], g[:, 2]), 1)
+        f = np.stack(forced[0].projection(g[:, 0], g[:, 1], g[:, 2]), 1)
+        d_acc.append(np.abs(f - a).max())
+    print("held-out grid, GPU vs reference fit (px):", ["%.1e" % v for v in d_ref])
+    print("held-out grid, GPU vs accurate restatement, equal passes (px):", ["%.1e" % v for v in d_acc])
+    assert max(d_ref) < 6e-2
+    assert max(d_acc) < 2e-3
+
+
 @pytest.mark.gpu
 def test_gpu_weighted_lsq_batch_vs_reference_golden(built):
     from sat_bundleadjust_b200 import ba_rpcfit
