@@ -50,6 +50,9 @@ WORKLOADS = {
               "BASELINE config 3 shard: 50-view affine BA, 1.25e5 tracks / ~6e5 observations per GPU, soft_l1, R+T"),
     "cfg3full": (50, 1000000, 0.1, "perspective", ["R", "T"],
                  "BASELINE config 3 whole: 50-view perspective BA, 1e6 tracks / ~5e6 observations per GPU, soft_l1, R+T"),
+    "cfg4": (300, 625000, 0.02, "perspective", ["R", "T"],
+             "BASELINE config 4: 300-view multi-date perspective BA, 6.25e5 tracks / ~3.7e6 observations per GPU (5e6 tracks / ~3e7 observations "
+             "on 8 GPUs), soft_l1, R+T, matrix-free PCG on the 1800-unknown reduced camera system"),
     "cfg4s": (300, 100000, 0.02, "perspective", ["R", "T"],
               "BASELINE config 4 reduced: 300-view perspective BA, 1e5 tracks / ~6e5 observations per GPU (1800 x 1800 reduced system)"),
 }
@@ -144,6 +147,9 @@ class ClockSampler:
 def build_problem(workload, world):
     from sat_bundleadjust_b200 import synth
     n_cam, tracks, p_vis, model, corr, _ = WORKLOADS[workload]
+    if n_cam >= 100 and tracks * world > 200000:      # time-series scale: never form the dense (2M x N) correspondence matrix
+        scene = synth.make_scene_sparse(n_cam=n_cam, n_tracks=tracks * world, p_vis=p_vis, cam_model=model, seed=0)
+        return synth.SparseParams(scene, corr)
     scene = synth.make_scene(n_cam=n_cam, n_tracks=tracks * world, p_vis=p_vis, cam_model=model, seed=0)
     return synth.scene_to_params(scene, corr)
 

@@ -296,10 +296,10 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
 #pragma unroll
                 for (int r = 0; r < NC; ++r) {
 #pragma unroll
-                    for (int c = 0; c <= r; ++c) { acc[q] += e.Jc[r] * e.Jc[c] + e.Jc[NC + r] * e.Jc[NC + c]; ++q; }
+                    for (int c = 0; c <= r; ++c) { acc[q] = fma(e.Jc[NC + r], e.Jc[NC + c], fma(e.Jc[r], e.Jc[c], acc[q])); ++q; }
                 }
 #pragma unroll
-                for (int r = 0; r < NC; ++r) acc[NU + r] += e.Jc[r] * e.f0 + e.Jc[NC + r] * e.f1;
+                for (int r = 0; r < NC; ++r) acc[NU + r] = fma(e.Jc[NC + r], e.f1, fma(e.Jc[r], e.f0, acc[NU + r]));
             }
             // per-track sums of the 9 point values: one lane per (track, value)
 #pragma unroll
@@ -545,7 +545,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
             double y1 = e.Jp[3] * t1p[0] + e.Jp[4] * t1p[1] + e.Jp[5] * t1p[2];
 #pragma unroll
             for (int q = 0; q < NC; ++q) { y0 += e.Jc[q] * t1c[q]; y1 += e.Jc[NC + q] * t1c[q]; }
-            acc[3] += y0 * y0 + y1 * y1;
+            acc[3] = fma(y1, y1, fma(y0, y0, acc[3]));
         }
     }
     // max |g| of this rank (non-negative doubles order like their bit patterns; the slot is zeroed by the host)
@@ -685,7 +685,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                         const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
                         const double z0 = w0 * Gm[0], z1 = w0 * Gm[1] + w1 * Gm[2], z2 = w0 * Gm[3] + w1 * Gm[4] + w2 * Gm[5];
                         z[3 * r] = z0; z[3 * r + 1] = z1; z[3 * r + 2] = z2;
-                        if (pass == 0) accR[r] += z0 * qv[0] + z1 * qv[1] + z2 * qv[2];
+                        if (pass == 0) accR[r] = fma(z2, qv[2], fma(z1, qv[1], fma(z0, qv[0], accR[r])));
                     }
                 }
                 __syncwarp();
@@ -703,7 +703,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                             const double b0 = zb[3 * s], b1 = zb[3 * s + 1], b2 = zb[3 * s + 2];
 #pragma unroll
                             for (int r = 0; r < PT_RC; ++r)
-                                acc[q][r * NC + s] += Ar[3 * r] * b0 + Ar[3 * r + 1] * b1 + Ar[3 * r + 2] * b2;
+                                acc[q][r * NC + s] = fma(Ar[3 * r + 2], b2, fma(Ar[3 * r + 1], b1, fma(Ar[3 * r], b0, acc[q][r * NC + s])));      // three chained DFMA
                         }
                     }
                 }
@@ -948,8 +948,8 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
                 double jt1 = e.Jp[3] * tp0 + e.Jp[4] * tp1 + e.Jp[5] * tp2;
 #pragma unroll
                 for (int q = 0; q < NC; ++q) { jt0 += e.Jc[q] * t1c[q]; jt1 += e.Jc[NC + q] * t1c[q]; }
-                acc[2] += jt0 * jd0 + jt1 * jd1;
-                acc[3] += jd0 * jd0 + jd1 * jd1;
+                acc[2] = fma(jt1, jd1, fma(jt0, jd0, acc[2]));
+                acc[3] = fma(jd1, jd1, fma(jd0, jd0, acc[3]));
             }
             __syncwarp();
         }

@@ -165,3 +165,78 @@ def scene_to_params(scene, correction_params=("R",), n_cam_fix=0, n_pts_fix=0, r
     pairs = [(a, b) for a in range(scene.n_cam) for b in range(a + 1, scene.n_cam)]
     return params_cls(scene.correspondence_matrix(), scene.pts3d_init, list(scene.cameras_init), scene.cam_model,
                       pairs, list(scene.camera_centers), d)
+
+
+class SparseParams:
+    """
+    The fields of `BundleAdjustmentParameters` that the solver reads, built WITHOUT the dense
+    (2M x N) correspondence matrix: at time-series scale (BASELINE config 4: 300 views x 5e6 tracks) that matrix alone
+    is 24 GB.  Same observation order (by track, camera ascending), same parameter vector layout
+    (bundle_adjust/ba_params.py:138-173) -- test_sparse_scene_matches_dense_packing pins it against the class.
+    """
+
+    def __init__(self, scene, correction_params=("R", "T"), n_cam_fix=0, n_pts_fix=0):
+        self.cam_model = scene.cam_model
+        self.cameras, self.camera_centers = list(scene.cameras_init), list(scene.camera_centers)
+        self.cam_params_to_optimize = list(correction_params)
+        self.n_cam, self.n_pts = scene.n_cam, scene.n_pts
+        self.n_cam_fix, self.n_pts_fix = n_cam_fix, n_pts_fix
+        self.pts3d = np.asarray(scene.pts3d_init)
+        self.pts_ind, self.cam_ind, self.pts2d = scene.pts_ind, scene.cam_ind, scene.pts2d
+        self.n_obs = int(self.pts_ind.size)
+        self.cam_params = np.array([load_cam_params_from_camera(c, ctr, self.cam_model)
+                                    for c, ctr in zip(self.cameras, self.camera_centers)])
+        nT = 2 if self.cam_model == "affine" else 3
+        self.n_params = 3 + (nT if "T" in correction_params else 0) if "R" in correction_params else 0
+        if "K" in correction_params:
+            raise NotImplementedError("SparseParams covers the R / R+T corrections of the large synthetic configs")
+        self.params_opt = np.hstack((self.cam_params[:, : self.n_params].ravel(), self.pts3d.astype(np.float64).ravel()))
+        self.pts2d_w = np.ones(self.n_obs)
+
+
+def make_scene_sparse(n_cam=300, n_tracks=100000, p_vis=0.02, cam_model="perspective", seed=0, box_m=(10e3, 10e3, 500.0),
+                      noise_px=0.5, outlier_frac=0.02, outlier_px=20.0, pts_sigma_m=1.0, ang_sigma=1e-6, min_obs=2):
+    """
+    `make_scene` for many cameras: the visibility is drawn sparsely (geometric gaps between the observed (track, camera)
+    cells of the row-major N x M table), so memory and time are O(observations), not O(N x M).  Not bit-identical to
+    make_scene for the same seed (different random draws), same statistics.
+    """
+    if cam_model not in ("perspective", "affine"):
+        raise ValueError("matrix cameras only")
+    rng = np.random.default_rng(seed)
+    basis = enu_basis(SCENE_LAT, SCENE_LON)
+    centre = np.array(geo_utils.latlon_to_ecef_custom(SCENE_LAT, SCENE_LON, SCENE_ALT))
+    cams, centers = [], []
+    for _ in range(n_cam):
+        P, C = make_perspective_camera(rng, centre, basis)
+        if cam_model == "affine":
+            P = affine_expansion(P, centre)
+        cams.append(P)
+        centers.append(C)
+    total = n_tracks * n_cam
+    n_draw = int(total * p_vis * 1.05 + 10 * np.sqrt(total * p_vis) + 100)
+    flat = np.cumsum(rng.geometric(p_vis, size=n_draw)) - 1
+    flat = flat[flat < total]
+    trk, cam_ind = np.divmod(flat, n_cam)
+    counts = np.bincount(trk, minlength=n_tracks)
+    keep_trk = counts >= min_obs
+    new_id = np.cumsum(keep_trk) - 1
+    sel = keep_trk[trk]
+    pts_ind, cam_ind = new_id[trk[sel]].astype(np.int64), cam_ind[sel].astype(np.int64)
+    n_pts = int(keep_trk.sum())
+    enu = rng.uniform(-0.5, 0.5, size=(n_pts, 3)) * np.array(box_m)
+    pts = centre + enu[:, :1] * basis[0] + enu[:, 1:2] * basis[1] + enu[:, 2:3] * basis[2]
+    pts2d = np.empty((pts_ind.size, 2))
+    order = np.argsort(cam_ind, kind="stable")
+    bounds = np.searchsorted(cam_ind[order], np.arange(n_cam + 1))
+    for j in range(n_cam):
+        o = order[bounds[j]: bounds[j + 1]]
+        pts2d[o] = cam_utils.apply_projection_matrix(cams[j], pts[pts_ind[o]])
+    pts2d += rng.normal(0.0, noise_px, size=pts2d.shape)
+    bad = rng.random(pts_ind.size) < outlier_frac
+    pts2d[bad] += rng.normal(0.0, outlier_px, size=(int(bad.sum()), 2))
+    pts_init = (pts + rng.normal(0.0, pts_sigma_m, size=pts.shape)).astype(np.float32)
+    cams_init = [perturb_camera(P, cam_model, rng.normal(0.0, ang_sigma, size=3)) for P in cams]
+    return Scene(cam_model=cam_model, cameras=cams, cameras_init=cams_init, camera_centers=centers, pts3d_true=pts,
+                 pts3d_init=pts_init, pts_ind=pts_ind, cam_ind=cam_ind, pts2d=pts2d, seed=seed,
+                 meta=dict(n_cam=n_cam, n_tracks=n_tracks, p_vis=p_vis, sparse=True))

@@ -463,3 +463,15 @@ def test_pattern_layout_rejects(built):
     # cameras not ascending inside a track / a track longer than 32 observations -> generic engine
     assert _pattern_layout([1, 0], [0, 0], 2, 1) is None
     assert _pattern_layout(np.arange(40), np.zeros(40, int), 40, 1) is None
+
+
+def test_sparse_scene_matches_dense_packing():
+    """synth.SparseParams (no dense correspondence matrix, used for the time-series scale configs) packs exactly like the class."""
+    sc = synth.make_scene_sparse(n_cam=12, n_tracks=500, p_vis=0.3, seed=2)
+    q = synth.scene_to_params(sc, ["R", "T"])
+    r = synth.SparseParams(sc, ["R", "T"])
+    for k in ("pts_ind", "cam_ind", "pts2d", "params_opt", "cam_params", "pts2d_w"):
+        assert np.array_equal(getattr(q, k), getattr(r, k)), k
+    assert (q.n_params, q.n_obs, q.n_cam, q.n_pts) == (r.n_params, r.n_obs, r.n_cam, r.n_pts)
+    same = r.pts_ind[1:] == r.pts_ind[:-1]
+    assert np.all(np.diff(r.pts_ind) >= 0) and np.all(r.cam_ind[1:][same] > r.cam_ind[:-1][same])

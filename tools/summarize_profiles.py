@@ -90,8 +90,9 @@ def full_table_r02(rep, out_csv):
            ("fp64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
            ("issue active %", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("warp instr", "smsp__inst_executed.sum"),
            ("L1 hit %", "l1tex__t_sector_hit_rate.pct"), ("L2 hit %", "lts__t_sector_hit_rate.pct")]
-    fl = ["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
-          "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+    # thread-level FP64 instructions per elapsed cycle (summed over the SMSPs) x elapsed cycles = executed FP64 operations
+    fl = ["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+          "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"]
     seen, table = set(), []
     for r in rows[2:]:
         name = short(r[col["Kernel Name"]])
@@ -100,7 +101,7 @@ def full_table_r02(rep, out_csv):
         seen.add(name)
         vals = [r[col[m]] if m in col else "" for _, m in sel]
         try:
-            gflop = (2 * float(r[col[fl[0]]]) + float(r[col[fl[1]]]) + float(r[col[fl[2]]])) / 1e9
+            gflop = (2 * float(r[col[fl[0]]]) + float(r[col[fl[1]]]) + float(r[col[fl[2]]])) * float(r[col["smsp__cycles_elapsed.avg"]]) / 1e9
         except (KeyError, ValueError):
             gflop = ""
         st = sorted(((float(r[col[s]] or 0), s[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for s in stalls),
