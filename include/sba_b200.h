@@ -201,6 +201,19 @@ void stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, float *kp_a, flo
 int sba_stereo_corresp_to_lonlatalt(double *lonlatalt, float *err, const float *kp_a, const float *kp_b, int64_t n_kp,
                                     const void *rpc_a, const void *rpc_b);
 
+/* Initial 3-D points of the feature tracks, replaces the pair loop of ft_triangulate.init_pts3d
+ * (bundle_adjust/feature_tracks/ft_triangulate.py:57-127): every track x every pair of `pairs` (in list order) whose two
+ * cameras see the track is triangulated -- cv2.triangulatePoints' DLT for 3x4 matrices (:18-34), the two-view RPC
+ * triangulation + geodetic -> ECEF for RPCs (:37-54) -- and averaged with the reference's float32 running mean, all in
+ * ONE launch.  Tracks in CSR form: observations of track t are track_ptr[t] .. track_ptr[t+1]-1, cameras ascending.
+ * cams: (n_cam, 12) row-major matrices, or (n_cam, 181) `struct rpc` (c/rpc.h:14-32) for SBA_MODEL_RPC.
+ * pts3d_out: (n_tracks, 3) float32; tracks without a suitable pair are zero, like in the reference.  Host pointers. */
+int sba_init_pts3d(int32_t cam_model, const double *cams, int32_t n_cam, const int64_t *track_ptr, const int32_t *cam_idx,
+                   const double *pts2d, int64_t n_tracks, const int32_t *pairs_n_x_2, int32_t n_pairs, float *pts3d_out);
+/* ft_triangulate.linear_triangulation_multiple_pts (:18-34): n matches between two 3x4 matrices -> (n,3) doubles. */
+int sba_linear_triangulation(const double *P1, const double *P2, const double *pts1_n_x_2, const double *pts2_n_x_2, int64_t n,
+                             double *pts3d_out);
+
 /* Batched RPC refit, replaces ba_rpcfit.weighted_lsq (bundle_adjust/ba_rpcfit.py:88-153) for n_cam cameras at once:
  * target (n_cam, n_samples, 2) = (col,row), input_locs (n_cam, n_samples, 3) = (lon,lat,alt) -> rpc_out (n_cam, 90)
  * in the table layout above; h = ridge (1e-3), tol = RMSE change that stops the re-weighting (1e-2 px), max_iter (20).

@@ -67,6 +67,7 @@ EXPORTED_SYMBOLS = [
     "sba_rpc_localization", "sba_rpc_throughput", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",
     "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import", "sba_comm_try_reuse", "sba_solve_errors_device",
+    "sba_init_pts3d", "sba_linear_triangulation",
 ]
 
 _lib = None
@@ -113,6 +114,9 @@ def load():
     lib.sba_rpcfit_weighted_lsq.argtypes = [c_double_p, c_double_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
                                             ctypes.c_double, ctypes.c_int32, c_double_p, ctypes.POINTER(ctypes.c_int32),
                                             c_double_p]
+    lib.sba_init_pts3d.argtypes = [ctypes.c_int32, c_double_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
+                                   c_double_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, c_float_p]
+    lib.sba_linear_triangulation.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p]
     _lib = lib
     return lib
 

@@ -114,6 +114,174 @@ k_rpc_localization(const double* __restrict__ rs, const double* __restrict__ col
         s_localize(r, col[i], row[i], alt[i], lon[i], lat[i]);
 }
 
+// ---- initial 3-D points of the feature tracks (feature_tracks/ft_triangulate.py:18-127) ---------------------------------
+// Two-view RPC triangulation of one match, c/rpc.c:480-514 + c/disp_to_h.c:50-64, result in ECEF metres
+// (ft_triangulate.py:51-53 -> geo_utils.py:218-233).  ra / rb may live in global memory.
+__device__ __forceinline__ void rpc_triangulate_one(const double* ra, const double* rb, double xa, double ya, double xb, double yb,
+                                                    double& lon, double& lat, double& h, double& e)
+{
+    h = 0.0; e = 0.0;
+    for (int t = 0; t < 100; ++t) {
+        double lo, la, px, py, qx, qy;
+        s_localize(ra, xa, ya, h, lo, la);
+        s_project(rb, lo, la, h, px, py);
+        s_localize(ra, xa, ya, h + 1.0, lo, la);
+        s_project(rb, lo, la, h + 1.0, qx, qy);
+        const double dx = qx - px, dy = qy - py, ex = xb - px, ey = yb - py;
+        const double lambda = (dx * ex + dy * ey) / (dx * dx + dy * dy);
+        const double zx = px + lambda * dx, zy = py + lambda * dy;
+        e = hypot(zx - xb, zy - yb);
+        h += lambda;
+        if (fabs(lambda) < 0.00001) break;
+    }
+    s_localize(ra, xa, ya, h, lon, lat);
+}
+
+__device__ __forceinline__ void geodetic_to_ecef(double lat, double lon, double alt, double& x, double& y, double& z)
+{
+    const double phi = lat * (3.141592653589793 / 180.0), lam = lon * (3.141592653589793 / 180.0);
+    const double f = 1 / 298.257223563, e2 = 1 - (1 - f) * (1 - f);
+    double s, c, sl, cl;
+    sincos(phi, &s, &c);
+    sincos(lam, &sl, &cl);
+    const double nu = 6378137.0 / sqrt(1 - e2 * s * s);
+    x = (nu + alt) * c * cl;
+    y = (nu + alt) * c * sl;
+    z = (nu * (1 - e2) + alt) * s;
+}
+
+// Linear (DLT) triangulation of one match with two 3x4 matrices: the unit homogeneous point minimising |A X|, A = the four
+// equations x P[2] - P[0], y P[2] - P[1] of both views -- what cv2.triangulatePoints computes (ft_triangulate.py:18-34).
+// Right singular vector of the smallest singular value by one-sided (Hestenes) Jacobi rotations on the columns of A: the
+// columns differ by 1e7 in magnitude (X, Y, Z ~ 6e6 m next to 1), and the Jacobi iteration keeps the small singular pair
+// to full relative accuracy where a bidiagonalising SVD loses millimetres.
+__device__ __forceinline__ void dlt_triangulate_one(const double* P1, const double* P2, double x1, double y1, double x2, double y2,
+                                                    double& X, double& Y, double& Z)
+{
+    double U[4][4], V[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        U[0][c] = x1 * P1[8 + c] - P1[c];
+        U[1][c] = y1 * P1[8 + c] - P1[4 + c];
+        U[2][c] = x2 * P2[8 + c] - P2[c];
+        U[3][c] = y2 * P2[8 + c] - P2[4 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) V[r][c] = r == c ? 1.0 : 0.0;
+    }
+    const double eps = 2.220446049250313e-16;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { alpha += U[r][p] * U[r][p]; beta += U[r][q] * U[r][q]; gamma += U[r][p] * U[r][q]; }
+                if (fabs(gamma) > eps * sqrt(alpha * beta)) {
+                    rotated = true;
+                    const double zeta = (beta - alpha) / (2.0 * gamma);
+                    const double t = zeta == 0.0 ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double up = U[r][p], uq = U[r][q], vp = V[r][p], vq = V[r][q];
+                        U[r][p] = c * up - s * uq; U[r][q] = s * up + c * uq;
+                        V[r][p] = c * vp - s * vq; V[r][q] = s * vp + c * vq;
+                    }
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    double best = 0.0, w = 1.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double nrm = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) nrm += U[r][c] * U[r][c];
+        if (c == 0 || nrm < best) { best = nrm; X = V[0][c]; Y = V[1][c]; Z = V[2][c]; w = V[3][c]; }
+    }
+    X /= w; Y /= w; Z /= w;
+}
+
+__global__ void __launch_bounds__(128)
+k_dlt_pairs(const double* __restrict__ P, const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ out)
+{
+    __shared__ double sP[24];
+    if (threadIdx.x < 24) sP[threadIdx.x] = P[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dlt_triangulate_one(sP, sP + 12, a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+// init_pts3d (ft_triangulate.py:57-127) in one launch: one thread per track walks the list of triangulation pairs IN ORDER,
+// triangulates every pair both of whose cameras see the track, and keeps the reference's float32 running mean
+// (avg = ((count - 1) avg + new) / count, every operation rounded to float32, :77-81) -- the float32 quantisation of the
+// start points (~0.5 m at ECEF magnitude) is part of the reference's input to bundle adjustment.  The lanes of a warp
+// first advance to their next matching pair (cheap bit tests), then triangulate together (the expensive part converged).
+// Observations of a track are stored with ascending cameras, one per camera, so the observation of camera c is found
+// by a population count of the track's camera bit mask below c.
+constexpr int TRI_MASK_WORDS = 16;                       // up to 1024 cameras
+__global__ void __launch_bounds__(128)
+k_init_pts3d(int rpc_model, const double* __restrict__ cams, int n_cam, const long long* __restrict__ track_ptr,
+             const int* __restrict__ cam_idx, const double* __restrict__ pts2d, long long n_tracks,
+             const int2* __restrict__ pairs, int n_pairs, float* __restrict__ out)
+{
+    const int cam_stride = rpc_model ? R_STRUCT_DOUBLES : 12;
+    for (long long t0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; t0 < n_tracks; t0 += (long long)gridDim.x * blockDim.x) {
+        const long long t = t0 + (threadIdx.x & 31);
+        const bool live = t < n_tracks;
+        unsigned long long m[TRI_MASK_WORDS];
+#pragma unroll
+        for (int k = 0; k < TRI_MASK_WORDS; ++k) m[k] = 0ull;
+        long long o0 = 0;
+        if (live) {
+            o0 = track_ptr[t];
+            const long long o1 = track_ptr[t + 1];
+            for (long long o = o0; o < o1; ++o) { const int c = cam_idx[o]; m[c >> 6] |= 1ull << (c & 63); }
+        }
+        float ax = 0.f, ay = 0.f, az = 0.f, cnt = 0.f;
+        int q = live ? 0 : n_pairs;
+        while (true) {
+            int ci = -1, cj = -1;
+            for (; q < n_pairs; ++q) {
+                const int2 pr = pairs[q];
+                if (pr.x >= 0 && pr.y >= 0 && pr.x < n_cam && pr.y < n_cam && ((m[pr.x >> 6] >> (pr.x & 63)) & 1ull) &&
+                    ((m[pr.y >> 6] >> (pr.y & 63)) & 1ull)) { ci = pr.x; cj = pr.y; ++q; break; }
+            }
+            if (__ballot_sync(0xffffffffu, ci >= 0) == 0u) break;
+            if (ci >= 0) {
+                int pi = 0, pj = 0;
+                for (int k = 0; k < TRI_MASK_WORDS; ++k) {
+                    if (k < (ci >> 6)) pi += __popcll(m[k]);
+                    if (k < (cj >> 6)) pj += __popcll(m[k]);
+                }
+                pi += __popcll(m[ci >> 6] & ((1ull << (ci & 63)) - 1ull));
+                pj += __popcll(m[cj >> 6] & ((1ull << (cj & 63)) - 1ull));
+                const double xi = pts2d[2 * (o0 + pi)], yi = pts2d[2 * (o0 + pi) + 1];
+                const double xj = pts2d[2 * (o0 + pj)], yj = pts2d[2 * (o0 + pj) + 1];
+                const double* ca = cams + (size_t)ci * cam_stride;
+                const double* cb = cams + (size_t)cj * cam_stride;
+                double X, Y, Z;
+                if (rpc_model) {
+                    double lon, lat, h, e;   // the reference's binding casts the keypoints to float32 (s2p/triangulation.py)
+                    rpc_triangulate_one(ca, cb, (double)(float)xi, (double)(float)yi, (double)(float)xj, (double)(float)yj, lon, lat, h, e);
+                    geodetic_to_ecef(lat, lon, h, X, Y, Z);
+                } else {
+                    dlt_triangulate_one(ca, cb, xi, yi, xj, yj, X, Y, Z);
+                }
+                cnt = __fadd_rn(cnt, 1.f);
+                const float c1 = __fsub_rn(cnt, 1.f);
+                ax = __fdiv_rn(__fadd_rn(__fmul_rn(c1, ax), (float)X), cnt);
+                ay = __fdiv_rn(__fadd_rn(__fmul_rn(c1, ay), (float)Y), cnt);
+                az = __fdiv_rn(__fadd_rn(__fmul_rn(c1, az), (float)Z), cnt);
+            }
+        }
+        if (live) { out[3 * t] = ax; out[3 * t + 1] = ay; out[3 * t + 2] = az; }
+    }
+}
+
 // c/rpc.c:480-514 (rpc_height) + c/disp_to_h.c:40-65, one match per thread
 __global__ void __launch_bounds__(128)
 k_rpc_triangulate(const double* __restrict__ rsa, const double* __restrict__ rsb, const float2* __restrict__ kp_a,
@@ -125,22 +293,8 @@ k_rpc_triangulate(const double* __restrict__ rsa, const double* __restrict__ rsb
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float2 a = kp_a[i], b = kp_b[i];
         const double xa = a.x, ya = a.y, xb = b.x, yb = b.y;
-        double h = 0.0, e = 0.0;
-        for (int t = 0; t < 100; ++t) {
-            double lo, la, px, py, qx, qy;
-            s_localize(ra, xa, ya, h, lo, la);
-            s_project(rb, lo, la, h, px, py);
-            s_localize(ra, xa, ya, h + 1.0, lo, la);
-            s_project(rb, lo, la, h + 1.0, qx, qy);
-            const double dx = qx - px, dy = qy - py, ex = xb - px, ey = yb - py;
-            const double lambda = (dx * ex + dy * ey) / (dx * dx + dy * dy);
-            const double zx = px + lambda * dx, zy = py + lambda * dy;
-            e = hypot(zx - xb, zy - yb);
-            h += lambda;
-            if (fabs(lambda) < 0.00001) break;
-        }
-        double lo, la;
-        s_localize(ra, xa, ya, h, lo, la);
+        double lo, la, h, e;
+        rpc_triangulate_one(ra, rb, xa, ya, xb, yb, lo, la, h, e);
         lonlatalt[3 * i] = lo;
         lonlatalt[3 * i + 1] = la;
         lonlatalt[3 * i + 2] = h;
@@ -291,6 +445,65 @@ extern "C" void stereo_corresp_to_lonlatalt(double* lonlatalt, float* err, float
         if (lonlatalt && err)
             for (int i = 0; i < n_kp; ++i) { lonlatalt[3 * i] = lonlatalt[3 * i + 1] = lonlatalt[3 * i + 2] = NAN; err[i] = NAN; }
     }
+}
+
+// Linear triangulation of n matches between two 3x4 matrices (ft_triangulate.py:18-34, the reference calls cv2.triangulatePoints)
+extern "C" int sba_linear_triangulation(const double* P1, const double* P2, const double* pts1, const double* pts2, int64_t n,
+                                        double* pts3d)
+{
+    if (!P1 || !P2 || !pts1 || !pts2 || !pts3d || n < 0) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    DevBuf dp, in, out;
+    SBA_TRY(dp.alloc(24 * sizeof(double))); SBA_TRY(in.alloc(4 * n * sizeof(double))); SBA_TRY(out.alloc(3 * n * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(dp.as<double>(), P1, 12 * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(dp.as<double>() + 12, P2, 12 * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>(), pts1, 2 * n * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + 2 * n, pts2, 2 * n * sizeof(double), cudaMemcpyHostToDevice));
+    k_dlt_pairs<<<grid_n(n, 128), 128>>>(dp.as<double>(), in.as<double>(), in.as<double>() + 2 * n, n, out.as<double>());
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(pts3d, out.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+// init_pts3d (ft_triangulate.py:57-127) for all tracks and all triangulation pairs in one launch.  Tracks in CSR form
+// (track_ptr, cam_idx ascending within a track, pts2d); cameras: n_cam x 12 doubles (row-major 3x4) for cam_model
+// affine / perspective, n_cam x 181 doubles (`struct rpc`, c/rpc.h:14-32) for cam_model rpc.
+extern "C" int sba_init_pts3d(int32_t cam_model, const double* cams, int32_t n_cam, const int64_t* track_ptr, const int32_t* cam_idx,
+                              const double* pts2d, int64_t n_tracks, const int32_t* pairs, int32_t n_pairs, float* pts3d)
+{
+    if (!cams || !track_ptr || !pts3d || n_tracks < 0 || n_cam < 1 || n_pairs < 0 || (n_pairs > 0 && !pairs) ||
+        (cam_model != MODEL_AFFINE && cam_model != MODEL_PERSPECTIVE && cam_model != MODEL_RPC)) {
+        set_error("bad argument"); return SBA_E_INVALID;
+    }
+    if (n_cam > 64 * TRI_MASK_WORDS) { set_error("unsupported size: init_pts3d handles up to 1024 cameras"); return SBA_E_INVALID; }
+    if (n_tracks == 0) return SBA_OK;
+    const int64_t K = track_ptr[n_tracks];
+    if (K < 0 || (K > 0 && (!cam_idx || !pts2d))) { set_error("bad argument"); return SBA_E_INVALID; }
+    for (int64_t t = 0; t < n_tracks; ++t)
+        for (int64_t o = track_ptr[t]; o < track_ptr[t + 1]; ++o)
+            if (cam_idx[o] < 0 || cam_idx[o] >= n_cam || (o > track_ptr[t] && cam_idx[o] <= cam_idx[o - 1])) {
+                set_error("init_pts3d: cameras of a track must be ascending and below n_cam"); return SBA_E_INVALID;
+            }
+    SBA_TRY(require_device());
+    const int rpc_model = cam_model == MODEL_RPC;
+    const size_t cam_doubles = (size_t)n_cam * (rpc_model ? R_STRUCT_DOUBLES : 12);
+    DevBuf dc, dt, di, dp, dq, out;
+    SBA_TRY(dc.alloc(cam_doubles * sizeof(double))); SBA_TRY(dt.alloc((n_tracks + 1) * sizeof(int64_t)));
+    SBA_TRY(di.alloc(K * sizeof(int32_t))); SBA_TRY(dp.alloc(2 * K * sizeof(double)));
+    SBA_TRY(dq.alloc((size_t)n_pairs * 2 * sizeof(int32_t))); SBA_TRY(out.alloc(3 * n_tracks * sizeof(float)));
+    SBA_CUDA(cudaMemcpy(dc.p, cams, cam_doubles * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(dt.p, track_ptr, (n_tracks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (K > 0) {
+        SBA_CUDA(cudaMemcpy(di.p, cam_idx, K * sizeof(int32_t), cudaMemcpyHostToDevice));
+        SBA_CUDA(cudaMemcpy(dp.p, pts2d, 2 * K * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (n_pairs > 0) SBA_CUDA(cudaMemcpy(dq.p, pairs, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    k_init_pts3d<<<grid_n(n_tracks, 128), 128>>>(rpc_model, dc.as<double>(), n_cam, dt.as<long long>(), di.as<int>(), dp.as<double>(),
+                                                n_tracks, dq.as<int2>(), n_pairs, out.as<float>());
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(pts3d, out.p, 3 * n_tracks * sizeof(float), cudaMemcpyDeviceToHost));
+    return SBA_OK;
 }
 
 // Measurement entry point (bench.py --workload rpc): device-resident throughput of the batched RPC kernels over n_cam cameras

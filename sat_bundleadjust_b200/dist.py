@@ -54,19 +54,6 @@ class _CudaView:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
-_PINNED = {}
-
-
-def _pinned(n):
-    """Page-locked host staging buffer of >= n doubles, kept for the life of the process (allocating one costs milliseconds)."""
-    import torch
-    buf = _PINNED.get("buf")
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(int(n * 1.25) + 1024, dtype=torch.float64, pin_memory=True)
-        _PINNED["buf"] = buf
-    return buf[:n]
-
-
 def run_ba_optimization_distributed(p, ls_params=None, group=None):
     """
     Multi-GPU counterpart of ba_core.run_ba_optimization, to be called by every rank of an initialised
@@ -146,16 +133,20 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         if failure is not None and "not finite" in str(failure):
             raise ValueError("Residuals are not finite in the initial point.") from failure
         raise failure if failure is not None else SbaError("the solve failed on another rank")
-    # one all-gather of [x_local | err_init | err] per rank (variable length -> padded to the longest shard), one D2H copy
+    # one all-gather of [x_local | err_init | err] per rank (variable length -> padded to the longest shard), compacted on the
+    # device into [x | err_init | err] and brought back with ONE copy into page-locked memory; the returned arrays are views of
+    # that buffer (torch's caching host allocator recycles it once the caller drops them), so the host never re-copies them
     out = torch.empty((world, longest), dtype=torch.float64, device="cuda")
     dist.all_gather_into_tensor(out, buf, group=group)
-    host = _pinned(world * longest)
-    host.copy_(out.view(-1), non_blocking=True)
+    res = torch.cat([out[0, :ncv]] + [out[r, ncv: n_loc[r]] for r in range(world)]
+                    + [out[r, n_loc[r]: n_loc[r] + k_loc[r]] for r in range(world)]
+                    + [out[r, n_loc[r] + k_loc[r]: n_loc[r] + 2 * k_loc[r]] for r in range(world)])
+    host = torch.empty(res.numel(), dtype=torch.float64, pin_memory=True)
+    host.copy_(res, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    h = host.numpy().reshape(world, longest)
-    x = merge_vars([h[r, : n_loc[r]] for r in range(world)], ncv)
-    err0 = np.concatenate([h[r, n_loc[r]: n_loc[r] + k_loc[r]] for r in range(world)])
-    err1 = np.concatenate([h[r, n_loc[r] + k_loc[r]: n_loc[r] + 2 * k_loc[r]] for r in range(world)])
+    h = host.numpy()
+    n_all, k_all = x0.size, sum(k_loc)
+    x, err0, err1 = h[:n_all], h[n_all: n_all + k_all], h[n_all + k_all:]
     t_end = time.perf_counter()
     info["wall_s"] = {"prepare": t_prep - t_start, "create": t_create - t_prep, "connect": t_connect - t_create,
                       "solve": t_solve - t_connect, "close": t_close - t_solve, "gather": t_end - t_close}

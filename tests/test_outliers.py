@@ -2,7 +2,7 @@
 Outlier removal between the two bundle-adjustment passes against golden vectors produced by the
 unmodified reference (tests/golden/make_outliers_golden.py).  Bar: thresholds, elbow values and the set of removed
 observations bit-exact; the re-triangulated float32 points within one float32 ulp (the reference triangulates with
-cv2.triangulatePoints, we with a batched one-sided Jacobi DLT that agrees with it to < 1e-7 m).
+cv2.triangulatePoints, we with a one-sided Jacobi DLT on the device that agrees with it to < 1e-7 m).
 """
 import os
 
@@ -63,8 +63,9 @@ def _scene_params():
                                       list(G["scene/centers"]), d)
 
 
-def test_reset_ba_params_from_golden_masks():
-    """reset_ba_params_after_outlier_removal (ba_outliers.py:61-109) on the correspondence matrix the reference filtered: CPU only."""
+@pytest.mark.gpu
+def test_reset_ba_params_from_golden_masks(built):
+    """reset_ba_params_after_outlier_removal (ba_outliers.py:61-109) on the correspondence matrix the reference filtered (re-triangulation on the device)."""
     p = _scene_params()
     C_new = p.C.copy()
     C_new[G["scene/auto/C_new_nan"]] = np.nan
