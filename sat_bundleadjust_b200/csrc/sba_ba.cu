@@ -262,6 +262,8 @@ static int run_residual(sba_problem* p, const double* x, const double* camrec, i
 }
 
 static int allreduce_any(sba_problem* p, double* buf, long long count);
+static CommView comm_view(const sba_problem* p);
+static CommFused comm_fused(sba_problem* p, long long count);
 
 // fused residual + analytic Jacobian + robust weighting + block assembly at x (camrec must be prepared).
 // The track-major half (V, g_p) runs on the solver's stream, the camera-major half (U, g_c) on a side stream.
@@ -302,23 +304,48 @@ static int run_assemble(sba_problem* p, const double* x, const double* camrec, i
     return SBA_OK;
 }
 
+static CommView comm_view(const sba_problem* p)
+{
+    CommView c;
+    for (int r = 0; r < COMM_MAX_RANKS; ++r) { c.data[r] = nullptr; c.flag[r] = nullptr; }
+    for (int r = 0; r < p->world; ++r) {
+        c.data[r] = (double*)p->comm_peer[r];
+        c.flag[r] = (unsigned long long*)((double*)p->comm_peer[r] + 2 * p->comm_cap);
+    }
+    c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
+    // 60 s by default (SBA_COMM_TIMEOUT_S): ranks make a host round trip per trial step, so ordinary skew (a busy host, first-touch
+    // IPC mapping, verbose output) must not be mistaken for a lost peer
+    static const double timeout_s = getenv("SBA_COMM_TIMEOUT_S") ? atof(getenv("SBA_COMM_TIMEOUT_S")) : 60.0;
+    c.timeout_cycles = (long long)(timeout_s * 1.9e9);
+    return c;
+}
+
+// Exchange descriptor for a kernel that does its all-reduce of `count` doubles in its own epilogue (cta_allreduce): takes the
+// next exchange number when the peer buffers are mapped, the message fits and SBA_COMM_FUSED is not 0; else on == 0 and
+// the caller falls back to allreduce_any() after the kernel.
+static CommFused comm_fused(sba_problem* p, long long count)
+{
+    static const bool enabled = !(getenv("SBA_COMM_FUSED") && atoi(getenv("SBA_COMM_FUSED")) == 0);
+    CommFused f;
+    f.on = 0; f.seq = 0;
+    if (p->world > 1 && p->comm_ready && !p->comm_split && enabled && count <= p->comm_cap) {
+        f.c = comm_view(p);
+        f.seq = ++g_comm.seq;
+        f.on = 1;
+    } else {
+        for (int r = 0; r < COMM_MAX_RANKS; ++r) { f.c.data[r] = nullptr; f.c.flag[r] = nullptr; }
+        f.c.cap = 0; f.c.timeout_cycles = 0; f.c.me = 0; f.c.world = 1;
+    }
+    return f;
+}
+
 // SUM all-reduce of `count` doubles at device pointer `buf`, in place, on the solver's stream: peer memory when the
 // symmetric buffers are mapped (sba_comm_import), else the caller's hook (NCCL through torch.distributed)
 static int allreduce_any(sba_problem* p, double* buf, long long count)
 {
     if (p->world <= 1) return SBA_OK;
     if (p->comm_ready && count <= p->comm_cap) {
-        CommView c;
-        for (int r = 0; r < COMM_MAX_RANKS; ++r) { c.data[r] = nullptr; c.flag[r] = nullptr; }
-        for (int r = 0; r < p->world; ++r) {
-            c.data[r] = (double*)p->comm_peer[r];
-            c.flag[r] = (unsigned long long*)((double*)p->comm_peer[r] + 2 * p->comm_cap);
-        }
-        c.cap = p->comm_cap; c.me = p->rank; c.world = p->world;
-        // 60 s by default (SBA_COMM_TIMEOUT_S): ranks make a host round trip per trial step, so ordinary skew (a busy host, first-touch
-        // IPC mapping, verbose output) must not be mistaken for a lost peer
-        static const double timeout_s = getenv("SBA_COMM_TIMEOUT_S") ? atof(getenv("SBA_COMM_TIMEOUT_S")) : 60.0;
-        c.timeout_cycles = (long long)(timeout_s * 1.9e9);
+        const CommView c = comm_view(p);
         const unsigned long long seq = ++g_comm.seq;
         const int grid = grid_for(count, 256, 16);
         if (p->comm_split) {        // SBA_COMM_SPLIT=1: the two-launch form (push, then pull)

@@ -130,4 +130,47 @@ k_comm_allreduce(CommView c, double* __restrict__ buf, long long count, unsigned
     }
 }
 
+// The same exchange done by ONE CTA from inside another kernel -- the epilogue of the kernel that produced `buf` (its last CTA
+// to finish, after the grid-wide sums are complete) -- so that the small exchanges of an iteration cost no launch of their own:
+// push, flags, spin, pull, all by the calling CTA.  Every thread of the CTA must call it; `buf` must be visible to the CTA
+// (written by it, or published by other CTAs with __threadfence() before the counter that elected this CTA).
+struct CommFused {           // kernel argument: on == 0 -> no exchange (single GPU, or the exchange is done by separate launches)
+    CommView c;
+    unsigned long long seq;
+    int on;
+};
+
+__device__ __forceinline__ void cta_allreduce(const CommView& c, double* buf, int count, unsigned long long seq, double* scal)
+{
+    const int parity = (int)(seq & 1ull);
+    double* mine = c.data[c.me] + (long long)parity * c.cap;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) mine[i] = __ldcg(buf + i);
+    __threadfence_system();
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if (threadIdx.x < c.world && threadIdx.x != c.me) {
+        st_release_sys(c.flag[threadIdx.x] + parity * COMM_MAX_RANKS + c.me, seq);
+        const unsigned long long* f = c.flag[c.me] + parity * COMM_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > c.timeout_cycles) { ok = 0; break; }  // a peer is gone: report instead of hanging
+        }
+    }
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) scal[SC_COMM_FAIL] = 1.0;
+        __syncthreads();
+        return;
+    }
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < c.world; ++r)
+            acc += (r == c.me) ? mine[i] : ld_volatile_f64(c.data[r] + (long long)parity * c.cap + i);
+        buf[i] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+}
+
 }  // namespace sba

@@ -13,6 +13,7 @@
 // Every reduction has a fixed order (static unit -> warp assignment, ordered merges), so results are
 // reproducible bit for bit.  Included by sba_ba.cu only.
 #pragma once
+#include "sba_comm.cuh"
 #include "sba_kernels.cuh"
 #include "sba_pattern.h"
 
@@ -358,7 +359,7 @@ template <int NC>
 __global__ void __launch_bounds__(256)
 k_pt_reduce_assemble(const double* __restrict__ partials, int n_cta, int M, double* __restrict__ camsys, int fold,
                      const double* __restrict__ dsq_c_cur, int first, double* __restrict__ dsq_c_new,
-                     double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal, unsigned* counter)
+                     double* __restrict__ idsq_c_new, double* __restrict__ g_new, double* scal, unsigned* counter, CommFused comm)
 {
     constexpr int NU = NC * (NC + 1) / 2, NV = NU + NC;
     const int lane = threadIdx.x & 31;
@@ -395,8 +396,9 @@ k_pt_reduce_assemble(const double* __restrict__ partials, int n_cta, int M, doub
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    cam_scale_dev(camsys, dsq_c_cur, first, M, NC, dsq_c_new, idsq_c_new, g_new, scal);
     if (threadIdx.x == 0) *counter = 0u;
+    if (comm.on) cta_allreduce(comm.c, camsys, M * NC * NC + M * NC + 1, comm.seq, scal);      // multi-GPU: [U | g_c | cost] summed over the ranks
+    cam_scale_dev(camsys, dsq_c_cur, first, M, NC, dsq_c_new, idsq_c_new, g_new, scal);
 }
 
 __global__ void __launch_bounds__(256)
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(PT_THREADS_LIGHT, 1)
 k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
           const double* __restrict__ g, const double* __restrict__ dsq_c, const double* __restrict__ idsq_c,
           double* __restrict__ dsq, double* __restrict__ idsq, const double2* __restrict__ osc, int first, int ns,
-          int count_cameras, int rank, double* partials, unsigned* counter, double* scal, int fold_ctl, double delta_arg)
+          int count_cameras, int rank, double* partials, unsigned* counter, double* scal, int fold_ctl, double delta_arg, CommFused comm)
 {
     extern __shared__ double smem[];
     double* s_cam = smem;
@@ -558,6 +560,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
     if (threadIdx.x == 0) { slots[0] = SC_GG; slots[1] = SC_XS; slots[2] = SC_XX; slots[3] = SC_A; }
     __syncthreads();
     const bool last = grid_sum_last<4>(tot, partials, counter, scal, slots);
+    if (last && comm.on) cta_allreduce(comm.c, scal + SC_COST, SC_GGN - SC_COST, comm.seq, scal);
     if (last && fold_ctl && threadIdx.x == 0) control_reg_dev(scal, delta_arg, -1.0);
 }
 
@@ -819,38 +822,92 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
 // Sum of the per-CTA Schur partials -> reduced camera system S (ns x ns column-major, symmetric, both triangles) and its
 // right-hand side:  S_jj' = [j == j'] (U_j + reg D_j^2) - sum,  rhs_j = -g_j + sum.  One warp per value.
 // add_diag: rank 0 only (the all-reduce over ranks then counts U and the damping once).
+// Multi-GPU (comm.on): the values go to the rank's exchange slot instead (block-upper layout, nS + ns doubles -- smaller than
+// the symmetric S), the last CTA to finish publishes the flags, every CTA waits for the peers' flags and the warps sum
+// the R contributions of their values in rank order straight out of peer memory (one remote load per lane) into S: the
+// all-reduce of [S | rhs] costs no launch of its own.  The grid is <= one CTA per SM, so all CTAs are resident while they wait.
 template <int NC>
-__global__ void __launch_bounds__(256)
-k_pt_reduce_schur(const double* __restrict__ partials, int n_cta, int M, int n_cam_fix, const double* __restrict__ camsys,
-                  const double* __restrict__ dsq_c, const double* __restrict__ scal, int add_diag, double* __restrict__ S)
+__device__ __forceinline__ void reduce_schur_store(int v, double val, int M, double* __restrict__ S)
 {
-    const int lane = threadIdx.x & 31;
     const int ns = M * NC, nS = NC * NC * (M * (M + 1) / 2);
-    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (v >= nS + ns) return;
-    double s = 0.0;
-    for (int b = lane; b < n_cta; b += 32) s += partials[(size_t)v * n_cta + b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane != 0) return;
-    const double reg = scal[SC_REG];
-    if (v >= nS) {
-        const int e = v - nS;
-        S[(size_t)ns * ns + e] = (add_diag ? -camsys[(size_t)M * NC * NC + e] : 0.0) + s;
-        return;
-    }
+    if (v >= nS) { S[(size_t)ns * ns + (v - nS)] = val; return; }
     int b = v / (NC * NC);
     const int rs = v - b * NC * NC, r = rs / NC, c = rs - r * NC;
     int j = 0;
     while (b >= M - j) { b -= M - j; ++j; }
     const int jp = j + b;
-    double val = -s;
-    if (j == jp && add_diag) {
-        val += camsys[(size_t)j * NC * NC + r * NC + c];
-        if (r == c) val += (j < n_cam_fix) ? 1.0 : reg * dsq_c[(size_t)j * NC + r];
-    }
     S[(size_t)(j * NC + r) + (size_t)(jp * NC + c) * ns] = val;
     if (j != jp) S[(size_t)(jp * NC + c) + (size_t)(j * NC + r) * ns] = val;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(512)
+k_pt_reduce_schur(const double* __restrict__ partials, int n_cta, int M, int n_cam_fix, const double* __restrict__ camsys,
+                  const double* __restrict__ dsq_c, double* scal, int add_diag, double* __restrict__ S, CommFused comm,
+                  unsigned* counter)
+{
+    const int lane = threadIdx.x & 31;
+    const int ns = M * NC, nS = NC * NC * (M * (M + 1) / 2), total = nS + ns;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    const int parity = (int)(comm.seq & 1ull);
+    double* mine = comm.on ? comm.c.data[comm.c.me] + (long long)parity * comm.c.cap : nullptr;
+    const double reg = scal[SC_REG];
+    for (int v = gw; v < total; v += nwarps) {
+        double s = 0.0;
+        for (int b = lane; b < n_cta; b += 32) s += partials[(size_t)v * n_cta + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane != 0) continue;
+        double val;
+        if (v >= nS) {
+            val = (add_diag ? -camsys[(size_t)M * NC * NC + (v - nS)] : 0.0) + s;
+        } else {
+            int b = v / (NC * NC);
+            const int rs = v - b * NC * NC, r = rs / NC, c = rs - r * NC;
+            int j = 0;
+            while (b >= M - j) { b -= M - j; ++j; }
+            val = -s;
+            if (b == 0 && add_diag) {
+                val += camsys[(size_t)j * NC * NC + r * NC + c];
+                if (r == c) val += (j < n_cam_fix) ? 1.0 : reg * dsq_c[(size_t)j * NC + r];
+            }
+        }
+        if (comm.on) mine[v] = val;
+        else reduce_schur_store<NC>(v, val, M, S);
+    }
+    if (!comm.on) return;
+    __threadfence_system();
+    __shared__ bool last;
+    __shared__ int ok;
+    __syncthreads();
+    if (threadIdx.x == 0) { last = (atomicAdd(counter, 1u) == gridDim.x - 1); ok = 1; }
+    __syncthreads();
+    const CommView& c = comm.c;
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < c.world && threadIdx.x != c.me)
+            st_release_sys(c.flag[threadIdx.x] + parity * COMM_MAX_RANKS + c.me, comm.seq);
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+    if (threadIdx.x < c.world && threadIdx.x != c.me) {
+        const unsigned long long* f = c.flag[c.me] + parity * COMM_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < comm.seq) {
+            if (clock64() - t0 > c.timeout_cycles) { ok = 0; break; }  // a peer is gone: report instead of hanging
+        }
+    }
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) scal[SC_COMM_FAIL] = 1.0;
+        return;
+    }
+    for (int v = gw; v < total; v += nwarps) {
+        double part = 0.0;
+        if (lane < c.world) part = ld_volatile_f64(c.data[lane] + (long long)parity * c.cap + v);
+        double acc = 0.0;
+        for (int r = 0; r < c.world; ++r) acc += __shfl_sync(0xffffffffu, part, r);
+        if (lane == 0) reduce_schur_store<NC>(v, acc, M, S);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -863,7 +920,8 @@ __global__ void __launch_bounds__(PT_THREADS_LIGHT, 1)
 k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
              const double* __restrict__ g, const double* __restrict__ dsq, const double* __restrict__ idsq,
              const double* __restrict__ dsq_c, const double* __restrict__ idsq_c, const double2* __restrict__ osc,
-             double* __restrict__ delta, int ns, int count_cameras, double* partials, unsigned* counter, double* scal, int fold_ctl)
+             double* __restrict__ delta, int ns, int count_cameras, double* partials, unsigned* counter, double* scal, int fold_ctl,
+             CommFused comm)
 {
     extern __shared__ double smem[];
     double* s_cam = smem;
@@ -962,6 +1020,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
     }
     __syncthreads();
     const bool last = grid_sum_last<7>(tot, partials, counter, scal, slots);
+    if (last && comm.on) cta_allreduce(comm.c, scal + SC_P_GD, 7, comm.seq, scal);
     if (last && fold_ctl && threadIdx.x == 0) control_tr2d_gram_dev(scal, -1.0);
 }
 

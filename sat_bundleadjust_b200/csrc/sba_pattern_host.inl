@@ -98,18 +98,19 @@ static int pt_run_assemble(sba_problem* p, int initial, int first, int loss, dou
 {
     const int ns = p->M * p->nc;
     const size_t cs_count = (size_t)ns * p->nc + ns + 1;
+    const CommFused cf = comm_fused(p, (long long)cs_count);
 #define L(MODEL, NC)                                                                                                          \
     k_pt_assemble<MODEL, NC><<<p->pt_n_cta, PT_THREADS, pt_smem_assemble(p), p->stream>>>(                                     \
         pat_view(p, 1), p->x, p->g, p->idsq, p->idsqc, p->delta, p->scal, initial, ns, loss, f_scale, p->x_new, p->camrec_new,    \
         p->V2, p->g2, (double2*)p->osc2, p->pt_partials);                                                                      \
     SBA_TRY(check_launch(p));                                                                                                  \
     k_pt_reduce_assemble<NC><<<(p->M * (NC * (NC + 1) / 2 + NC) + 1 + 7) / 8, 256, 0, p->stream>>>(                          \
-        p->pt_partials, p->pt_n_cta, p->M, p->camsys2, p->world == 1, p->dsqc, first, p->dsqc2, p->idsqc2, p->g2, p->scal,     \
-        p->counters + 4)
+        p->pt_partials, p->pt_n_cta, p->M, p->camsys2, p->world == 1 || cf.on, p->dsqc, first, p->dsqc2, p->idsqc2, p->g2, p->scal, \
+        p->counters + 4, cf)
     PT_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
-    if (p->world > 1) {
+    if (p->world > 1 && !cf.on) {
         SBA_TRY(allreduce_any(p, p->camsys2, (long long)cs_count));
         k_pt_cam_scale<<<1, 256, 0, p->stream>>>(p->camsys2, p->dsqc, first, p->M, p->nc, p->dsqc2, p->idsqc2, p->g2, p->scal);
         SBA_TRY(check_launch(p));
@@ -129,11 +130,12 @@ static int pt_run_jvp1(sba_problem* p, int first, int loss, double f_scale, doub
 {
     const int ns = p->M * p->nc;
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_GMAX_SLOTS, 0, 16 * sizeof(double), p->stream));
-    const int fold = p->world == 1;
+    const CommFused cf = comm_fused(p, SC_GGN - SC_COST);
+    const int fold = p->world == 1 || cf.on;
 #define L(MODEL, NC)                                                                                                       \
     k_pt_jvp1<MODEL, NC><<<p->pt_n_cta, PT_THREADS_LIGHT, pt_smem_jvp1(p), p->stream>>>(                                    \
         pat_view(p, 0), p->x, p->camrec, p->V, p->g, p->dsqc, p->idsqc, p->dsq, p->idsq, (const double2*)p->osc, first, ns,   \
-        p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal, fold, delta_arg)
+        p->rank == 0, p->rank, p->red_partials, p->counters + 2, p->scal, fold, delta_arg, cf)
     PT_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
@@ -150,28 +152,30 @@ static int pt_run_schur(sba_problem* p, int loss, double f_scale)
 {
     const int ns = p->M * p->nc, nS = p->nc * p->nc * (p->M * (p->M + 1) / 2);
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
+    const CommFused cf = comm_fused(p, (long long)nS + ns);
 #define L(MODEL, NC)                                                                                                        \
     k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                                   \
         pat_view(p, 2), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
         p->scal + SC_BAD_POINTS);                                                                                            \
     SBA_TRY(check_launch(p));                                                                                                \
-    k_pt_reduce_schur<NC><<<(nS + ns + 7) / 8, 256, 0, p->stream>>>(p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, \
-                                                                   p->dsqc, p->scal, p->rank == 0, p->S)
+    k_pt_reduce_schur<NC><<<std::min(PT_CTAS, (nS + ns + 15) / 16), 512, 0, p->stream>>>(                                    \
+        p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, p->dsqc, p->scal, p->rank == 0, p->S, cf, p->counters + 6)
     PT_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
-    SBA_TRY(allreduce_any(p, p->S, (long long)ns * ns + ns));
+    if (!cf.on) SBA_TRY(allreduce_any(p, p->S, (long long)ns * ns + ns));
     return SBA_OK;
 }
 
 static int pt_run_backsub(sba_problem* p, int loss, double f_scale)
 {
     const int ns = p->M * p->nc;
-    const int fold = p->world == 1;
+    const CommFused cf = comm_fused(p, 7);
+    const int fold = p->world == 1 || cf.on;
 #define L(MODEL, NC)                                                                                                      \
     k_pt_backsub<MODEL, NC><<<p->pt_n_cta, PT_THREADS_LIGHT, pt_smem_backsub(p), p->stream>>>(                             \
         pat_view(p, 0), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
-        p->rank == 0, p->red_partials, p->counters + 3, p->scal, fold)
+        p->rank == 0, p->red_partials, p->counters + 3, p->scal, fold, cf)
     PT_DISPATCH(p, L);
 #undef L
     SBA_TRY(check_launch(p));
