@@ -8,32 +8,49 @@
 // rides along as an extra row, so the forward substitution L y = rhs falls out of the factorisation and only the
 // backward substitution remains.
 #include "sba_internal.cuh"
+#include <math_constants.h>
 
 namespace sba {
 
 constexpr int CB = 32, CB_LD = CB + 1, CU_TILE = 64;
 constexpr int CHOL_FUSED_MAX_N = 127;        // one CTA, matrix in shared memory, 4 x 4 register tiles of the trailing update
+__device__ long long g_chol_clk[16];         // stage clocks of the last k_chol_fused launch (diagnostics, tools/chol_time.py)
+#define CHOL_CLK(i) do { if (threadIdx.x == 0) g_chol_clk[i] = clock64(); } while (0)
 constexpr int CHOL_FUSED_WARPS = 16, CHOL_FUSED_THREADS = 32 * CHOL_FUSED_WARPS;    // 128 registers per thread: warp_chol32 needs ~110
 
 // Cholesky factorisation of a 32 x 32 block held by ONE warp in registers: lane r owns row r (a[c], c <= r; identity
 // padding for unused rows), right-looking, the pivot column travels by shuffles; entries above the diagonal are scratch
 // and never leave their lane.  ~150 dependent cycles per column instead of the ~1500 of a shared-memory/barrier version.
 // Returns 0 or (c+1) for the first non-positive pivot (uniform across the warp); inv receives 1 / L[lane, lane].
+// 1 / sqrt(x) for the pivots: hardware seed (rsqrt.approx.ftz.f64, ~2^-22) and ONE cubically convergent step, r (1 + e/2 + 3 e^2 / 8) with e = 1 - x r^2 --
+// four dependent FP64 operations instead of the six of two Newton steps; the remainder 5 e^3 / 16 is below 2^-64.
+__device__ __forceinline__ double pivot_rsqrt(double x)
+{
+    double r;                                  // MUFU.RSQ64H on the high word: no conversions to and from FP32 on the pivot chain
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-(x * r), r, 1.0);
+    return fma(r * e, fma(0.375, e, 0.5), r);
+}
+
 __device__ __forceinline__ int warp_chol32(double (&a)[CB], int lane, double& inv)
 {
     inv = 1.0;
+    int bad = 0;
+    // No branch inside the column loop: a failed pivot is recorded and replaced by 1, so the 32 columns are ONE basic block and
+    // the pending updates of column c overlap the dependent chain (shuffle, rsqrt, scale) of column c + 1.
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
         const double d = __shfl_sync(0xffffffffu, a[c], c);
-        if (!(d > 0.0) || !isfinite(d)) return c + 1;
-        const double ip = fast_rsqrt(d);
+        const bool ok = d > 0.0 && d < CUDART_INF;
+        bad = (bad == 0 && !ok) ? c + 1 : bad;
+        const double ip = pivot_rsqrt(ok ? d : 1.0);
         const double l = a[c] * ip;
         a[c] = l;
         if (lane == c) inv = ip;
 #pragma unroll
-        for (int k = c + 1; k < CB; ++k) a[k] -= l * __shfl_sync(0xffffffffu, l, k);
+        for (int k = c + 1; k < CB; ++k) a[k] = fma(-l, __shfl_sync(0xffffffffu, l, k), a[k]);
     }
-    return 0;
+    return bad;
 }
 
 // n <= 127: the whole solve in one CTA.  W = lower triangle of A plus the right-hand side as row n, in shared memory
@@ -48,6 +65,7 @@ __global__ void __launch_bounds__(CHOL_FUSED_THREADS)
 k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool write_factor)
 {
     extern __shared__ double W[];                    // (n+1) x ld
+    CHOL_CLK(0);
     __shared__ double s_inv[CB * NT];
     __shared__ int s_bad;
     const int ld = n | 1;
@@ -69,6 +87,7 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
     for (int j = tid; j < n; j += CHOL_FUSED_THREADS) W[n * ld + j] = b[j];
     if (tid == 0) s_bad = 0;
     __syncthreads();
+    CHOL_CLK(1);
     for (int j0 = 0; j0 < n; j0 += CB) {
         const int nb = min(CB, n - j0), m0 = j0 + nb;
         if (warp == 0) {
@@ -85,6 +104,7 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
             }
         }
         __syncthreads();
+        if (j0 < 2 * CB) CHOL_CLK(2 + 3 * (j0 / CB));
         if (s_bad) break;
         // rows m0 + warp + 16 k of the panel (row n = right-hand side): X L_jj^T = rows
         {
@@ -95,13 +115,21 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
                 xv[k] = (r <= n && lane < nb) ? W[r * ld + j0 + lane] : 0.0;
             }
             if (m0 + warp <= n) {
-                for (int c = 0; c < nb; ++c) {
-                    const double lc = lane < nb ? W[(j0 + lane) * ld + j0 + c] : 0.0, inv = s_inv[j0 + c];
+                // row `lane` of the factored block and the inverse pivots in registers: the substitution below is then a pure
+                // shuffle -> multiply -> fma chain (no shared-memory latency inside it)
+                double lrow[CB];
 #pragma unroll
-                    for (int k = 0; k < RPW; ++k) {
-                        const double xc = __shfl_sync(0xffffffffu, xv[k], c) * inv;
-                        if (lane == c) xv[k] = xc;
-                        else if (lane > c) xv[k] -= xc * lc;
+                for (int c = 0; c < CB; ++c) lrow[c] = (lane < nb && c < nb && c <= lane) ? W[(j0 + lane) * ld + j0 + c] : 0.0;
+                const double invl = lane < nb ? s_inv[j0 + lane] : 1.0;
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    if (c < nb) {                                   // uniform
+                        const double ic = __shfl_sync(0xffffffffu, invl, c);
+#pragma unroll
+                        for (int k = 0; k < RPW; ++k) {
+                            const double xc = __shfl_sync(0xffffffffu, xv[k], c) * ic;
+                            xv[k] = lane == c ? xc : fma(-xc, lrow[c], xv[k]);        // lrow[c] = 0 for lanes < c: they are done
+                        }
                     }
                 }
 #pragma unroll
@@ -112,6 +140,7 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
             }
         }
         __syncthreads();
+        if (j0 < 2 * CB) CHOL_CLK(3 + 3 * (j0 / CB));
         // trailing triangle (rows <= n, columns < n): W[i,j] -= sum_c W[i,j0+c] W[j,j0+c]; i = m0 + warp + 16 a, j = m0 + lane + 32 q
         if (m0 < n) {
             double acc[RPW][NT];
@@ -145,6 +174,7 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
                 }
         }
         __syncthreads();
+        if (j0 < 2 * CB) CHOL_CLK(4 + 3 * (j0 / CB));
     }
     if (s_bad) {
         if (tid == 0) *fail = (double)s_bad;
@@ -155,21 +185,29 @@ k_chol_fused(double* Ag, const double* b, double* x, int n, double* fail, bool w
         double yv[NT];
 #pragma unroll
         for (int m = 0; m < NT; ++m) yv[m] = lane + 32 * m < n ? W[n * ld + lane + 32 * m] : 0.0;
+        double invv[NT];
 #pragma unroll
-        for (int m = NT - 1; m >= 0; --m)
+        for (int m = 0; m < NT; ++m) invv[m] = lane + 32 * m < n ? s_inv[lane + 32 * m] : 1.0;
+#pragma unroll
+        for (int m = NT - 1; m >= 0; --m) {
+            if (32 * m >= n) continue;                                       // uniform
+#pragma unroll 8
             for (int kk = 31; kk >= 0; --kk) {
                 const int k = 32 * m + kk;
-                if (k >= n) continue;                                        // uniform
-                const double xk = __shfl_sync(0xffffffffu, yv[m], kk) * s_inv[k];
-                const double* rk = W + k * ld;
+                if (k < n) {                                                 // uniform
+                    // the row of L is fetched before the value it multiplies is known: only shuffle -> fma stays on the chain
+                    double lk[NT];
 #pragma unroll
-                for (int m2 = 0; m2 <= m; ++m2) {
-                    const int i = lane + 32 * m2;
-                    if (i < k) yv[m2] -= rk[i] * xk; else if (i == k) yv[m2] = xk;
+                    for (int m2 = 0; m2 <= m; ++m2) lk[m2] = lane + 32 * m2 < k ? W[k * ld + lane + 32 * m2] : 0.0;
+                    const double xk = __shfl_sync(0xffffffffu, yv[m] * invv[m], kk);
+#pragma unroll
+                    for (int m2 = 0; m2 <= m; ++m2) yv[m2] = (lane + 32 * m2 == k) ? xk : fma(-lk[m2], xk, yv[m2]);
                 }
             }
+        }
 #pragma unroll
         for (int m = 0; m < NT; ++m) if (lane + 32 * m < n) x[lane + 32 * m] = yv[m];
+        CHOL_CLK(8);
     }
     if (write_factor)
         for (int j = warp; j < n; j += FW)
@@ -430,6 +468,12 @@ int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, do
         k_chol_backsolve<<<1, 1024, 2 * (size_t)n * sizeof(double), stream>>>(A_dev, work_dev, Dblk, Dinv, x_dev, n, fail_dev);
     }
     SBA_CUDA(cudaGetLastError());
+    return SBA_OK;
+}
+
+int chol_stage_clocks(long long* out16)
+{
+    SBA_CUDA(cudaMemcpyFromSymbol(out16, g_chol_clk, 16 * sizeof(long long)));
     return SBA_OK;
 }
 

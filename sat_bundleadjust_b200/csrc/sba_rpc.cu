@@ -345,6 +345,7 @@ static inline int grid_n(long long n, int threads)
 
 int launch_cholesky_solve(double* A_dev, double* b_dev, double* x_dev, int n, double* fail_dev, double* work_dev,
                           cudaStream_t stream, bool write_factor);
+int chol_stage_clocks(long long* out16);
 
 }  // namespace sba
 
@@ -606,6 +607,12 @@ extern "C" int sba_cholesky_solve_timed(const double* A, const double* b, int32_
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     SBA_CUDA(cudaMemcpy(x, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (getenv("SBA_CHOL_CLK") && n <= 127) {      // stage clocks of the one-CTA kernel: load | per panel: block, rows, trailing | back-substitution
+        long long c[16];
+        SBA_TRY(chol_stage_clocks(c));
+        fprintf(stderr, "chol n=%d cycles: load %lld | p0 %lld %lld %lld | p1 %lld %lld %lld | backsub %lld | total %lld\n", n, c[1] - c[0],
+                c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[7] - c[6], c[8] - c[7], c[8] - c[0]);
+    }
     *ms = total / reps;
     return SBA_OK;
 }
