@@ -72,8 +72,7 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
     from ._lib import SbaError
     from .solver import DeviceProblem, initial_vars, n_common_params
 
-    if n_common_params(p):
-        raise NotImplementedError("COMMON_K is not supported by the distributed driver")
+    k_common = n_common_params(p)                  # COMMON_K: the caller's vector is [K | cameras | points] (ba_params.py:167-171)
     t_start = time.perf_counter()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     cfg = ba_core.init_optimization_config(ls_params)
@@ -89,7 +88,8 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         ranges, a = cache[1], cache[2]
     if any(a1 == a0 for a0, a1 in a):
         raise ValueError("fewer tracks with observations than ranks: use a smaller process group")
-    ncv = p.n_cam * p.n_params
+    ncv = p.n_cam * p.n_params                                     # camera part of the device vector (n_params slots per camera)
+    ncv_ref = ncv - (p.n_cam - 1) * k_common                       # ... and of the caller's vector
     x0 = initial_vars(p)
     stream = torch.cuda.current_stream().cuda_stream
     n_loc = [ncv + 3 * (t1 - t0) for t0, t1 in ranges]
@@ -115,7 +115,7 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
         if os.environ.get("SBA_COMM", "peer") == "peer":
             prob.connect_peers(gather_obj)
         t_connect = time.perf_counter()
-        xl0 = torch.from_numpy(prob._vars(local_vars(x0, ncv, ranges[rank]))).cuda()
+        xl0 = torch.from_numpy(prob._vars(local_vars(x0, ncv_ref, ranges[rank]))).cuda()
         nl, kl = n_loc[rank], k_loc[rank]
         base = buf.data_ptr()
         try:
@@ -145,8 +145,11 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
     host.copy_(res, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     h = host.numpy()
-    n_all, k_all = x0.size, sum(k_loc)
+    n_all, k_all = ncv + 3 * p.n_pts, sum(k_loc)
     x, err0, err1 = h[:n_all], h[n_all: n_all + k_all], h[n_all + k_all:]
+    if k_common:                                                   # device layout -> [K | cameras | points]
+        cams = x[:ncv].reshape(p.n_cam, p.n_params)
+        x = np.concatenate([cams[0, p.n_params - k_common:], cams[:, : p.n_params - k_common].ravel(), x[ncv:]])
     t_end = time.perf_counter()
     info["wall_s"] = {"prepare": t_prep - t_start, "create": t_create - t_prep, "connect": t_connect - t_create,
                       "solve": t_solve - t_connect, "close": t_close - t_solve, "gather": t_end - t_close}

@@ -54,6 +54,21 @@ def main():
                 ok = ok and rel < tol and np.array_equal(v0, s0) and np.abs(e0 - f0).max() < 1e-9
                 if max_iter == 12:
                     ok = ok and nfev == nfev1
+    # COMMON_K (one calibration shared by all cameras): generic engine, shared columns folded after the all-reduce.
+    # The reference's packing mis-initialises the shared intrinsics: repaired in place so that both runs start sanely.
+    sc = synth.make_scene(n_cam=4, n_tracks=4000, p_vis=0.8, cam_model="perspective", seed=12)
+    p = synth.scene_to_params(sc, ["R", "T", "K", "COMMON_K"])
+    p.params_opt[:5] = p.cam_params[0, -5:]
+    ls = {"loss": "soft_l1", "f_scale": 1.0, "max_iter": 60, "verbose": 0}
+    v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
+    if rank == 0:
+        s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+        rel = abs(info["cost"] - info1["cost"]) / info1["cost"]
+        print("COMMON_K max_iter 60: dist cost %.12e nfev %d | single cost %.12e nfev %d | rel %.2e | n_vars %d vs %d" % (
+            info["cost"], nfev, info1["cost"], nfev1, rel, v1.size, s1.size), flush=True)
+        ok_k = rel < 1e-5 and v1.shape == s1.shape and np.array_equal(v0, s0) and info["cost"] < 0.999 * info["cost_init"]
+        print("COMMON_K: cost_init %.6e max|dx| %.2e ok %s" % (info["cost_init"], np.abs(v1 - s1).max(), ok_k), flush=True)
+        ok = ok and ok_k
     # all ranks hold identical results
     t = torch.from_numpy(v1[:100].copy()).cuda()
     lst = [torch.empty_like(t) for _ in range(dist.get_world_size())]
