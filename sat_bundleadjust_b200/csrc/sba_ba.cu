@@ -846,7 +846,8 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     stamp("host index pass");
     if (try_pattern) {
         PatternLayout lay;
-        build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, PT_RC,
+        if (const char* e = getenv("SBA_PT_SCHUR")) p->pt_schur_mma = std::strcmp(e, "mma") == 0;
+        build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, p->pt_schur_mma ? 0 : PT_RC,
                              lay);
         stamp("pattern layout");
         if (lay.ok) {

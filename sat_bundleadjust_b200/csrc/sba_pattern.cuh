@@ -819,6 +819,240 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
     }
 }
 
+// D += A (8 x 4, row-major fragment: lane holds A[lane / 4][lane % 4]) x B (4 x 8, column-major fragment: lane holds
+// B[lane % 4][lane / 4]); a lane owns D[lane / 4][2 (lane % 4)] and the column next to it.  FP64 tensor-core path (DMMA):
+// one warp instruction does the 256 FMAs that cost 8 DFMA instructions plus their operand loads on the FP64 pipe.
+__device__ __forceinline__ void mma_f64_884(double (&d)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+template <int NC> __host__ __device__ constexpr int pt_record_doubles_mma() { return PT_MMA_TILES * 64 + NC * 32; }
+
+// K3, tensor-core variant (SBA_PT_SCHUR=mma; NOT the default): the same elimination, with the products Z_a Z_b^T of all camera
+// pairs of a track formed as the Gram matrix of the track's stacked Z rows by m8n8k4 DMMA (k = 3 padded to 4).  When a tile lies
+// on the diagonal of the Gram matrix both triangles are computed; the merge reads the upper one.  Results agree with the DFMA
+// kernel to rounding (tests/test_gpu_ba.py::test_schur_kernel_variants).  Measured on B200 at 1e6 observations: 236 us against
+// 127 us -- the DFMA kernel already spreads the (pair, row chunk) tasks of a track over the 32 lanes, so both issue ~80 warp
+// instructions per track, and with 3 warps per scheduler the DMMA chain (fragment loads -> 10 dependent-accumulator MMAs) hides
+// less latency than 54 independent DFMAs per lane.  tools/dmma_lat.cu: DMMA issues at 16 cycles per SM sub-partition (37 TFLOP/s)
+// from 3 warps on, so the pipe itself is not the limit.
+template <int MODEL, int NC>
+__global__ void __launch_bounds__(PT_THREADS_SCHUR, 1)
+k_pt_schur_mma(PatView A, const double* __restrict__ x, const double* __restrict__ camrec, const double* __restrict__ V,
+           const double* __restrict__ g, const double* __restrict__ dsq, const double2* __restrict__ osc,
+           const double* __restrict__ scal, int ns, double* __restrict__ records, double* __restrict__ partials, double* bad_points)
+{
+    constexpr int ZS = NC * 3, ZP = ZS + 1;
+    constexpr int NTP = PT_MMA_TILES;
+    constexpr int REC = pt_record_doubles_mma<NC>();
+    extern __shared__ double smem[];
+    const int nS = NC * NC * (A.M * (A.M + 1) / 2);
+    double* s_cam = smem;
+    double* s_rpc = s_cam + A.M * CAMREC_STRIDE;
+    double* s_Z = s_rpc + (MODEL == MODEL_RPC ? A.M * RPC_TAB_STRIDE : 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double reg = scal[SC_REG];
+    load_cameras_shared<MODEL>(A, camrec, s_cam, s_rpc);
+    __syncthreads();
+    double* zs = s_Z + (size_t)warp * (32 * ZP + PT_RC * 3);          // tail padding: the last chunk may read past row NC-1
+    int nbad = 0;
+    const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const int frow = lane >> 2, fk = lane & 3;           // fragment coordinates of the lane: row of the 8 x 4 operand, k index
+    for (int u = u0; u < u1; ++u) {
+        const PUnit un = A.units[u];
+        const LaneGeo G = lane_geometry(un, lane);
+        const bool cam_free = G.cam >= A.n_cam_fix, pt_free = un.pts_free != 0;
+        const double* rec = s_cam + G.cam * CAMREC_STRIDE;
+        const double* rpc_j = MODEL == MODEL_RPC ? s_rpc + G.cam * RPC_TAB_STRIDE : nullptr;
+        // Gram matrix of a track's stacked Z rows (L NC rows x 3): 8 x 8 tiles, upper triangle, tile (i, j) = number j (j + 1) / 2 + i.
+        // One pass when R <= 6 (the tile -> (i, j) map is then static and every operand fragment is loaded once per track).
+        const int nrows = G.L * NC, R = (nrows + 7) >> 3, ntile = R * (R + 1) / 2, npass = (ntile + NTP - 1) / NTP;
+        int foff[6];                                         // offset of the lane's element of row block i inside a track's Z rows
+        bool fok[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int row = 8 * i + frow, pos = row / NC;
+            fok[i] = row < nrows && fk < 3;
+            foff[i] = fok[i] ? pos * ZP + (row - pos * NC) * 3 + fk : 0;
+        }
+        for (int pass = 0; pass < npass; ++pass) {
+            double C[NTP][2], accR[NC];
+#pragma unroll
+            for (int q = 0; q < NTP; ++q) { C[q][0] = 0.0; C[q][1] = 0.0; }
+#pragma unroll
+            for (int r = 0; r < NC; ++r) accR[r] = 0.0;
+            for (int tb = 0; tb < un.ntrk; tb += G.T) {
+                const int tt = tb + G.t;
+                const bool on = G.on && tt < un.ntrk;
+                const int nact = min(G.T, un.ntrk - tb);
+                if (G.on && tt + G.T < un.ntrk) {          // next tile
+                    const size_t in = (size_t)(un.trk0 + tt + G.T), en = (size_t)ns + 3 * in;
+                    prefetch_l1(osc + (size_t)un.obs0 + (size_t)(tt + G.T) * G.L + G.k);
+                    prefetch_l1(x + en); prefetch_l1(g + en); prefetch_l1(dsq + en); prefetch_l1(V + 6 * in);
+                }
+                if (on) {
+                    const int i = un.trk0 + tt;
+                    const size_t a = (size_t)un.obs0 + (size_t)tt * G.L + G.k;
+                    const size_t e3 = (size_t)ns + 3 * (size_t)i;
+                    const double2 sc = osc[a];
+                    const double X = x[e3], Y = x[e3 + 1], Z = x[e3 + 2];
+                    const double* v = V + 6 * (size_t)i;
+                    double Gm[6], qv[3] = {0.0, 0.0, 0.0};
+                    bool ok = false;
+                    if (pt_free) ok = invert_point_block_d2(v[0], v[1], v[2], v[3], v[4], v[5], dsq[e3], dsq[e3 + 1], dsq[e3 + 2], reg, Gm);
+                    if (!ok) {
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) Gm[m] = 0.0;
+                        if (pt_free && G.k == 0 && pass == 0) ++nbad;
+                    } else {
+                        const double g0 = g[e3], g1 = g[e3 + 1], g2 = g[e3 + 2];
+                        qv[0] = Gm[0] * g0;
+                        qv[1] = Gm[1] * g0 + Gm[2] * g1;
+                        qv[2] = Gm[3] * g0 + Gm[4] * g1 + Gm[5] * g2;
+                    }
+                    ObsEval<MODEL, NC> e;
+                    eval_scaled<MODEL, NC>(rec, rpc_j, X, Y, Z, sc, cam_free, pt_free, e);
+                    double* z = zs + lane * ZP;
+#pragma unroll
+                    for (int r = 0; r < NC; ++r) {
+                        const double w0 = e.Jc[r] * e.Jp[0] + e.Jc[NC + r] * e.Jp[3];
+                        const double w1 = e.Jc[r] * e.Jp[1] + e.Jc[NC + r] * e.Jp[4];
+                        const double w2 = e.Jc[r] * e.Jp[2] + e.Jc[NC + r] * e.Jp[5];
+                        const double z0 = w0 * Gm[0], z1 = w0 * Gm[1] + w1 * Gm[2], z2 = w0 * Gm[3] + w1 * Gm[4] + w2 * Gm[5];
+                        z[3 * r] = z0; z[3 * r + 1] = z1; z[3 * r + 2] = z2;
+                        if (pass == 0) accR[r] = fma(z2, qv[2], fma(z1, qv[1], fma(z0, qv[0], accR[r])));
+                    }
+                }
+                __syncwarp();
+                if (npass == 1) {
+                    for (int ts = 0; ts < nact; ++ts) {
+                        const double* zt = zs + ts * G.L * ZP;
+                        double fr[6];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) fr[i] = (i < R && fok[i]) ? zt[foff[i]] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            if (j < R) {                               // warp-uniform
+#pragma unroll
+                                for (int i = 0; i <= j; ++i) mma_f64_884(C[j * (j + 1) / 2 + i], fr[i], fr[j]);
+                            }
+                        }
+                    }
+                } else {
+                    // many row blocks (long tracks): the tiles of this pass are decoded at run time, two operand loads per MMA
+                    for (int ts = 0; ts < nact; ++ts) {
+                        const double* zt = zs + ts * G.L * ZP;
+                        int j = 0, s0 = pass * NTP;
+                        while ((j + 1) * (j + 2) / 2 <= s0) ++j;
+                        int i = s0 - j * (j + 1) / 2;
+#pragma unroll
+                        for (int q = 0; q < NTP; ++q) {
+                            if (s0 + q < ntile) {                      // warp-uniform
+                                const int ra = 8 * i + frow, pa = ra / NC, rb = 8 * j + frow, pb = rb / NC;
+                                const double fa = (ra < nrows && fk < 3) ? zt[pa * ZP + (ra - pa * NC) * 3 + fk] : 0.0;
+                                const double fb = (rb < nrows && fk < 3) ? zt[pb * ZP + (rb - pb * NC) * 3 + fk] : 0.0;
+                                mma_f64_884(C[q], fa, fb);
+                                if (++i > j) { i = 0; ++j; }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // the record of this (unit, pass): the accumulator tiles, row-major 8 x 8 each (a lane owns two adjacent columns), then the rhs rows
+            double* rp = records + (size_t)(un.rec + pass) * REC;
+#pragma unroll
+            for (int q = 0; q < NTP; ++q)
+                if (pass * NTP + q < ntile) { rp[q * 64 + 2 * lane] = C[q][0]; rp[q * 64 + 2 * lane + 1] = C[q][1]; }
+            if (pass == 0) {
+#pragma unroll
+                for (int r = 0; r < NC; ++r) rp[(size_t)NTP * 64 + r * 32 + lane] = slot_reduce(accR[r], G);
+            }
+        }
+    }
+    if (nbad) atomicAdd(bad_points, (double)nbad);
+    __threadfence();
+    __syncthreads();
+    // Merge: every entry of the CTA's partial S (and rhs) is owned by one thread, which adds up the contributions of the
+    // CTA's units in unit order -- parallel over the entries, fixed summation order, no read-modify-write conflicts.  Where a
+    // unit's record holds the entry follows from its camera set: positions ka, kb of the two cameras -> pair -> task -> lane.
+    // The unit descriptors go through shared memory (the Z areas are free now) and the record loads are issued eight units at
+    // a time (units that do not contain the entry read a zero), so the L2 round trips overlap.
+    {
+        constexpr int MU = 4;
+        const int cu0 = A.warp_unit0[blockIdx.x * nw], cu1 = A.warp_unit0[(blockIdx.x + 1) * nw];
+        const int ncu = cu1 - cu0;
+        // per unit: mask (2 ints), L, rec -> 4 ints; capacity of the Z area
+        int* s_units = reinterpret_cast<int*>(s_Z);
+        const int cap = (int)(((size_t)nw * (32 * ZP + PT_RC * 3) * sizeof(double)) / (4 * sizeof(int))) - 1;
+        for (int c0 = 0; c0 < max(ncu, 1); c0 += cap) {        // a CTA without units still writes its (zero) partial
+            const int nc_here = min(cap, ncu - c0);
+            __syncthreads();
+            for (int q = threadIdx.x; q < nc_here; q += blockDim.x) {
+                const PUnit un = A.units[cu0 + c0 + q];
+                s_units[4 * q] = (int)un.mask_lo; s_units[4 * q + 1] = (int)un.mask_hi; s_units[4 * q + 2] = un.L; s_units[4 * q + 3] = un.rec;
+            }
+            if (threadIdx.x == 0) { s_units[4 * nc_here] = 0; }
+            __syncthreads();
+            // one thread per (camera block, row) -- the NC entries of a row are contiguous in a task's record -- and one per
+            // camera for the rhs; MU units at a time: NC * MU independent loads in flight
+            const int nrow = (A.M * (A.M + 1) / 2) * NC;
+            for (int task = threadIdx.x; task < nrow + A.M; task += blockDim.x) {
+                double sum[NC];
+                const bool is_S = task < nrow;
+                int ja = 0, jb = 0, r_in = 0;
+                size_t t0;       // first entry of this thread in the partial vector
+                if (is_S) {
+                    int bq = task / NC;
+                    const int r = task - bq * NC;
+                    t0 = (size_t)bq * NC * NC + (size_t)r * NC;
+                    while (bq >= A.M - ja) { bq -= A.M - ja; ++ja; }
+                    jb = ja + bq;
+                    r_in = r;
+                } else {
+                    ja = jb = task - nrow;
+                    t0 = (size_t)nS + (size_t)ja * NC;
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) sum[c] = c0 == 0 ? 0.0 : partials[(t0 + c) * A.n_cta + blockIdx.x];
+                for (int q0 = 0; q0 < nc_here; q0 += MU) {
+                    double val[MU][NC];
+#pragma unroll
+                    for (int qq = 0; qq < MU; ++qq) {
+                        const int q = min(q0 + qq, nc_here - 1);
+                        const unsigned long long mask = ((unsigned long long)(unsigned)s_units[4 * q + 1] << 32) | (unsigned)s_units[4 * q];
+                        const int rec0 = s_units[4 * q + 3];
+                        const bool has = q0 + qq < nc_here && ((mask >> ja) & 1ull) && ((mask >> jb) & 1ull);
+                        const int ka = __popcll(mask & ((1ull << ja) - 1ull)), kb = __popcll(mask & ((1ull << jb) - 1ull));
+                        if (is_S) {
+                            // entry (row r_in of camera ka, column c of camera kb) of the unit's Gram matrix -> tile, element
+                            const int grow = ka * NC + r_in;
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                const int gcol = kb * NC + c;
+                                const int lo = min(grow, gcol), hi = max(grow, gcol);       // the Gram matrix is symmetric: upper triangle stored
+                                const int ti = lo >> 3, tj = hi >> 3, tile = tj * (tj + 1) / 2 + ti, ps = tile / NTP;
+                                const double* src = records + (size_t)(rec0 + ps) * REC + (tile - ps * NTP) * 64 + (lo & 7) * 8 + (hi & 7);
+                                val[qq][c] = has ? __ldcg(src) : 0.0;
+                            }
+                        } else {
+                            const double* src = records + (size_t)rec0 * REC + (size_t)NTP * 64 + ka;
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) val[qq][c] = has ? __ldcg(src + c * 32) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < MU; ++qq)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) sum[c] += val[qq][c];
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) partials[(t0 + c) * A.n_cta + blockIdx.x] = sum[c];
+            }
+        }
+    }
+}
+
 // Sum of the per-CTA Schur partials -> reduced camera system S (ns x ns column-major, symmetric, both triangles) and its
 // right-hand side:  S_jj' = [j == j'] (U_j + reg D_j^2) - sum,  rhs_j = -g_j + sum.  One warp per value.
 // add_diag: rank 0 only (the all-reduce over ranks then counts U and the damping once).

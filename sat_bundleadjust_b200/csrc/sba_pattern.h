@@ -64,9 +64,17 @@ inline int pattern_tile_tracks(int L) { return std::min(32 / L, PT_MAX_T); }
 
 struct PatternRun { int trk0, ntrk, L, pts_free; uint64_t mask; long long tile0; };
 
-// passes of the Schur kernel over a unit: a lane holds at most two (camera pair, row chunk) tasks at a time
+// passes of the Schur kernel over a unit: a lane holds at most two (camera pair, row chunk) tasks at a time.
+// rows_per_task == 0 selects the tensor-core kernel: the (L nc) x (L nc) Gram matrix of a track's Z rows is cut into 8 x 8
+// tiles (upper triangle, enumerated column by column: tile (i, j <= ...) has number j (j + 1) / 2 + i), PT_MMA_TILES per pass.
+constexpr int PT_MMA_TILES = 21;       // tiles of a pass = accumulator fragments of a lane (2 doubles each): R <= 6 row blocks in one pass
+inline int pattern_mma_row_blocks(int L, int nc) { return (L * nc + 7) / 8; }
 inline int pattern_schur_passes(int L, int nc, int rows_per_task)
 {
+    if (rows_per_task == 0) {
+        const int R = pattern_mma_row_blocks(L, nc);
+        return (R * (R + 1) / 2 + PT_MMA_TILES - 1) / PT_MMA_TILES;
+    }
     const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
     return (ntask + 63) / 64;
 }
@@ -77,6 +85,10 @@ inline int pattern_tile_cost(int L, int nc, int rows_per_task, bool schur)
 {
     if (!schur) return 8;
     const int T = pattern_tile_tracks(L);
+    if (rows_per_task == 0) {          // evaluation once per pass + per track R fragment loads and one MMA per tile
+        const int R = pattern_mma_row_blocks(L, nc), nt = R * (R + 1) / 2, np = (nt + PT_MMA_TILES - 1) / PT_MMA_TILES;
+        return np * 24 + (T * (np == 1 ? R + nt : 3 * nt)) / 4;
+    }
     const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
     const int npar = ntask <= 16 ? 32 / ntask : 1;
     const int rounds = (T + npar - 1) / npar;

@@ -61,6 +61,7 @@ static int pt_set_smem_attributes(const sba_problem* p)
     SBA_CUDA(cudaFuncSetAttribute(k_pt_assemble<MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt_smem_assemble(p))); \
     SBA_CUDA(cudaFuncSetAttribute(k_pt_jvp1<MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt_smem_jvp1(p)));   \
     SBA_CUDA(cudaFuncSetAttribute(k_pt_schur<MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt_smem_schur(p))); \
+    SBA_CUDA(cudaFuncSetAttribute(k_pt_schur_mma<MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt_smem_schur(p))); \
     SBA_CUDA(cudaFuncSetAttribute(k_pt_backsub<MODEL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt_smem_backsub(p)))
     PT_DISPATCH(p, L);
 #undef L
@@ -154,9 +155,14 @@ static int pt_run_schur(sba_problem* p, int loss, double f_scale)
     SBA_CUDA(cudaMemsetAsync(p->scal + SC_BAD_POINTS, 0, 2 * sizeof(double), p->stream));
     const CommFused cf = comm_fused(p, (long long)nS + ns);
 #define L(MODEL, NC)                                                                                                        \
-    k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                                   \
-        pat_view(p, 2), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
-        p->scal + SC_BAD_POINTS);                                                                                            \
+    if (p->pt_schur_mma)                                                                                                     \
+        k_pt_schur_mma<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                           \
+            pat_view(p, 2), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
+            p->scal + SC_BAD_POINTS);                                                                                        \
+    else                                                                                                                     \
+        k_pt_schur<MODEL, NC><<<p->pt_n_cta, PT_THREADS_SCHUR, pt_smem_schur(p), p->stream>>>(                               \
+            pat_view(p, 2), p->x, p->camrec, p->V, p->g, p->dsq, (const double2*)p->osc, p->scal, ns, p->pt_records, p->pt_partials, \
+            p->scal + SC_BAD_POINTS);                                                                                        \
     SBA_TRY(check_launch(p));                                                                                                \
     k_pt_reduce_schur<NC><<<std::min(PT_CTAS, (nS + ns + 15) / 16), 512, 0, p->stream>>>(                                    \
         p->pt_partials, p->pt_n_cta, p->M, p->n_cam_fix, p->camsys, p->dsqc, p->scal, p->rank == 0, p->S, cf, p->counters + 6)
@@ -420,7 +426,8 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
     const size_t nv = (size_t)nc * (nc + 1) / 2 + nc, nS = (size_t)nc * nc * ((size_t)M * (M + 1) / 2);
     SBA_TRY(dev_alloc(p, &p->pt_partials, std::max((size_t)M * nv + 1, nS + ns) * lay.n_cta));
-    SBA_TRY(dev_alloc(p, &p->pt_records, (size_t)std::max(1, lay.narrow.n_records) * (2 * PT_RC * nc + nc) * 32));
+    SBA_TRY(dev_alloc(p, &p->pt_records, (size_t)std::max(1, lay.narrow.n_records) *
+                                             (p->pt_schur_mma ? (size_t)PT_MMA_TILES * 64 + nc * 32 : (size_t)(2 * PT_RC * nc + nc) * 32)));
     SBA_TRY(dev_alloc(p, &p->red_partials, (size_t)std::max(NUM_SMS * 16, lay.n_cta + 1) * 8));
     SBA_TRY(dev_alloc(p, &p->counters, 16));
     SBA_CUDA(cudaMemsetAsync(p->counters, 0, 16 * sizeof(unsigned), s));

@@ -366,3 +366,26 @@ def test_reduced_camera_system(built, model, corr, loss, reg):
     assert np.allclose(S, S.T, rtol=0, atol=1e-12 * scale)
     n = np.where(~used)[0]                                           # unused slots: identity rows, zero right-hand side
     assert np.array_equal(S[np.ix_(n, n)], np.eye(n.size)) and not S[np.ix_(n, u)].any() and not rhs[n].any()
+
+
+@pytest.mark.parametrize("model,corr,n_cam,p_vis", [("perspective", ["R", "T"], 10, 0.5), ("affine", ["R"], 6, 0.7),
+                                                    ("perspective", ["R", "T"], 12, 0.85)])
+def test_schur_kernel_variants(built, model, corr, n_cam, p_vis, monkeypatch):
+    """
+    The two Schur kernels of the pattern engine -- DFMA task kernel (default) and the FP64 tensor-core variant (SBA_PT_SCHUR=mma,
+    m8n8k4 DMMA Gram tiles) -- form the same reduced camera system: S and rhs equal to rounding, including tracks long enough
+    for the multi-pass path of the tensor-core kernel (n_cam 12, p_vis 0.85: up to 12 observations x 6 = 72 rows > 48).
+    """
+    sc = synth.make_scene(n_cam=n_cam, n_tracks=4000, p_vis=p_vis, cam_model=model, seed=5)
+    p = synth.scene_to_params(sc, corr)
+    x0 = initial_vars(p)
+    out = {}
+    for variant in ("fma", "mma"):
+        monkeypatch.setenv("SBA_PT_SCHUR", variant)
+        with DeviceProblem(p) as prob:
+            assert prob.engine == "pattern"
+            out[variant] = prob.reduced_system(x0, "soft_l1", 1.0, 0.25)
+    S0, r0 = out["fma"]
+    S1, r1 = out["mma"]
+    assert np.abs(S0).max() > 0 and np.abs(S1 - S0).max() <= 1e-12 * np.abs(S0).max()
+    assert np.abs(r1 - r0).max() <= 1e-12 * np.abs(r0).max()
