@@ -9,6 +9,8 @@ timeout 600 python bench.py --workload 5m --steps 10 --warmup 3 --no-cpu-baselin
 timeout 600 python bench.py --workload cfg3full --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_cfg3full.json 2> gpurun_out/r02_bench_cfg3full.err; echo "cfg3full exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_under_ncu.json 2> /dev/null; echo "ncu list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_pt_|k_chol_fused' -s 8 -c 9 -o gpurun_out/r02_full_1m -f python tools/profile_iter.py 1m 3 > gpurun_out/ncu_full_1m.log 2>&1; echo "ncu full exit $?"
+(timeout 600 compute-sanitizer --tool memcheck python tools/profile_iter.py small 3; SBA_ENGINE=generic timeout 600 compute-sanitizer --tool memcheck python tools/profile_iter.py small 3; timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_triangulate.py -m gpu -x -q -k "edge or golden or oracle-perspective-10") > gpurun_out/r02_memcheck_raw.log 2>&1; grep -h "ERROR SUMMARY\|passed\|failed\|engine\|Error" gpurun_out/r02_memcheck_raw.log | cut -c1-200 > gpurun_out/r02_memcheck.log; cat gpurun_out/r02_memcheck.log
+SBA_CHOL_CLK=1 python tools/chol_time.py 30 60 90 120 300 1800 > gpurun_out/r02_chol_time.log 2>&1; tail -14 gpurun_out/r02_chol_time.log | cut -c1-200
 python - <<'PY'
 import json
 for f in ("r02_bench_n1", "r02_bench_5m", "r02_bench_cfg3full"):

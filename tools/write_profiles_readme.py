@@ -1,0 +1,157 @@
+"""
+Writes the round-2 part of profiles/README.md from the tracked artefacts under profiles/ (bench JSON lines, the ncu
+selected-metrics CSV, the ncu launch list).  The round-1 text is kept below it.  Usage: python tools/write_profiles_readme.py
+"""
+import collections
+import csv
+import json
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(ROOT, "profiles")
+MARK = "<!-- round 1 below -->"
+
+
+def load(name):
+    path = os.path.join(PROF, name)
+    if not os.path.exists(path) or os.path.getsize(path) == 0:
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+def short(name):
+    return re.sub(r"^void ", "", re.sub(r"\(.*", "", name)).replace("sba::", "")
+
+
+def phases(d):
+    return ", ".join("%s %.1f" % (k, 1e3 * v) for k, v in d["phases_ms_per_iteration"].items() if v > 0)
+
+
+def bench_line(tag, d):
+    e = d["e2e"]
+    return "| %s | %d | %s | %s | %.3f | %.3g | %.3g | %.1f | %d |" % (
+        tag, d["n_gpus"], "{:,}".format(d["config"]["n_obs"]).replace(",", " "), d["config"]["engine"], d["ms_per_step"], d["value"],
+        e["value"], 1e3 * e["wall_s"], e["iterations"])
+
+
+def main():
+    out = ["# profiles — round 2", ""]
+    out += ["All numbers were taken on B200s (sm_100a, 148 SMs) through `gpurun`; clocks and throttle reasons sampled during the timed",
+            "region are in every JSON line (`clocks`).  ncu figures are per launch, cold cache, `--clock-control none`: their SHARE of",
+            "the iteration is what is comparable with the CUDA-event timings of `bench.py`, not the absolute values.", ""]
+    out += ["| file | what |", "|---|---|",
+            "| `r02_bench_n1.json` | `python bench.py` (default workload `1m` = the metric's size, secondary line config 2) |",
+            "| `r02_bench_reference_n1.json` | `python bench.py --impl reference` (scipy TRF on the oracle port, same box) |",
+            "| `r02_bench_n2.json`, `r02_bench_n4.json`, `r02_bench_n8.json` | the same under torchrun on 2 / 4 / 8 GPUs (weak scaling: `1m` per GPU) |",
+            "| `r02_bench_5m.json`, `r02_bench_cfg3full.json` | 5e6 observations on one GPU: 10 views (pattern engine) and BASELINE config 3 whole (50 views, generic engine) |",
+            "| `r02_bench_cfg3_n8.json`, `r02_bench_cfg4_n8.json` | BASELINE configs 3 and 4 on 8 GPUs (config 4: 300 views, 3.0e7 observations, PCG) |",
+            "| `r02_bench_rpc.json` | `bench.py --workload rpc` (BASELINE config 5: RPC projection / localisation / triangulation / refit, 300 cameras) |",
+            "| `r02_dist_check_n2.log`, `r02_dist_check_n8.log` | sharded solve against the single-GPU solve (`tools/dist_check.py --tight`) |",
+            "| `r02_launches_bench.csv` | ncu launch list of the bench command itself (`--metrics gpu__time_duration.sum`) |",
+            "| `r02_ncu_1m_selected_metrics.csv` | selected metrics of one `ncu --set full --import-source on` capture per kernel of the `1m` workload (`tools/summarize_profiles.py r02`) |",
+            "| `r02_sass_pattern_kernels.txt` | `cuobjdump -sass` excerpts of the four pattern kernels (DFMA / LDS / SHFL mix, no local memory in the inner loops) |",
+            "| `r02_fp64_peak.json`, `r02_dmma_issue_rate.txt` | measured FP64 peaks (`tools/fp64_peak.cu`: DFMA 33.9, DMMA 37.1 TFLOP/s) and DMMA issue rate vs occupancy (`tools/dmma_lat.cu`) |",
+            "| `r02_memcheck.log` | `compute-sanitizer --tool memcheck` over a solve of both engines and the triangulation kernels |", ""]
+    b1 = load("r02_bench_n1.json")
+    if b1:
+        e, r, c = b1["e2e"], b1["roofline"], b1["cpu_baseline"]
+        out += ["## bench.py, N = 1 (default: %s)" % b1["config"]["workload"], ""]
+        out += ["* **%.3f ms per trust-region iteration = %.4g observation-iterations/s** (%d observations, engine `%s`, %d timed iterations, one CUDA-event"
+                % (b1["ms_per_step"], b1["value"], b1["config"]["n_obs"], b1["config"]["engine"], b1["steps"]),
+                "  pair per iteration, 256 MiB L2 flush between iterations); SM clock %s MHz, throttle reasons %s." % (b1["clocks"]["sm_mhz"], b1["clocks"]["reasons"]),
+                "* per-phase device time (us per iteration): %s" % phases(b1),
+                "* end to end through `ba_core.run_ba_optimization` (host numpy buffers in, x and both error vectors out, mean of %d calls): **%.4g obs-it/s**,"
+                % (e["calls"], e["value"]),
+                "  %.1f ms per call for %d iterations / %d evaluations (%s); first call of the process %.1f ms."
+                % (1e3 * e["wall_s"], e["iterations"], e["nfev"], ", ".join("%s %.1f ms" % (k, 1e3 * v) for k, v in e["wall_breakdown_s"].items() if v > 1e-4),
+                   1e3 * e["first_call_wall_s"]),
+                "* CPU baseline in the same line (%s, %d core): %.3g obs-it/s." % (c["kind"], c["cores"], c["value"])]
+        ref = load("r02_bench_reference_n1.json")
+        if ref:
+            out += ["* reference arm (`--impl reference`): %.3g obs-it/s = %.2f s per iteration on the same host." % (ref["value"], ref["ms_per_step"] / 1e3)]
+        fp = r.get("fp64") or {}
+        out += ["* roofline of the dominant phase (%s): %.0f GB/s of algorithmic bytes against %.0f GB/s measured HBM = **%.3f**; ncu DRAM traffic of that kernel %s MB per launch;"
+                % (r["kernel"], r["achieved"], r["peak"], r["frac"], "%.1f" % (r["traffic"] / 1e6) if r.get("traffic") else "n/a"),
+                "  FP64: %s" % (("%.2f TFLOP/s of %.2f measured DFMA peak = **%.3f**, FP64 pipe busy %.1f %% of cycles" % (
+                    fp["achieved_tflops"], fp["peak_tflops"], fp["frac"], 100 * (r.get("fp64_pipe_frac") or 0))) if fp else "n/a"),
+                "  Jacobian/assembly pass: %.0f GB/s = %.3f of HBM (%.1f us per pass)." % (r["jacobian_assembly"]["achieved"], r["jacobian_assembly"]["frac"],
+                                                                                         1e3 * r["jacobian_assembly"]["ms"]), ""]
+        for s2 in b1.get("secondary") or []:
+            out += ["Secondary line — %s: %.3f ms per iteration, %.4g obs-it/s, e2e %.4g; phases (us): %s" % (
+                s2["workload"], s2["ms_per_step"], s2["value"], s2["e2e"]["value"], phases(s2)), ""]
+    # ncu per-kernel table
+    path = os.path.join(PROF, "r02_ncu_1m_selected_metrics.csv")
+    if os.path.exists(path):
+        rows = list(csv.DictReader(open(path)))
+        out += ["## ncu, one capture per kernel (`1m` workload)", "",
+                "| kernel | us | DRAM rd+wr MB | regs | grid x block | FP64 pipe % | issue active % | warp instr (M) | FP64 Gflop | top stalls (cycles per issue) |",
+                "|---|---:|---:|---:|---|---:|---:|---:|---:|---|"]
+        for r in rows:
+            out.append("| `%s` | %.1f | %.1f | %s | %s x %s | %.1f | %.1f | %.2f | %.3f | %s |" % (
+                r["kernel"], float(r["time us"]), float(r["dram rd MB"]) + float(r["dram wr MB"]), r["regs"], r["grid"], r["block"],
+                float(r["fp64 pipe %"]), float(r["issue active %"]), float(r["warp instr"]) / 1e6, float(r["fp64 Gflop"]), r["top stalls (warp cycles per issue)"]))
+        out += [""]
+    path = os.path.join(PROF, "r02_launches_bench.csv")
+    if os.path.exists(path):
+        lines = [l for l in open(path) if not l.startswith("==")]
+        agg = collections.OrderedDict()
+        for r in csv.DictReader(lines):
+            a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0])
+            a[0] += 1
+            a[1] += float(r["Metric Value"]) / 1e3
+        tot = sum(v[1] for v in agg.values())
+        out += ["## launch list of the bench command (first 600 launches under ncu: set-up, warm-up and timed iterations)", "",
+                "| kernel | launches | mean us | share of kernel time |", "|---|---:|---:|---:|"]
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
+            out.append("| `%s` | %d | %.1f | %.1f%% |" % (k, v[0], v[1] / v[0], 100 * v[1] / tot))
+        out += [""]
+    # scaling
+    runs = [(n, load("r02_bench_n%d.json" % n)) for n in (1, 2, 4, 8)]
+    runs = [(n, d) for n, d in runs if d]
+    if len(runs) > 1:
+        base = runs[0][1]
+        out += ["## Scaling (weak: `1m` per GPU; exchanges over NVLink peer memory inside the producing kernels; max over ranks of CUDA-event times)", "",
+                "| GPUs | observations | ms / iteration | obs-it/s | weak-scaling efficiency | e2e obs-it/s | e2e ms / call | phases (us) |", "|---:|---:|---:|---:|---:|---:|---:|---|"]
+        for n, d in runs:
+            out.append("| %d | %d | %.4f | %.4g | %.0f%% | %.4g | %.1f | %s |" % (
+                n, d["config"]["n_obs"], d["ms_per_step"], d["value"], 100 * d["value"] / (n * base["value"]), d["e2e"]["value"], 1e3 * d["e2e"]["wall_s"], phases(d)))
+        out += [""]
+    others = [("5e6 observations, 10 views, one GPU", "r02_bench_5m.json"), ("BASELINE config 3 whole on one GPU", "r02_bench_cfg3full.json"),
+              ("BASELINE config 3 on 8 GPUs", "r02_bench_cfg3_n8.json"), ("BASELINE config 4 on 8 GPUs (PCG)", "r02_bench_cfg4_n8.json")]
+    rows = [(t, load(f)) for t, f in others]
+    rows = [(t, d) for t, d in rows if d]
+    if rows:
+        out += ["## Other sizes", "", "| workload | GPUs | observations | engine | ms / iteration | obs-it/s | e2e obs-it/s | e2e ms / call | iterations |", "|---|---:|---:|---|---:|---:|---:|---:|---:|"]
+        out += [bench_line(t, d) for t, d in rows]
+        out += [""]
+        for t, d in rows:
+            out += ["* %s — phases (us per iteration): %s" % (t, phases(d))]
+        out += [""]
+    rpc = load("r02_bench_rpc.json")
+    if rpc:
+        out += ["## RPC helpers (BASELINE config 5)", "", "| operation | GPU | CPU (compiled reference / oracle, one core) |", "|---|---:|---:|"]
+        for k, v in rpc["operations"].items():
+            out.append("| %s | %.3g %s | %.3g |" % (k, v["value"], v["unit"], v.get("cpu_baseline", float("nan"))))
+        out += ["", "Projection kernel: %.2f TFLOP/s of cubic evaluation = %.3f of the measured DFMA peak." % (
+            rpc["roofline"]["fp64"]["achieved_tflops"], rpc["roofline"]["fp64"]["frac"]), ""]
+    out += ["## Fixed cost per launch and the small Cholesky", "",
+            "`SBA_PT_SKIP=1` (the kernels skip their tile loops; `tools/fixed_cost.py`): K1 8 us, reduce 6-8 us, K2 11-13 us, K3 ~30 us (record merge), K4 15 us of",
+            "the per-iteration time are prologue (camera tables into shared memory), grid-wide reduction tails and launch latency.",
+            "`SBA_CHOL_CLK=1 python tools/chol_time.py 60`: stage clocks of `k_chol_fused<2>` at n = 60 (cycles): load 2152 | panel 0: block 9534, rows 8877,",
+            "trailing 4981 | panel 1: block 9685, rows 5368 | back-substitution 7241 | total 47985 = 30.6 us (round 1: 52 k cycles); the 32 dependent pivots of a",
+            "block cost ~300 cycles each (shuffle -> MUFU.RSQ64H -> cubic step -> scale -> shuffle -> fma).", ""]
+    text = "\n".join(out) + "\n"
+    path = os.path.join(PROF, "README.md")
+    old = open(path).read() if os.path.exists(path) else ""
+    if MARK in old:
+        old = old[old.index(MARK) + len(MARK):].lstrip("\n")
+    old = re.sub(r"^# profiles — round 1", "# round 1", old)
+    with open(path, "w") as f:
+        f.write(text + "\n" + MARK + "\n\n" + old)
+    print("wrote", path, len(text), "bytes of round-2 text")
+
+
+if __name__ == "__main__":
+    main()
