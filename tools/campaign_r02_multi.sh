@@ -17,3 +17,4 @@ for f in gpurun_out/r02_bench_n$N.json gpurun_out/r02_bench_cfg3_n$N.json gpurun
   [ -s $f ] && python -c "
 import json,sys; d=json.load(open('$f')); print('$f', d['n_gpus'], d['config']['n_obs'], d['config']['engine'], 'value %.4g' % d['value'], 'ms/it %.4f' % d['ms_per_step'], 'e2e %.4g' % d['e2e']['value'], 'wall %.3f' % d['e2e']['wall_s'], d['e2e']['iterations'], d['e2e'].get('wall_breakdown_s')); print({k: round(v,4) for k,v in d['phases_ms_per_iteration'].items()})"
 done
+exit 0
