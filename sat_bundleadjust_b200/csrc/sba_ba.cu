@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -850,6 +851,14 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         build_pattern_layout(cam.data(), track_ptr.data(), K, M, N, p->n_pts_fix, PT_CTAS, PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, nc, p->pt_schur_mma ? 0 : PT_RC,
                              lay);
         stamp("pattern layout");
+        // A tile holds tracks with ONE camera set: when the visibility patterns are too diverse (many cameras, random visibility)
+        // the tiles stay mostly empty and the generic engine, which packs arbitrary tracks into a warp, is the faster one
+        // (it costs ~1.9x the pattern engine at full tiles).  Small problems keep the pattern engine; SBA_ENGINE=pattern forces it.
+        const char* eng = getenv("SBA_ENGINE");
+        if (lay.ok && K >= 65536 && lay.fill < 0.5 && !(eng && std::strcmp(eng, "pattern") == 0)) {
+            lay.ok = false;
+            lay.why = "visibility patterns too diverse (tile fill " + std::to_string(lay.fill) + ")";
+        }
         if (lay.ok) {
             const int rc = pattern_create(p, d, hidx, lay);
             stamp("pattern uploads + state");

@@ -57,6 +57,7 @@ struct PatternLayout {
     int n_cta = 0, Lmax = 0, n_runs = 0;
     int n_frozen_tracks = 0;           // frozen tracks with observations = internal tracks [0, n_frozen_tracks)
     long long n_tiles = 0;
+    double fill = 0.0;                 // observations per lane slot of the tiles (K / (32 n_tiles)): how well tracks share their camera sets
 };
 
 constexpr int PT_MAX_T = 16;           // track slots per tile (bounds the per-warp staging buffers)
@@ -220,6 +221,7 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     }
     out.n_runs = (int)runs.size();
     out.n_tiles = tiles;
+    out.fill = tiles > 0 ? (double)K / (32.0 * (double)tiles) : 0.0;
     out.n_cta = n_cta;
     if (runs.empty()) { out.why = "no observations"; return; }
     assign_pattern_units(runs, out.track_ptr, n_cta, warps_light, nc, rows_per_task, false, out.light);

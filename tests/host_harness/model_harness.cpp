@@ -99,7 +99,7 @@ int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, 
     PatternLayout L;
     build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, warps + 8, warps, std::max(1, warps - 4), 6, 3, L);
     sizes[0] = L.ok ? 1 : 0; sizes[1] = (int)L.wide.units.size(); sizes[2] = 0; sizes[3] = L.n_frozen_tracks;
-    sizes[4] = (int)L.n_tiles; sizes[5] = L.n_runs;
+    sizes[4] = (int)L.n_tiles; sizes[5] = L.n_runs; sizes[6] = (int)(1000.0 * L.fill);
     if (!L.ok || !trk_new2old) return 0;
     std::copy(L.trk_new2old.begin(), L.trk_new2old.end(), trk_new2old);
     for (int t = 0; t < N; ++t)          // the observation permutation the device derives (k_pt_build_obs)

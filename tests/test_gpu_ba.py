@@ -389,3 +389,28 @@ def test_schur_kernel_variants(built, model, corr, n_cam, p_vis, monkeypatch):
     S1, r1 = out["mma"]
     assert np.abs(S0).max() > 0 and np.abs(S1 - S0).max() <= 1e-12 * np.abs(S0).max()
     assert np.abs(r1 - r0).max() <= 1e-12 * np.abs(r0).max()
+
+
+def test_engine_choice_follows_tile_fill(built, monkeypatch):
+    """
+    Tracks that rarely share their camera set (18 views seen with probability 0.3: tile fill ~0.2) go to the generic engine, which is
+    the faster one there (tools/engine_choice.py: 0.55 against 1.03 ms per iteration at 5e5 observations); SBA_ENGINE=pattern still
+    forces the pattern engine, and both form the same reduced camera system.
+    """
+    sc = synth.make_scene(n_cam=18, n_tracks=14000, p_vis=0.3, cam_model="perspective", seed=3)
+    p = synth.scene_to_params(sc, ["R", "T"])
+    assert p.n_obs >= 65536
+    x0 = initial_vars(p)
+    monkeypatch.delenv("SBA_ENGINE", raising=False)
+    with DeviceProblem(p) as prob:
+        assert prob.engine == "generic"
+        S0, r0 = prob.reduced_system(x0, "soft_l1", 1.0, 0.25)
+    monkeypatch.setenv("SBA_ENGINE", "pattern")
+    with DeviceProblem(p) as prob:
+        assert prob.engine == "pattern"
+        S1, r1 = prob.reduced_system(x0, "soft_l1", 1.0, 0.25)
+    assert np.abs(S1 - S0).max() <= 1e-8 * np.abs(S0).max() and np.abs(r1 - r0).max() <= 1e-8 * np.abs(r0).max()
+    sc = synth.make_scene(n_cam=10, n_tracks=14000, p_vis=0.5, cam_model="perspective", seed=3)
+    monkeypatch.delenv("SBA_ENGINE", raising=False)
+    with DeviceProblem(synth.scene_to_params(sc, ["R", "T"])) as prob:
+        assert prob.engine == "pattern"

@@ -392,7 +392,7 @@ def _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=0, n_cta=148, warps=16):
     cam = np.ascontiguousarray(cam_ind, dtype=np.int32)
     tp = np.ascontiguousarray(np.searchsorted(pts_ind, np.arange(N + 1), side="left"), dtype=np.int32)
     K = cam.size
-    sizes = (ctypes.c_int * 6)()
+    sizes = (ctypes.c_int * 8)()
     null = ctypes.cast(None, ip)
     args = [cam.ctypes.data_as(ip), tp.ctypes.data_as(ip), ctypes.c_longlong(K), M, N, n_pts_fix, n_cta, warps, sizes]
     lib.hh_pattern_layout(*args, *([null] * 5))
@@ -401,7 +401,7 @@ def _pattern_layout(cam_ind, pts_ind, M, N, n_pts_fix=0, n_cta=148, warps=16):
     out = {"trk_new2old": np.zeros(N, np.int32), "obs_new2old": np.zeros(K, np.int32), "track_ptr": np.zeros(N + 1, np.int32),
            "units": np.zeros((sizes[1], 8), np.int32), "warp_unit0": np.zeros(n_cta * warps + 1, np.int32)}
     lib.hh_pattern_layout(*args, *[out[k].ctypes.data_as(ip) for k in ("trk_new2old", "obs_new2old", "track_ptr", "units", "warp_unit0")])
-    out["n_frozen"], out["n_tiles"], out["n_runs"] = sizes[3], sizes[4], sizes[5]
+    out["n_frozen"], out["n_tiles"], out["n_runs"], out["fill"] = sizes[3], sizes[4], sizes[5], sizes[6] / 1000.0
     return out
 
 
@@ -463,6 +463,22 @@ def test_pattern_layout_rejects(built):
     # cameras not ascending inside a track / a track longer than 32 observations -> generic engine
     assert _pattern_layout([1, 0], [0, 0], 2, 1) is None
     assert _pattern_layout(np.arange(40), np.zeros(40, int), 40, 1) is None
+
+
+def test_pattern_layout_tile_fill(built):
+    """Tile fill = observations per lane slot: high when many tracks share a camera set (10 views), low when nearly every track has
+    its own (50 views seen with probability 0.1) -- sba_problem_create then prefers the generic engine (fill < 0.5, >= 65536 obs)."""
+    rng = np.random.default_rng(0)
+    fills = {}
+    for M, N, p_vis in ((10, 20000, 0.5), (50, 20000, 0.1)):
+        vis = rng.random((N, M)) < p_vis
+        vis[vis.sum(axis=1) < 2, :2] = True
+        pts_ind, cam_ind = np.nonzero(vis)
+        lay = _pattern_layout(cam_ind, pts_ind, M, N)
+        assert lay is not None
+        fills[M] = lay["fill"]
+        assert abs(lay["fill"] - cam_ind.size / (32.0 * lay["n_tiles"])) < 2e-3
+    assert fills[10] > 0.7 and fills[50] < 0.3, fills
 
 
 def test_sparse_scene_matches_dense_packing():
