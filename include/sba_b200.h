@@ -56,6 +56,10 @@ typedef struct sba_problem_desc {
        unknowns shared by all cameras.  The device vector keeps n_params slots per camera: the shared values live in
        camera 0's slots, the same slots of cameras 1..M-1 are unused and must be 0.  Requires n_cam_fix == 0. */
     int32_t n_common;
+    /* Choices that sba_problem_create otherwise makes from the problem itself (0 = automatic).  The ranks of a multi-GPU solve must
+       agree on both (their exchanges differ): the distributed driver creates with 0, compares, and re-creates with a common value. */
+    int32_t engine;           /* 1: pattern engine (fails if it does not apply), 2: generic engine */
+    int32_t solver;           /* 1: dense Cholesky of the reduced camera system, 2: matrix-free PCG */
 } sba_problem_desc;
 
 /* Solver options = the reference's ls_params (bundle_adjust/ba_core.py:222-241) + scipy's gtol default */
@@ -132,6 +136,8 @@ int64_t sba_problem_num_vars(const sba_problem *p);
  * system of at most 132 unknowns, n_params <= 6: fused passes, nothing per-observation stored), 0 = generic (static pair
  * lists, any size up to 4096 camera unknowns).  SBA_ENGINE=generic in the environment forces 0. */
 int sba_problem_engine(const sba_problem *p);
+/* Solver of the reduced camera system chosen for this problem: 0 = dense Cholesky, 1 = block-Jacobi PCG. */
+int sba_problem_solver(const sba_problem *p);
 
 /* Replaces ba_core.fun(v, p) (ba_core.py:157-183): x (n) -> weighted residuals r (2K), interleaved.
  * Also returns 0.5*sum(rho(r)) for the given loss in *cost (may be NULL). */

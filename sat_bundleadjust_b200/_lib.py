@@ -30,7 +30,8 @@ class ProblemDesc(ctypes.Structure):
                 ("n_cam_fix", ctypes.c_int32), ("n_pts_fix", ctypes.c_int32),
                 ("cam_ind", c_int64_p), ("pts_ind", c_int64_p), ("pts2d", c_double_p), ("pts2d_w", c_double_p),
                 ("cam_params", c_double_p), ("rpc_coefs", c_double_p), ("rpc_float32", ctypes.c_int32),
-                ("rank", ctypes.c_int32), ("world_size", ctypes.c_int32), ("n_common", ctypes.c_int32)]
+                ("rank", ctypes.c_int32), ("world_size", ctypes.c_int32), ("n_common", ctypes.c_int32),
+                ("engine", ctypes.c_int32), ("solver", ctypes.c_int32)]
 
 
 class SolveOpts(ctypes.Structure):
@@ -62,7 +63,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 # every symbol include/sba_b200.h declares
 EXPORTED_SYMBOLS = [
     "sba_last_error", "sba_version", "sba_problem_create", "sba_problem_destroy", "sba_release_cached_memory", "sba_problem_set_allreduce",
-    "sba_problem_num_vars", "sba_problem_engine", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve", "sba_solve_errors",
+    "sba_problem_num_vars", "sba_problem_engine", "sba_problem_solver", "sba_residuals", "sba_jacobian_blocks", "sba_normal_blocks", "sba_reduced_system", "sba_solve", "sba_solve_errors",
     "sba_solve_device", "sba_assemble_device", "sba_tr2d", "sba_rpc_projection", "sba_rpc_projection_ecef",
     "sba_rpc_localization", "sba_rpc_throughput", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",
@@ -94,6 +95,7 @@ def load():
     lib.sba_problem_num_vars.argtypes = [vp]
     lib.sba_problem_num_vars.restype = ctypes.c_int64
     lib.sba_problem_engine.argtypes = [vp]
+    lib.sba_problem_solver.argtypes = [vp]
     lib.sba_residuals.argtypes = [vp, c_double_p, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p]
     lib.sba_jacobian_blocks.argtypes = [vp, c_double_p, c_double_p, c_double_p]
     lib.sba_normal_blocks.argtypes = [vp, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_double_p, c_double_p]

@@ -837,7 +837,8 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     };
     // --- indices: int64 -> int32, track offsets, camera-major order, chunks, warp tiles (host, O(K), a few threads) ---
     HostIndex hidx;
-    const bool try_pattern = pattern_engine_applicable(p);
+    const bool try_pattern = d->engine != 2 && !(p->use_pcg && d->engine == 0) && pattern_engine_applicable(p, d->engine == 1);
+    if (d->engine == 1 && !try_pattern) { set_error("the pattern engine does not apply to this problem (size, n_params or shared calibration)"); return SBA_E_INVALID; }
     int irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx, try_pattern);
     if (irc == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
     if (irc == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
@@ -855,7 +856,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
         // the tiles stay mostly empty and the generic engine, which packs arbitrary tracks into a warp, is the faster one
         // (it costs ~1.9x the pattern engine at full tiles).  Small problems keep the pattern engine; SBA_ENGINE=pattern forces it.
         const char* eng = getenv("SBA_ENGINE");
-        if (lay.ok && K >= 65536 && lay.fill < 0.5 && !(eng && std::strcmp(eng, "pattern") == 0)) {
+        if (lay.ok && K >= 65536 && lay.fill < 0.5 && d->engine != 1 && !(eng && std::strcmp(eng, "pattern") == 0)) {
             lay.ok = false;
             lay.why = "visibility patterns too diverse (tile fill " + std::to_string(lay.fill) + ")";
         }
@@ -865,6 +866,7 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
             return rc;
         }
         if (timing) fprintf(stderr, "[sba create] pattern engine not applicable: %s\n", lay.why.c_str());
+        if (d->engine == 1) { set_error(("the pattern engine does not apply: " + lay.why).c_str()); return SBA_E_INVALID; }
         irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx);       // the generic engine needs the camera-major tables too
         if (irc) { set_error("cam_ind / pts_ind invalid"); return SBA_E_INVALID; }
     }
@@ -1047,6 +1049,9 @@ extern "C" int sba_problem_create(sba_problem** out, const sba_problem_desc* d, 
         if (std::strcmp(e, "pcg") == 0) use_pcg = true;
         if (std::strcmp(e, "dense") == 0) use_pcg = false;
     }
+    if (d->solver == 1) use_pcg = false;
+    if (d->solver == 2) use_pcg = true;
+    if (d->engine < 0 || d->engine > 2 || d->solver < 0 || d->solver > 2) { set_error("bad engine / solver choice"); return SBA_E_INVALID; }
     if (use_pcg && d->n_common > 0) use_pcg = false;      // the shared-calibration border is only folded on the dense path
     if (!use_pcg && (double)d->n_cam * d->n_pts > 1.5e9) { set_error("unsupported size: n_cam * n_pts > 1.5e9 needs the PCG path (no shared calibration, SBA_SOLVER unset)"); return SBA_E_INVALID; }
     if (!use_pcg && ns_all > 4096) { set_error("unsupported size: more than 4096 camera unknowns need the PCG path (no shared calibration, SBA_SOLVER unset)"); return SBA_E_INVALID; }
@@ -1082,6 +1087,7 @@ extern "C" int sba_problem_set_allreduce(sba_problem* p, sba_allreduce_fn fn, vo
 
 extern "C" int64_t sba_problem_num_vars(const sba_problem* p) { return p ? p->n : -1; }
 extern "C" int sba_problem_engine(const sba_problem* p) { return p ? p->engine : -1; }
+extern "C" int sba_problem_solver(const sba_problem* p) { return p ? (p->use_pcg ? 1 : 0) : -1; }
 
 // Multi-GPU exchange over peer memory: every rank exports the IPC handle of its symmetric buffer ...
 extern "C" int sba_comm_export(sba_problem* p, void* handle_out)

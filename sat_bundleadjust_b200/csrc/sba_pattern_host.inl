@@ -68,9 +68,9 @@ static int pt_set_smem_attributes(const sba_problem* p)
     return SBA_OK;
 }
 
-static bool pattern_engine_applicable(const sba_problem* p)
+static bool pattern_engine_applicable(const sba_problem* p, bool forced = false)
 {
-    if (const char* e = getenv("SBA_ENGINE")) if (std::strcmp(e, "generic") == 0) return false;
+    if (const char* e = getenv("SBA_ENGINE")) if (std::strcmp(e, "generic") == 0 && !forced) return false;
     if (p->n_common != 0 || p->nc > 6 || p->M * p->nc > PT_MAX_NS || p->M > 64) return false;
     return pt_smem_schur(p) <= (size_t)220 * 1024 && pt_smem_assemble(p) <= (size_t)220 * 1024 && pt_smem_backsub(p) <= (size_t)220 * 1024;
 }

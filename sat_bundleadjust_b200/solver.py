@@ -56,7 +56,8 @@ def initial_vars(p):
 class DeviceProblem:
     """RAII wrapper of sba_problem_create / sba_problem_destroy."""
 
-    def __init__(self, p, stream=0, rank=0, world_size=1, rpc_float32=True, track_range=None):
+    def __init__(self, p, stream=0, rank=0, world_size=1, rpc_float32=True, track_range=None, engine=None, solver=None):
+        """engine: None (automatic) | "pattern" | "generic";  solver: None (automatic) | "dense" | "pcg"."""
         check_supported(p)
         self.lib = _lib.load()
         self.cam_model = p.cam_model
@@ -88,10 +89,13 @@ class DeviceProblem:
         d.rpc_float32 = 1 if rpc_float32 else 0
         d.rank, d.world_size = rank, world_size
         self.n_common = d.n_common = n_common_params(p)
+        d.engine = {None: 0, "pattern": 1, "generic": 2}[engine]
+        d.solver = {None: 0, "dense": 1, "pcg": 2}[solver]
         self.handle = ctypes.c_void_p()
         check(self.lib.sba_problem_create(ctypes.byref(self.handle), ctypes.byref(d), ctypes.c_void_p(stream)))
         self.n_vars_device = int(self.lib.sba_problem_num_vars(self.handle))
         self.engine = "pattern" if self.lib.sba_problem_engine(self.handle) == 1 else "generic"
+        self.solver = "pcg" if self.lib.sba_problem_solver(self.handle) == 1 else "dense"
         # length of the caller's vector (the reference's params_opt layout); the device keeps n_params slots per camera
         self.n_vars = self.n_vars_device - (self.n_cam - 1) * self.n_common
         self._cb = None

@@ -109,10 +109,12 @@ def perturb_camera(P, cam_model, d_angles):
 
 def make_scene(n_cam=10, n_tracks=1000, p_vis=0.5, cam_model="perspective", seed=0,
                box_m=(10e3, 10e3, 500.0), noise_px=0.5, outlier_frac=0.02, outlier_px=20.0,
-               pts_sigma_m=1.0, ang_sigma=1e-6, min_obs=2):
+               pts_sigma_m=1.0, ang_sigma=1e-6, min_obs=2, visibility=None):
     """
     Build a seeded synthetic scene.  `n_tracks` is the number of candidate ground points; tracks seen
     by fewer than `min_obs` cameras are dropped, so the scene ends up with slightly fewer.
+    `visibility` (optional): callable(rng, n_tracks, n_cam) -> boolean (n_tracks, n_cam) matrix replacing the
+    independent draws with probability p_vis (used to build scenes whose shards differ in structure).
     """
     if cam_model not in ("perspective", "affine"):
         raise ValueError("make_scene builds matrix cameras; see make_rpc_scene for cam_model='rpc'")
@@ -131,7 +133,7 @@ def make_scene(n_cam=10, n_tracks=1000, p_vis=0.5, cam_model="perspective", seed
     enu = rng.uniform(-0.5, 0.5, size=(n_tracks, 3)) * np.array(box_m)
     pts = centre + enu[:, :1] * basis[0] + enu[:, 1:2] * basis[1] + enu[:, 2:3] * basis[2]
 
-    seen = rng.random((n_tracks, n_cam)) < p_vis
+    seen = rng.random((n_tracks, n_cam)) < p_vis if visibility is None else np.asarray(visibility(rng, n_tracks, n_cam), dtype=bool)
     keep = seen.sum(axis=1) >= min_obs
     pts, seen = pts[keep], seen[keep]
     pts_ind, cam_ind = np.nonzero(seen)

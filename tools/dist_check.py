@@ -69,6 +69,23 @@ def main():
         ok_k = rel < 1e-5 and v1.shape == s1.shape and np.array_equal(v0, s0) and info["cost"] < 0.999 * info["cost_init"]
         print("COMMON_K: cost_init %.6e max|dx| %.2e ok %s" % (info["cost_init"], np.abs(v1 - s1).max(), ok_k), flush=True)
         ok = ok and ok_k
+    # Shards that would choose different engines: the first half of the tracks see 18 views at random (diverse camera sets -> generic
+    # engine), the second half only views 0..4 (few camera sets -> pattern engine).  The driver must settle on one engine for all ranks.
+    def vis(rng, n, m):
+        v = rng.random((n, m)) < 0.3
+        v[n // 2:, 5:] = False
+        v[n // 2:, :5] = rng.random((n - n // 2, 5)) < 0.8
+        return v
+    sc = synth.make_scene(n_cam=18, n_tracks=60000, p_vis=0.3, cam_model="perspective", seed=7, visibility=vis)
+    p = synth.scene_to_params(sc, ["R", "T"])
+    ls = {"loss": "soft_l1", "f_scale": 1.0, "max_iter": 12, "verbose": 0}
+    v0, v1, e0, e1, nfev, info = sdist.run_ba_optimization_distributed(p, ls)
+    if rank == 0:
+        s0, s1, f0, f1, nfev1, info1 = ba_core.run_ba_optimization(p, ls, False, False, return_info=True)
+        rel = abs(info["cost"] - info1["cost"]) / info1["cost"]
+        print("mixed shards (%d obs) max_iter 12: dist cost %.12e nfev %d | single cost %.12e nfev %d | rel %.2e" % (
+            p.n_obs, info["cost"], nfev, info1["cost"], nfev1, rel), flush=True)
+        ok = ok and rel < 1e-5 and info["cost"] < info["cost_init"]
     # all ranks hold identical results
     t = torch.from_numpy(v1[:100].copy()).cuda()
     lst = [torch.empty_like(t) for _ in range(dist.get_world_size())]
