@@ -194,6 +194,12 @@ int sba_rpc_projection_ecef(const double *rpc, const double *xyz, int64_t n, dou
 /* c/rpc.c:378-439 eval_rpc (iterative) / rpcm localization: (col,row,alt) -> (lon,lat); delta = first probe */
 int sba_rpc_localization(const double *rpc, const double *col, const double *row, const double *alt, int64_t n,
                          double delta, double *lon, double *lat);
+/* The same for n_cam cameras in ONE launch (tables (n_cam, 90)).  shared_points != 0: lon/lat/alt (col/row/alt) hold n values used for
+ * every camera (one grid projected through all cameras, bundle_adjust/ba_rpcfit.py:78-95 per camera); else (n_cam, n).  Outputs (n_cam, n). */
+int sba_rpc_projection_batch(const double *tables, int32_t n_cam, const double *lon, const double *lat, const double *alt, int64_t n,
+                             int32_t shared_points, double *col, double *row);
+int sba_rpc_localization_batch(const double *tables, int32_t n_cam, const double *col, const double *row, const double *alt, int64_t n,
+                               int32_t shared_points, double delta, double *lon, double *lat);
 /* Measurement only (bench.py --workload rpc): device-resident time per pass of the batched RPC kernels over n_cam cameras x n
  * points (kind 0 projection, 1 localisation, 2 triangulation between tables 2j and 2j+1), inputs uploaded once. */
 int sba_rpc_throughput(int32_t kind, const double *tables_n_cam_x_90, int32_t n_cam, const double *a, const double *b,

@@ -68,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "sba_rpc_localization", "sba_rpc_throughput", "stereo_corresp_to_lonlatalt", "sba_stereo_corresp_to_lonlatalt", "sba_cholesky_solve",
     "sba_cholesky_solve_timed", "sba_outlier_elbow", "sba_outlier_mark",
     "sba_rpcfit_weighted_lsq", "sba_comm_export", "sba_comm_import", "sba_comm_try_reuse", "sba_solve_errors_device",
-    "sba_init_pts3d", "sba_linear_triangulation",
+    "sba_init_pts3d", "sba_linear_triangulation", "sba_rpc_projection_batch", "sba_rpc_localization_batch",
 ]
 
 _lib = None
@@ -107,6 +107,10 @@ def load():
     lib.sba_rpc_projection.argtypes = [c_double_p] * 4 + [ctypes.c_int64, c_double_p, c_double_p]
     lib.sba_rpc_projection_ecef.argtypes = [c_double_p, c_double_p, ctypes.c_int64, c_double_p]
     lib.sba_rpc_localization.argtypes = [c_double_p] * 4 + [ctypes.c_int64, ctypes.c_double, c_double_p, c_double_p]
+    lib.sba_rpc_projection_batch.argtypes = [c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int32,
+                                             c_double_p, c_double_p]
+    lib.sba_rpc_localization_batch.argtypes = [c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int32,
+                                               ctypes.c_double, c_double_p, c_double_p]
     lib.sba_rpc_throughput.argtypes = [ctypes.c_int32, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
                                        ctypes.c_int64, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]
     lib.sba_stereo_corresp_to_lonlatalt.argtypes = [c_double_p, c_float_p, c_float_p, c_float_p, ctypes.c_int64, vp, vp]

@@ -8,6 +8,7 @@
 // rounding; only the execution is different: coefficients staged once per block in shared memory,
 // one match per thread, arrays of structure-of-arrays inputs read coalesced.
 #include "sba_internal.cuh"
+#include <algorithm>
 #include <vector>
 
 namespace sba {
@@ -282,6 +283,23 @@ k_init_pts3d(int rpc_model, const double* __restrict__ cams, int n_cam, const lo
     }
 }
 
+// The same for many cameras in ONE launch: blockIdx.y = camera, whose coefficients the block stages in shared memory; the
+// points are shared by all cameras (in_stride == 0, e.g. one lon/lat/alt grid) or given per camera (in_stride == n).
+// kind 0: (a, b, c) = (lon, lat, alt) -> (col, row);  kind 1: (a, b, c) = (col, row, alt) -> (lon, lat)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_rpc_batch(const double* __restrict__ rs, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+            long long n, long long in_stride, double* __restrict__ o0, double* __restrict__ o1)
+{
+    __shared__ double r[R_STRUCT_DOUBLES];
+    load_struct(r, rs + (size_t)blockIdx.y * R_STRUCT_DOUBLES, R_STRUCT_DOUBLES);
+    const size_t in0 = (size_t)blockIdx.y * in_stride, out0 = (size_t)blockIdx.y * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (KIND == 0) s_project(r, a[in0 + i], b[in0 + i], c[in0 + i], o0[out0 + i], o1[out0 + i]);
+        else s_localize(r, a[in0 + i], b[in0 + i], c[in0 + i], o0[out0 + i], o1[out0 + i]);
+    }
+}
+
 // c/rpc.c:480-514 (rpc_height) + c/disp_to_h.c:40-65, one match per thread
 __global__ void __launch_bounds__(128)
 k_rpc_triangulate(const double* __restrict__ rsa, const double* __restrict__ rsb, const float2* __restrict__ kp_a,
@@ -507,6 +525,50 @@ extern "C" int sba_init_pts3d(int32_t cam_model, const double* cams, int32_t n_c
     return SBA_OK;
 }
 
+// Projection / localisation for n_cam cameras in one launch (BASELINE config 5: a 100 x 100 x 10 grid for each of 300 cameras).
+// tables: (n_cam, 90) in the layout of sba_b200.h; a, b, c: n values each when shared != 0 (the same points for every camera),
+// else (n_cam, n); outputs (n_cam, n) each.  kind 0: (lon, lat, alt) -> (col, row); kind 1: (col, row, alt) -> (lon, lat).
+static int rpc_batch(int kind, const double* tables, int32_t n_cam, const double* a, const double* b, const double* c, int64_t n,
+                     int32_t shared, double delta, double* o0, double* o1)
+{
+    if (!tables || !a || !b || !c || !o0 || !o1 || n < 0 || n_cam < 1 || n_cam > 65535) { set_error("bad argument"); return SBA_E_INVALID; }
+    if (n == 0) return SBA_OK;
+    SBA_TRY(require_device());
+    std::vector<double> hs((size_t)n_cam * R_STRUCT_DOUBLES);
+    for (int j = 0; j < n_cam; ++j) table_to_struct(tables + (size_t)j * 90, delta, hs.data() + (size_t)j * R_STRUCT_DOUBLES);
+    const size_t n_in = (size_t)(shared ? 1 : n_cam) * n, n_out = (size_t)n_cam * n;
+    DevBuf ds, in, out;
+    SBA_TRY(ds.alloc(hs.size() * sizeof(double))); SBA_TRY(in.alloc(3 * n_in * sizeof(double))); SBA_TRY(out.alloc(2 * n_out * sizeof(double)));
+    SBA_CUDA(cudaMemcpy(ds.p, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>(), a, n_in * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + n_in, b, n_in * sizeof(double), cudaMemcpyHostToDevice));
+    SBA_CUDA(cudaMemcpy(in.as<double>() + 2 * n_in, c, n_in * sizeof(double), cudaMemcpyHostToDevice));
+    const dim3 grid((unsigned)std::min<long long>((n + 255) / 256, 4 * NUM_SMS), (unsigned)n_cam);
+    const long long stride = shared ? 0 : n;
+    if (kind == 0)
+        k_rpc_batch<0><<<grid, 256>>>(ds.as<double>(), in.as<double>(), in.as<double>() + n_in, in.as<double>() + 2 * n_in, n, stride,
+                                      out.as<double>(), out.as<double>() + n_out);
+    else
+        k_rpc_batch<1><<<grid, 256>>>(ds.as<double>(), in.as<double>(), in.as<double>() + n_in, in.as<double>() + 2 * n_in, n, stride,
+                                      out.as<double>(), out.as<double>() + n_out);
+    SBA_CUDA(cudaGetLastError());
+    SBA_CUDA(cudaMemcpy(o0, out.as<double>(), n_out * sizeof(double), cudaMemcpyDeviceToHost));
+    SBA_CUDA(cudaMemcpy(o1, out.as<double>() + n_out, n_out * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBA_OK;
+}
+
+extern "C" int sba_rpc_projection_batch(const double* tables, int32_t n_cam, const double* lon, const double* lat, const double* alt,
+                                        int64_t n, int32_t shared_points, double* col, double* row)
+{
+    return rpc_batch(0, tables, n_cam, lon, lat, alt, n, shared_points, 1.0, col, row);
+}
+
+extern "C" int sba_rpc_localization_batch(const double* tables, int32_t n_cam, const double* col, const double* row, const double* alt,
+                                          int64_t n, int32_t shared_points, double delta, double* lon, double* lat)
+{
+    return rpc_batch(1, tables, n_cam, col, row, alt, n, shared_points, delta, lon, lat);
+}
+
 // Measurement entry point (bench.py --workload rpc): device-resident throughput of the batched RPC kernels over n_cam cameras
 // x n points, inputs uploaded once, `reps` timed repetitions of one launch per camera (CUDA events).
 //   kind 0: projection  (a, b, c) = (lon, lat, alt) -> (col, row)
@@ -536,14 +598,20 @@ extern "C" int sba_rpc_throughput(int32_t kind, const double* tables, int32_t n_
     }
     cudaEvent_t e0, e1;
     SBA_CUDA(cudaEventCreate(&e0)); SBA_CUDA(cudaEventCreate(&e1));
+    // kinds 0 and 1: ONE launch for all cameras (blockIdx.y = camera, the same points for every camera); the output of the last
+    // camera is what `out` receives.  kind 2: one launch per pair.
+    DevBuf big;
+    if (kind != 2) SBA_TRY(big.alloc((size_t)2 * n_cam * n * sizeof(double)));
     auto pass = [&]() {
-        for (int j = 0; j < n_cam; ++j) {
-            const double* sj = ds.as<double>() + (size_t)(kind == 2 ? 2 * j : j) * R_STRUCT_DOUBLES;
-            double* x = in.as<double>();
-            if (kind == 0) k_rpc_projection<<<grid_n(n, 256), 256>>>(sj, x, x + n, x + 2 * n, n, o.as<double>(), o.as<double>() + n);
-            else if (kind == 1) k_rpc_localization<<<grid_n(n, 256), 256>>>(sj, x, x + n, x + 2 * n, n, o.as<double>(), o.as<double>() + n);
-            else k_rpc_triangulate<<<grid_n(n, 128), 128>>>(sj, sj + R_STRUCT_DOUBLES, kf.as<float2>(), kf.as<float2>() + n, n, o.as<double>(), ef.as<float>());
-        }
+        double* x = in.as<double>();
+        const dim3 grid((unsigned)std::min<long long>((n + 255) / 256, 4 * NUM_SMS), (unsigned)n_cam);
+        if (kind == 0) k_rpc_batch<0><<<grid, 256>>>(ds.as<double>(), x, x + n, x + 2 * n, n, 0, big.as<double>(), big.as<double>() + (size_t)n_cam * n);
+        else if (kind == 1) k_rpc_batch<1><<<grid, 256>>>(ds.as<double>(), x, x + n, x + 2 * n, n, 0, big.as<double>(), big.as<double>() + (size_t)n_cam * n);
+        else
+            for (int j = 0; j < n_cam; ++j) {
+                const double* sj = ds.as<double>() + (size_t)2 * j * R_STRUCT_DOUBLES;
+                k_rpc_triangulate<<<grid_n(n, 128), 128>>>(sj, sj + R_STRUCT_DOUBLES, kf.as<float2>(), kf.as<float2>() + n, n, o.as<double>(), ef.as<float>());
+            }
     };
     pass();                                     // warm-up
     SBA_CUDA(cudaDeviceSynchronize());
@@ -555,7 +623,11 @@ extern "C" int sba_rpc_throughput(int32_t kind, const double* tables, int32_t n_
     SBA_CUDA(cudaEventElapsedTime(&t, e0, e1));
     SBA_CUDA(cudaGetLastError());
     *ms = (double)t / reps;
-    if (out) SBA_CUDA(cudaMemcpy(out, o.p, (kind == 2 ? 3 : 2) * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out && kind == 2) SBA_CUDA(cudaMemcpy(out, o.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out && kind != 2) {      // last camera: [first output (n) | second output (n)]
+        SBA_CUDA(cudaMemcpy(out, big.as<double>() + (size_t)(n_cam - 1) * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+        SBA_CUDA(cudaMemcpy(out + n, big.as<double>() + (size_t)n_cam * n + (size_t)(n_cam - 1) * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return SBA_OK;
 }

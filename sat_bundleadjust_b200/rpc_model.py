@@ -104,3 +104,32 @@ def rpc_from_rpc_file(path):
                 k, v = line.split(":", 1)
                 d[k.strip()] = v.split()[0]
     return RPCModel(d)
+
+
+def _batch(kind, models, a, b, c, delta=1.0):
+    """kind 0: projection, 1: localisation, for a list of RPC models in one launch.  a, b, c: (n,) shared by all models or (len(models), n)."""
+    tables = np.ascontiguousarray(np.stack([np.asarray(m.table(), dtype=np.float64) for m in models]))
+    a, b, c = [np.ascontiguousarray(v, dtype=np.float64) for v in np.broadcast_arrays(a, b, c)]
+    shared = a.ndim == 1
+    if not shared and (a.ndim != 2 or a.shape[0] != len(models)):
+        raise ValueError("expected (n,) arrays shared by all models or (n_models, n) arrays")
+    n = a.shape[-1]
+    o0, o1 = np.empty((len(models), n)), np.empty((len(models), n))
+    lib = _lib.load()
+    if kind == 0:
+        _lib.check(lib.sba_rpc_projection_batch(_lib.dptr(tables), len(models), _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), n, int(shared),
+                                                _lib.dptr(o0), _lib.dptr(o1)))
+    else:
+        _lib.check(lib.sba_rpc_localization_batch(_lib.dptr(tables), len(models), _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), n, int(shared),
+                                                  float(delta), _lib.dptr(o0), _lib.dptr(o1)))
+    return o0, o1
+
+
+def projection_batch(models, lon, lat, alt):
+    """(lon, lat, alt) -> (col, row) through every model of `models` in ONE kernel launch; returns two (len(models), n) arrays."""
+    return _batch(0, models, lon, lat, alt)
+
+
+def localization_batch(models, col, row, alt, delta=1.0):
+    """(col, row, alt) -> (lon, lat) through every model of `models` in ONE kernel launch; returns two (len(models), n) arrays."""
+    return _batch(1, models, col, row, alt, delta)

@@ -180,3 +180,21 @@ def test_init_pts3d_rpc_branch(built):
     assert seen.sum() > 100
     assert np.abs(got[seen] - avg[seen]).max() <= 1.0      # float32 ulp at 6.4e6 m is 0.5 m
     assert np.array_equal(got[~seen], avg[~seen])
+
+
+def test_batched_projection_and_localization(built):
+    """sba_rpc_projection_batch / sba_rpc_localization_batch: all cameras in one launch, bit-identical to the per-camera calls."""
+    from sat_bundleadjust_b200 import rpc_model
+    models = [rpc_model.RPCModel(util.rpc_from_array(a).to_dict()) for a in R["rpc_cams"][:3]]
+    lla = R["lonlatalt"]
+    col, row = rpc_model.projection_batch(models, lla[:, 0], lla[:, 1], lla[:, 2])              # shared points
+    for j, m in enumerate(models):
+        c1, r1 = m.projection(lla[:, 0], lla[:, 1], lla[:, 2])
+        assert np.array_equal(col[j], c1) and np.array_equal(row[j], r1)
+    lon, lat = rpc_model.localization_batch(models, col, row, np.broadcast_to(lla[:, 2], col.shape))   # per-camera points
+    for j, m in enumerate(models):
+        l1, a1 = m.localization(col[j], row[j], lla[:, 2])
+        assert np.array_equal(lon[j], l1) and np.array_equal(lat[j], a1)
+        assert np.abs(lon[j] - lla[:, 0]).max() < 1e-7 and np.abs(lat[j] - lla[:, 1]).max() < 1e-7
+    with pytest.raises(ValueError):
+        rpc_model.projection_batch(models, np.zeros((2, 5)), np.zeros((2, 5)), np.zeros((2, 5)))
