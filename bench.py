@@ -53,6 +53,8 @@ WORKLOADS = {
     "cfg4": (300, 625000, 0.02, "perspective", ["R", "T"],
              "BASELINE config 4: 300-view multi-date perspective BA, 6.25e5 tracks / ~3.7e6 observations per GPU (5e6 tracks / ~3e7 observations "
              "on 8 GPUs), soft_l1, R+T, matrix-free PCG on the 1800-unknown reduced camera system"),
+    "rpcba": (4, 250000, 0.8, "rpc", ["R", "T"],
+              "cam_model='rpc' (the pipeline default): 4 RPC cameras of the golden scene, 2.5e5 tracks / ~8e5 observations per GPU, soft_l1, R+T"),
     "cfg4s": (300, 100000, 0.02, "perspective", ["R", "T"],
               "BASELINE config 4 reduced: 300-view perspective BA, 1e5 tracks / ~6e5 observations per GPU (1800 x 1800 reduced system)"),
 }
@@ -147,6 +149,10 @@ class ClockSampler:
 def build_problem(workload, world):
     from sat_bundleadjust_b200 import synth
     n_cam, tracks, p_vis, model, corr, _ = WORKLOADS[workload]
+    if model == "rpc":                                # the golden fixture's RPC cameras (tests/golden/rpc_golden.npz), synthetic tracks
+        G = np.load(os.path.join(ROOT, "tests", "golden", "rpc_golden.npz"))
+        scene = synth.make_rpc_scene(G["rpc_cams"][:n_cam], G["rpcba/camera_centers"][:n_cam], n_tracks=tracks * world, p_vis=p_vis, seed=0)
+        return synth.SparseParams(scene, corr)
     if n_cam >= 100 and tracks * world > 200000:      # time-series scale: never form the dense (2M x N) correspondence matrix
         scene = synth.make_scene_sparse(n_cam=n_cam, n_tracks=tracks * world, p_vis=p_vis, cam_model=model, seed=0)
         return synth.SparseParams(scene, corr)

@@ -242,3 +242,44 @@ def make_scene_sparse(n_cam=300, n_tracks=100000, p_vis=0.02, cam_model="perspec
     return Scene(cam_model=cam_model, cameras=cams, cameras_init=cams_init, camera_centers=centers, pts3d_true=pts,
                  pts3d_init=pts_init, pts_ind=pts_ind, cam_ind=cam_ind, pts2d=pts2d, seed=seed,
                  meta=dict(n_cam=n_cam, n_tracks=n_tracks, p_vis=p_vis, sparse=True))
+
+
+def make_rpc_scene(rpc_tables, camera_centers, n_tracks=100000, p_vis=0.8, seed=0, noise_px=0.5, outlier_frac=0.02, outlier_px=20.0,
+                   pts_sigma_m=1.0, min_obs=2):
+    """
+    Synthetic scene for cam_model == "rpc" (the pipeline's default model, ba_pipeline.py:83): ground points drawn inside the
+    validity box shared by the given RPC cameras ((M, 90) coefficient tables, layout of include/sba_b200.h), observations =
+    their RPC projections (one batched GPU launch, sba_rpc_projection_batch) + Gaussian noise + a few outliers, random
+    visibility.  Needs the CUDA library (the generator is used by bench.py and the GPU tests only).
+    """
+    from . import rpc_model
+    from .ba_rpcfit import _model_from_table
+    rng = np.random.default_rng(seed)
+    T = np.asarray(rpc_tables, dtype=np.float64)
+    M = T.shape[0]
+    cams = [_model_from_table(T[j]) for j in range(M)]
+    # common validity box in normalised coordinates: |x| <= 0.45 of every camera's scale around the mean offset
+    lat0, lon0, alt0 = T[:, 2].mean(), T[:, 3].mean(), T[:, 4].mean()
+    dlat = 0.45 * T[:, 7].min() - np.abs(T[:, 2] - lat0).max()
+    dlon = 0.45 * T[:, 8].min() - np.abs(T[:, 3] - lon0).max()
+    dalt = 0.45 * T[:, 9].min() - np.abs(T[:, 4] - alt0).max()
+    if min(dlat, dlon, dalt) <= 0:
+        raise ValueError("the RPC cameras do not share a validity box")
+    lat = lat0 + dlat * rng.uniform(-1, 1, n_tracks)
+    lon = lon0 + dlon * rng.uniform(-1, 1, n_tracks)
+    alt = alt0 + dalt * rng.uniform(-1, 1, n_tracks)
+    seen = rng.random((n_tracks, M)) < p_vis
+    keep = seen.sum(axis=1) >= min_obs
+    lat, lon, alt, seen = lat[keep], lon[keep], alt[keep], seen[keep]
+    col, row = rpc_model.projection_batch(cams, lon, lat, alt)                     # (M, N)
+    pts_ind, cam_ind = np.nonzero(seen)
+    pts2d = np.stack((col[cam_ind, pts_ind], row[cam_ind, pts_ind]), axis=1)
+    pts2d += noise_px * rng.standard_normal(pts2d.shape)
+    bad = rng.random(pts_ind.size) < outlier_frac
+    pts2d[bad] += outlier_px * rng.standard_normal((int(bad.sum()), 2))
+    x, y, z = geo_utils.latlon_to_ecef_custom(lat, lon, alt)
+    pts_true = np.stack((x, y, z), axis=1)
+    pts_init = (pts_true + pts_sigma_m * rng.standard_normal(pts_true.shape)).astype(np.float32).astype(np.float64)
+    return Scene(cam_model="rpc", cameras=cams, cameras_init=cams, camera_centers=[np.asarray(c, dtype=np.float64) for c in camera_centers],
+                 pts3d_true=pts_true, pts3d_init=pts_init, pts_ind=pts_ind.astype(np.int64), cam_ind=cam_ind.astype(np.int64),
+                 pts2d=pts2d, seed=seed, meta={"box_deg_m": (float(dlat), float(dlon), float(dalt))})

@@ -119,7 +119,8 @@ def main():
                 n, d["config"]["n_obs"], d["ms_per_step"], d["value"], 100 * d["value"] / (n * base["value"]), d["e2e"]["value"], 1e3 * d["e2e"]["wall_s"], phases(d)))
         out += [""]
     others = [("5e6 observations, 10 views, one GPU", "r02_bench_5m.json"), ("BASELINE config 3 whole on one GPU", "r02_bench_cfg3full.json"),
-              ("BASELINE config 3 on 8 GPUs", "r02_bench_cfg3_n8.json"), ("BASELINE config 4 on 8 GPUs (PCG)", "r02_bench_cfg4_n8.json")]
+              ("BASELINE config 3 on 8 GPUs", "r02_bench_cfg3_n8.json"), ("BASELINE config 4 on 8 GPUs (PCG)", "r02_bench_cfg4_n8.json"),
+              ("cam_model='rpc' (pipeline default), 4 RPC cameras, one GPU", "r02_bench_rpcba.json")]
     rows = [(t, load(f)) for t, f in others]
     rows = [(t, d) for t, d in rows if d]
     if rows:
