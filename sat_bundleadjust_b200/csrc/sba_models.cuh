@@ -208,10 +208,10 @@ SBA_HD D3 operator/(D3 a, D3 b)
     return D3{q, (a.d0 - q * b.d0) * ib, (a.d1 - q * b.d1) * ib, (a.d2 - q * b.d2) * ib};
 }
 SBA_HD D3 d3_chain(double v, double dv, D3 a) { return D3{v, dv * a.d0, dv * a.d1, dv * a.d2}; }
-SBA_HD D3 d3_sqrt(D3 a) { const double s = sqrt(a.v); return d3_chain(s, 0.5 / s, a); }
+SBA_HD D3 d3_sqrt(D3 a) { const double r = fast_rsqrt(a.v); return d3_chain(a.v * r, 0.5 * r, a); }
 SBA_HD D3 d3_atan2(D3 y, D3 x)
 {
-    const double n = 1.0 / (x.v * x.v + y.v * y.v);
+    const double n = fast_rcp(x.v * x.v + y.v * y.v);
     const double gy = x.v * n, gx = -y.v * n;
     return D3{atan2(y.v, x.v), gy * y.d0 + gx * x.d0, gy * y.d1 + gx * x.d1, gy * y.d2 + gx * x.d2};
 }
@@ -246,17 +246,25 @@ SBA_HD void ecef_to_geodetic_d(double x, double y, double z, D3& lat, D3& lon, D
     const double ep2 = (asq - bsq) / bsq;
     const D3 X{x, 1.0, 0.0, 0.0}, Y{y, 0.0, 1.0, 0.0}, Z{z, 0.0, 0.0, 1.0};
     const D3 p = d3_sqrt(X * X + Y * Y);
-    const D3 th = d3_atan2(a * Z, b * p);
+    // sin / cos of the auxiliary angle th = atan2(a z, b p) and of the latitude follow algebraically from the arguments of
+    // the arc tangents (u / hypot(u, v), v / hypot(u, v)): no atan2 + sincos round trips on this path (the value-only
+    // conversion above keeps the reference's operations for the parity of `fun`; the two agree to rounding)
+    const D3 tu = a * Z, tv = b * p;
+    const D3 th2 = tu * tu + tv * tv;
+    const double rth = fast_rsqrt(th2.v);
+    const D3 irt = d3_chain(rth, -0.5 * rth * rth * rth, th2);            // 1 / hypot(tu, tv)
+    const D3 sth = tu * irt, cth = tv * irt;
+    const D3 s3 = sth * sth * sth, c3 = cth * cth * cth;
+    const D3 lnum = Z + (ep2 * b) * s3, lden = p - (esq * a) * c3;
+    const D3 latr = d3_atan2(lnum, lden);
     const D3 lonr = d3_atan2(Y, X);
-    const double sth = sin(th.v), cth = cos(th.v);
-    const D3 s3 = d3_chain(sth * sth * sth, 3.0 * sth * sth * cth, th);
-    const D3 c3 = d3_chain(cth * cth * cth, -3.0 * cth * cth * sth, th);
-    const D3 latr = d3_atan2(Z + (ep2 * b) * s3, p - (esq * a) * c3);
-    const double sl = sin(latr.v), cl = cos(latr.v);
-    const double root = sqrt(1.0 - esq * sl * sl);
+    const double rl = fast_rsqrt(lnum.v * lnum.v + lden.v * lden.v);
+    const double sl = lnum.v * rl, cl = lden.v * rl;
+    const double iroot = fast_rsqrt(1.0 - esq * sl * sl);
     // N = a / root ; dN/dlat = a esq sl cl / root^3
-    const D3 N = d3_chain(a / root, a * esq * sl * cl / (root * root * root), latr);
-    const D3 invc = d3_chain(1.0 / cl, sl / (cl * cl), latr);
+    const D3 N = d3_chain(a * iroot, a * esq * sl * cl * (iroot * iroot * iroot), latr);
+    const double icl = fast_rcp(cl);
+    const D3 invc = d3_chain(icl, sl * icl * icl, latr);
     alt = p * invc - N;
     lon = RAD2DEG * lonr;
     lat = RAD2DEG * latr;
@@ -328,25 +336,29 @@ SBA_HD void rpc_project_ecef_d(const double* __restrict__ t, double x, double y,
 {
     D3 lat, lon, alt;
     ecef_to_geodetic_d(x, y, z, lat, lon, alt);
-    const double nlon = (lon.v - t[3]) / t[8];
-    const double nlat = (lat.v - t[2]) / t[7];
-    const double nalt = (alt.v - t[4]) / t[9];
+    // reciprocals of the three ground scales and of the two denominators once (13 FP64 divisions otherwise: ~25 instructions each);
+    // the values differ from rpc_project's (which keeps the reference's divisions for the parity of `fun`) in the last bit only
+    const double i_lon = fast_rcp(t[8]), i_lat = fast_rcp(t[7]), i_alt = fast_rcp(t[9]);
+    const double nlon = (lon.v - t[3]) * i_lon;
+    const double nlat = (lat.v - t[2]) * i_lat;
+    const double nalt = (alt.v - t[4]) * i_alt;
     double cn, cnx, cny, cnz, cd, cdx, cdy, cdz, rn, rnx, rny, rnz, rd, rdx, rdy, rdz;
     poly20_grad(t + 50, nlon, nlat, nalt, cn, cnx, cny, cnz);
     poly20_grad(t + 70, nlon, nlat, nalt, cd, cdx, cdy, cdz);
     poly20_grad(t + 10, nlon, nlat, nalt, rn, rnx, rny, rnz);
     poly20_grad(t + 30, nlon, nlat, nalt, rd, rdx, rdy, rdz);
-    const double ncol = cn / cd, nrow = rn / rd;
+    const double rcd = fast_rcp(cd), rrd = fast_rcp(rd);
+    const double ncol = cn * rcd, nrow = rn * rrd;
     col = ncol * t[6] + t[1];
     row = nrow * t[5] + t[0];
     // d(ncol)/d(nlon, nlat, nalt), scaled back to pixels per (deg, deg, m)
-    const double icd = t[6] / cd, ird = t[5] / rd;
-    const double c_lon = (cnx - ncol * cdx) * icd / t[8];
-    const double c_lat = (cny - ncol * cdy) * icd / t[7];
-    const double c_alt = (cnz - ncol * cdz) * icd / t[9];
-    const double r_lon = (rnx - nrow * rdx) * ird / t[8];
-    const double r_lat = (rny - nrow * rdy) * ird / t[7];
-    const double r_alt = (rnz - nrow * rdz) * ird / t[9];
+    const double icd = t[6] * rcd, ird = t[5] * rrd;
+    const double c_lon = (cnx - ncol * cdx) * icd * i_lon;
+    const double c_lat = (cny - ncol * cdy) * icd * i_lat;
+    const double c_alt = (cnz - ncol * cdz) * icd * i_alt;
+    const double r_lon = (rnx - nrow * rdx) * ird * i_lon;
+    const double r_lat = (rny - nrow * rdy) * ird * i_lat;
+    const double r_alt = (rnz - nrow * rdz) * ird * i_alt;
     A[0] = c_lon * lon.d0 + c_lat * lat.d0 + c_alt * alt.d0;
     A[1] = c_lon * lon.d1 + c_lat * lat.d1 + c_alt * alt.d1;
     A[2] = c_lon * lon.d2 + c_lat * lat.d2 + c_alt * alt.d2;
