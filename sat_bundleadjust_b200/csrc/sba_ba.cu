@@ -807,6 +807,7 @@ extern "C" int sba_problem_destroy(sba_problem* p)
     cudaSetDevice(p->device);
     if (p->stream2) cudaStreamSynchronize(p->stream2);
     cudaStreamSynchronize(p->stream);               // nothing of this problem may still be running on the slabs
+    if (p->engine == 1) pt_print_cycles(p);
     for (size_t i = 0; i < p->arena_chunks.size(); ++i) pool_give(p->arena_chunks[i], p->arena_chunk_bytes[i], p->device);
     // the exchange buffer and its peer mappings belong to the process (g_comm), not to the problem
     if (p->h_scal) { std::lock_guard<std::mutex> lock(g_pool_mutex); g_pinned_pool.push_back(p->h_scal); }

@@ -35,6 +35,7 @@ struct PatView {
     const double* rpc_tab;
     int M, P, n_cam_fix, n_cta;
     int debug_skip;           // measurement only (SBA_PT_SKIP=1): the warps walk no units, leaving the fixed cost of a pass
+    long long* cycles;        // measurement only (SBA_PT_CYCLES=1): per warp, clocks spent in its unit loop (load balance of the assignment)
 };
 
 __device__ __forceinline__ double step_value2(double x, double t, double d, double pa, double pb)
@@ -232,6 +233,7 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
     double* stg = s_stage + warp * 9 * 33;           // stride 33: the (track, value) lanes below read conflict-free
     double* my_acc = s_acc + warp * A.M * NV;            // camera blocks of this warp's units: private, no ordering needed
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const long long cyc0 = clock64();
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -327,6 +329,7 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
         }
         __syncwarp();
     }
+    if (A.cycles && lane == 0) A.cycles[blockIdx.x * nw + warp] = clock64() - cyc0;
     const double ctot = cta_reduce_sum<1>(cost, s_red);       // contains __syncthreads: all flushes are complete
     for (int t = threadIdx.x; t < A.M * NV; t += blockDim.x) {
         double sum = 0.0;
@@ -505,6 +508,7 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
         }
     }
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const long long cyc0 = clock64();
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -550,6 +554,8 @@ k_pt_jvp1(PatView A, const double* __restrict__ x, const double* __restrict__ ca
             acc[3] = fma(y1, y1, fma(y0, y0, acc[3]));
         }
     }
+    if (A.cycles && lane == 0) A.cycles[blockIdx.x * nw + warp] = clock64() - cyc0;
+    if (A.cycles && threadIdx.x == 0) { unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); A.cycles[(size_t)4 * PT_CTAS * 32 + blockIdx.x] = sm; }
     // max |g| of this rank (non-negative doubles order like their bit patterns; the slot is zeroed by the host)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_down_sync(0xffffffffu, gmax, o));
@@ -633,6 +639,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
     int nbad = 0;
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     SchurTasks<NC> tk;
+    const long long cyc0 = clock64();
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -739,6 +746,7 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
             }
         }
     }
+    if (A.cycles && lane == 0) A.cycles[blockIdx.x * nw + warp] = clock64() - cyc0;
     if (nbad) atomicAdd(bad_points, (double)nbad);
     __threadfence();
     __syncthreads();
@@ -858,6 +866,7 @@ k_pt_schur_mma(PatView A, const double* __restrict__ x, const double* __restrict
     int nbad = 0;
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
     const int frow = lane >> 2, fk = lane & 3;           // fragment coordinates of the lane: row of the 8 x 4 operand, k index
+    const long long cyc0 = clock64();
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -970,6 +979,7 @@ k_pt_schur_mma(PatView A, const double* __restrict__ x, const double* __restrict
             }
         }
     }
+    if (A.cycles && lane == 0) A.cycles[blockIdx.x * nw + warp] = clock64() - cyc0;
     if (nbad) atomicAdd(bad_points, (double)nbad);
     __threadfence();
     __syncthreads();
@@ -1178,6 +1188,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
     }
     double* stg = s_stage + warp * 3 * 32;
     const int u0 = A.warp_unit0[blockIdx.x * nw + warp], u1 = A.debug_skip ? u0 : A.warp_unit0[blockIdx.x * nw + warp + 1];
+    const long long cyc0 = clock64();
     for (int u = u0; u < u1; ++u) {
         const PUnit un = A.units[u];
         const LaneGeo G = lane_geometry(un, lane);
@@ -1246,6 +1257,7 @@ k_pt_backsub(PatView A, const double* __restrict__ x, const double* __restrict__
             __syncwarp();
         }
     }
+    if (A.cycles && lane == 0) A.cycles[blockIdx.x * nw + warp] = clock64() - cyc0;
     const double tot = cta_reduce_sum<7>(acc, s_red);
     __shared__ int slots[7];
     if (threadIdx.x == 0) {

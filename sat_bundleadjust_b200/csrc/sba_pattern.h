@@ -80,28 +80,42 @@ inline int pattern_schur_passes(int L, int nc, int rows_per_task)
     return (ntask + 63) / 64;
 }
 
-// relative cost of one tile: uniform for the evaluation kernels (one observation per lane); for the Schur kernel the
-// evaluation (once per pass) plus the product rounds (track slots / parallel groups x tasks per lane)
-inline int pattern_tile_cost(int L, int nc, int rows_per_task, bool schur)
+// Cost of one tile (all tiles of a run have the same track length L) and of starting a unit, per kernel shape, in clocks.  The
+// numbers are a least-squares fit of the clocks every warp spent in its unit loop (SBA_PT_CYCLES_FILE, 2368 warps, B200,
+// perspective, 6 unknowns per camera, the 1e6-observation bench scene) against the warp's tile counts per track length and its
+// number of units (tools/fit_tile_cost.py).  With a uniform tile cost the slowest warp of a kernel took 1.2-1.3x the average, and
+// a kernel ends with its slowest warp.  kind: 0 = light (K2 + K4 share the assignment: sum of both), 1 = assembly (K1), 2 = Schur
+// (K3, DFMA kernel; the tensor-core variant keeps its formula).
+inline int pattern_unit_cost(int kind, int rows_per_task)
 {
-    if (!schur) return 8;
+    if (kind == 2 && rows_per_task == 0) return 0;
+    return kind == 0 ? 2100 : (kind == 1 ? 10400 : 3100);
+}
+inline int pattern_tile_cost(int L, int nc, int rows_per_task, int kind)
+{
+    static const int light[11] = {0, 0, 5515, 6283, 6405, 7048, 7400, 7734, 7762, 8120, 8422};
+    static const int wide[11] = {0, 0, 5909, 5026, 4683, 4458, 4669, 4573, 4430, 4036, 4108};
+    static const int narrow[11] = {0, 0, 4312, 4832, 6161, 5406, 6803, 6125, 10793, 9247, 10266};
     const int T = pattern_tile_tracks(L);
-    if (rows_per_task == 0) {          // evaluation once per pass + per track R fragment loads and one MMA per tile
+    if (kind == 2 && rows_per_task == 0) {          // evaluation once per pass + per track R fragment loads and one MMA per tile
         const int R = pattern_mma_row_blocks(L, nc), nt = R * (R + 1) / 2, np = (nt + PT_MMA_TILES - 1) / PT_MMA_TILES;
         return np * 24 + (T * (np == 1 ? R + nt : 3 * nt)) / 4;
     }
+    const int l = L < 2 ? 2 : L;
+    if (kind == 0) return l <= 10 ? light[l] : 8422 + 300 * (l - 10);
+    if (kind == 1) return l <= 10 ? wide[l] : 4100;
+    if (l <= 10) return narrow[l];
+    // longer tracks (more than 10 cameras): one evaluation per pass plus the product rounds, scaled to meet the table at L = 10
     const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
-    const int npar = ntask <= 16 ? 32 / ntask : 1;
-    const int rounds = (T + npar - 1) / npar;
     int cost = 0;
-    for (int left = ntask; left > 0; left -= 64) cost += 8 + rounds * (left > 32 ? 2 : 1) * 3;
-    return cost;
+    for (int left = ntask; left > 0; left -= 64) cost += 8 + T * (left > 32 ? 2 : 1) * 3;
+    return cost * (10266 / 52);
 }
 
 // Cut the tile sequence of the runs into one contiguous range per warp (equal cost); a unit is the part of a warp's
 // range inside one run.
 inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std::vector<int>& track_ptr, int n_cta, int warps,
-                                 int nc, int rows_per_task, bool schur, PatternAssignment& A)
+                                 int nc, int rows_per_task, int kind, PatternAssignment& A)
 {
     A.warps = warps;
     A.units.clear();
@@ -110,9 +124,10 @@ inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std:
     A.warp_unit0.assign(nw + 1, 0);
     // cumulative cost at the start of every run
     std::vector<long long> cost0(runs.size() + 1, 0);
+    const long long ucost = pattern_unit_cost(kind, rows_per_task);       // starting a unit (first tile not prefetched, flush of the camera blocks)
     for (size_t r = 0; r < runs.size(); ++r) {
         const int T = pattern_tile_tracks(runs[r].L);
-        cost0[r + 1] = cost0[r] + (long long)((runs[r].ntrk + T - 1) / T) * pattern_tile_cost(runs[r].L, nc, rows_per_task, schur);
+        cost0[r + 1] = cost0[r] + ucost + (long long)((runs[r].ntrk + T - 1) / T) * pattern_tile_cost(runs[r].L, nc, rows_per_task, kind);
     }
     const long long total = cost0.back();
     size_t r = 0;
@@ -122,9 +137,9 @@ inline void assign_pattern_units(const std::vector<PatternRun>& runs, const std:
         const long long target = total * (g + 1) / nw;       // this warp takes tiles while the cumulative cost stays <= target
         while (r < runs.size()) {
             const PatternRun& R = runs[r];
-            const int T = pattern_tile_tracks(R.L), c = pattern_tile_cost(R.L, nc, rows_per_task, schur);
+            const int T = pattern_tile_tracks(R.L), c = pattern_tile_cost(R.L, nc, rows_per_task, kind);
             const long long run_tiles = (R.ntrk + T - 1) / T;
-            const long long done = cost0[r] + tile * c;
+            const long long done = cost0[r] + ucost + tile * c;
             long long take = g == nw - 1 ? run_tiles - tile : std::min(run_tiles - tile, (target - done) / c);
             if (take <= 0) break;
             PUnit u;
@@ -224,9 +239,9 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     out.fill = tiles > 0 ? (double)K / (32.0 * (double)tiles) : 0.0;
     out.n_cta = n_cta;
     if (runs.empty()) { out.why = "no observations"; return; }
-    assign_pattern_units(runs, out.track_ptr, n_cta, warps_light, nc, rows_per_task, false, out.light);
-    assign_pattern_units(runs, out.track_ptr, n_cta, warps_wide, nc, rows_per_task, false, out.wide);
-    assign_pattern_units(runs, out.track_ptr, n_cta, warps_narrow, nc, rows_per_task, true, out.narrow);
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_light, nc, rows_per_task, 0, out.light);
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_wide, nc, rows_per_task, 1, out.wide);
+    assign_pattern_units(runs, out.track_ptr, n_cta, warps_narrow, nc, rows_per_task, 2, out.narrow);
     out.ok = true;
 }
 

@@ -7,7 +7,7 @@
 // i.e. 6 launches and 4 Jacobian evaluations per observation and iteration, nothing per-observation stored in HBM.
 
 // shape: 0 = light (jvp1, backsub), 1 = wide (assemble), 2 = narrow (schur)
-static PatView pat_view(const sba_problem* p, int shape)
+static PatView pat_view(const sba_problem* p, int shape, int slot = -1)
 {
     PatView A;
     A.units = (const PUnit*)p->pt_units[shape];
@@ -16,6 +16,7 @@ static PatView pat_view(const sba_problem* p, int shape)
     A.M = p->M; A.P = p->P; A.n_cam_fix = p->n_cam_fix; A.n_cta = p->pt_n_cta;
     static const bool skip = getenv("SBA_PT_SKIP") != nullptr;
     A.debug_skip = skip ? 1 : 0;
+    A.cycles = p->pt_cycles ? p->pt_cycles + (size_t)(slot < 0 ? shape : slot) * PT_CTAS * 32 : nullptr;
     return A;
 }
 
@@ -180,7 +181,7 @@ static int pt_run_backsub(sba_problem* p, int loss, double f_scale)
     const int fold = p->world == 1 || cf.on;
 #define L(MODEL, NC)                                                                                                      \
     k_pt_backsub<MODEL, NC><<<p->pt_n_cta, PT_THREADS_LIGHT, pt_smem_backsub(p), p->stream>>>(                             \
-        pat_view(p, 0), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
+        pat_view(p, 0, 3), p->x, p->camrec, p->V, p->g, p->dsq, p->idsq, p->dsqc, p->idsqc, (const double2*)p->osc, p->delta, ns, \
         p->rank == 0, p->red_partials, p->counters + 3, p->scal, fold, cf)
     PT_DISPATCH(p, L);
 #undef L
@@ -202,6 +203,40 @@ static int pt_reset_state(sba_problem* p)
     SBA_CUDA(cudaMemcpyAsync(p->x_new, p->x, n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     SBA_CUDA(cudaMemsetAsync(p->delta, 0, n * sizeof(double), p->stream));
     return SBA_OK;
+}
+
+// SBA_PT_CYCLES=1: load balance of the static assignment -- clocks every warp spent in its unit loop during the LAST launch of each kernel
+static void pt_print_cycles(sba_problem* p)
+{
+    if (!p->pt_cycles) return;
+    std::vector<long long> h((size_t)5 * PT_CTAS * 32);
+    if (cudaMemcpy(h.data(), p->pt_cycles, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    const char* names[4] = {"K2 jvp1 (16 warps)", "K1 assemble (16 warps)", "K3 schur (12 warps)", "K4 backsub (16 warps)"};
+    const int warps[4] = {PT_THREADS_LIGHT / 32, PT_THREADS / 32, PT_THREADS_SCHUR / 32, PT_THREADS_LIGHT / 32};
+    if (const char* path = getenv("SBA_PT_CYCLES_FILE")) {      // raw per-warp clocks: 4 kernels x 148 CTAs x 32 slots + the SM id of every CTA
+        if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
+    }
+    if (getenv("SBA_PT_CYCLES_DUMP")) {
+        for (int k = 0; k < 4; ++k) {
+            fprintf(stderr, "[sba cycles dump] k%d:", k);
+            for (int c = 0; c < p->pt_n_cta; ++c) { double a = 0; for (int w = 0; w < warps[k]; ++w) a += (double)h[(size_t)k * PT_CTAS * 32 + (size_t)c * warps[k] + w]; fprintf(stderr, " %d:%.0f", (int)h[(size_t)4 * PT_CTAS * 32 + c], a / warps[k] / 100.0); }
+            fprintf(stderr, "\n");
+        }
+    }
+    for (int k = 0; k < 4; ++k) {
+        double wsum = 0, wmax = 0, csum = 0, cmax = 0, cmin = 1e30;
+        for (int c = 0; c < p->pt_n_cta; ++c) {
+            double cta = 0;
+            for (int w = 0; w < warps[k]; ++w) {
+                const double v = (double)h[(size_t)k * PT_CTAS * 32 + (size_t)c * warps[k] + w];
+                wsum += v; wmax = std::max(wmax, v); cta = std::max(cta, v);
+            }
+            csum += cta; cmax = std::max(cmax, cta); cmin = std::min(cmin, cta);
+        }
+        const int nwarp = p->pt_n_cta * warps[k];
+        fprintf(stderr, "[sba cycles] %-24s per warp: avg %.0f max %.0f (max/avg %.2f) | per CTA (slowest warp): min %.0f avg %.0f max %.0f (max/avg %.2f)\n",
+                names[k], wsum / nwarp, wmax, wmax / (wsum / nwarp), cmin, csum / p->pt_n_cta, cmax, cmax / (csum / p->pt_n_cta));
+    }
 }
 
 // ---- the iteration -------------------------------------------------------------------------------------------------------
@@ -426,6 +461,10 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     SBA_TRY(dev_alloc(p, &p->chol_work, (size_t)34 * (ns + 32)));
     const size_t nv = (size_t)nc * (nc + 1) / 2 + nc, nS = (size_t)nc * nc * ((size_t)M * (M + 1) / 2);
     SBA_TRY(dev_alloc(p, &p->pt_partials, std::max((size_t)M * nv + 1, nS + ns) * lay.n_cta));
+    if (getenv("SBA_PT_CYCLES")) {
+        SBA_TRY(dev_alloc(p, &p->pt_cycles, (size_t)5 * PT_CTAS * 32));
+        SBA_CUDA(cudaMemsetAsync(p->pt_cycles, 0, (size_t)5 * PT_CTAS * 32 * sizeof(long long), s));
+    }
     SBA_TRY(dev_alloc(p, &p->pt_records, (size_t)std::max(1, lay.narrow.n_records) *
                                              (p->pt_schur_mma ? (size_t)PT_MMA_TILES * 64 + nc * 32 : (size_t)(2 * PT_RC * nc + nc) * 32)));
     SBA_TRY(dev_alloc(p, &p->red_partials, (size_t)std::max(NUM_SMS * 16, lay.n_cta + 1) * 8));

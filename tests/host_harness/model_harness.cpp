@@ -111,4 +111,22 @@ int hh_pattern_layout(const int* cam, const int* track_ptr, long long K, int M, 
     return 0;
 }
 
+
+// units of one kernel shape (which: 0 light, 1 wide, 2 narrow) for explicit warp counts; returns the number of units
+int hh_pattern_assignment(const int* cam, const int* track_ptr, long long K, int M, int N, int n_pts_fix, int n_cta, int w_light, int w_wide,
+                          int w_narrow, int nc, int rows_per_task, int which, int* units, int max_units, int* warp_unit0)
+{
+    PatternLayout L;
+    build_pattern_layout(cam, track_ptr, K, M, N, n_pts_fix, n_cta, w_light, w_wide, w_narrow, nc, rows_per_task, L);
+    if (!L.ok) return -1;
+    const PatternAssignment& A = which == 0 ? L.light : (which == 1 ? L.wide : L.narrow);
+    if ((int)A.units.size() > max_units) return -2;
+    std::copy((const int*)A.units.data(), (const int*)A.units.data() + 8 * A.units.size(), units);
+    std::copy(A.warp_unit0.begin(), A.warp_unit0.end(), warp_unit0);
+    return (int)A.units.size();
+}
+
+int hh_tile_cost(int L, int nc, int rows_per_task, int kind) { return pattern_tile_cost(L, nc, rows_per_task, kind); }
+int hh_unit_cost(int kind, int rows_per_task) { return pattern_unit_cost(kind, rows_per_task); }
+
 }
