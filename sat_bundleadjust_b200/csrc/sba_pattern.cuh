@@ -157,6 +157,22 @@ __device__ __forceinline__ double slot_reduce(double v, const LaneGeo& g)
     return v;
 }
 
+// the same for N values at once: the N shuffles of a step are independent and pipeline, where N separate calls would walk N
+// dependent shuffle chains one after the other (27 values at the end of every unit of the assembly kernel)
+template <int N>
+__device__ __forceinline__ void slot_reduce_n(double (&v)[N], const LaneGeo& g)
+{
+    for (int off = 1; off < g.T; off <<= 1) {
+        const unsigned delta = (unsigned)(off * g.L) & 31;
+        const bool take = g.on && g.t + off < g.T;
+        double o[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q) o[q] = __shfl_down_sync(0xffffffffu, v[q], delta);
+#pragma unroll
+        for (int q = 0; q < N; ++q) if (take) v[q] += o[q];
+    }
+}
+
 // The inputs of the NEXT tile of a unit are requested into L1 while the current tile is computed: a warp has only a
 // dozen tiles to walk, so an exposed HBM round trip per tile would dominate the kernel.  Addresses are arithmetic (no
 // index arrays), one prefetch per lane and array; lanes of a track share cache lines.
@@ -320,8 +336,7 @@ k_pt_assemble(PatView A, const double* __restrict__ x, const double* __restrict_
             __syncwarp();
         }
         // flush the camera blocks of the unit: sum over the track slots, then into the warp's accumulators
-#pragma unroll
-        for (int q = 0; q < NV; ++q) acc[q] = slot_reduce(acc[q], G);
+        slot_reduce_n<NV>(acc, G);
         if (G.on && G.t == 0) {
             double* dst = my_acc + G.cam * NV;
 #pragma unroll
@@ -741,8 +756,9 @@ k_pt_schur(PatView A, const double* __restrict__ x, const double* __restrict__ c
                 __syncwarp();
             }
             if (pass == 0) {
+                slot_reduce_n<NC>(accR, G);
 #pragma unroll
-                for (int r = 0; r < NC; ++r) rp[(2 * NA + r) * 32 + lane] = slot_reduce(accR[r], G);
+                for (int r = 0; r < NC; ++r) rp[(2 * NA + r) * 32 + lane] = accR[r];
             }
         }
     }
@@ -974,8 +990,9 @@ k_pt_schur_mma(PatView A, const double* __restrict__ x, const double* __restrict
             for (int q = 0; q < NTP; ++q)
                 if (pass * NTP + q < ntile) { rp[q * 64 + 2 * lane] = C[q][0]; rp[q * 64 + 2 * lane + 1] = C[q][1]; }
             if (pass == 0) {
+                slot_reduce_n<NC>(accR, G);
 #pragma unroll
-                for (int r = 0; r < NC; ++r) rp[(size_t)NTP * 64 + r * 32 + lane] = slot_reduce(accR[r], G);
+                for (int r = 0; r < NC; ++r) rp[(size_t)NTP * 64 + r * 32 + lane] = accR[r];
             }
         }
     }

@@ -89,12 +89,12 @@ inline int pattern_schur_passes(int L, int nc, int rows_per_task)
 inline int pattern_unit_cost(int kind, int rows_per_task)
 {
     if (kind == 2 && rows_per_task == 0) return 0;
-    return kind == 0 ? 2100 : (kind == 1 ? 10400 : 3100);
+    return kind == 0 ? 2100 : (kind == 1 ? 3300 : 3100);
 }
 inline int pattern_tile_cost(int L, int nc, int rows_per_task, int kind)
 {
     static const int light[11] = {0, 0, 5515, 6283, 6405, 7048, 7400, 7734, 7762, 8120, 8422};
-    static const int wide[11] = {0, 0, 5909, 5026, 4683, 4458, 4669, 4573, 4430, 4036, 4108};
+    static const int wide[11] = {0, 0, 5872, 5040, 4930, 4756, 4953, 4980, 4811, 4458, 4662};
     static const int narrow[11] = {0, 0, 4312, 4832, 6161, 5406, 6803, 6125, 10793, 9247, 10266};
     const int T = pattern_tile_tracks(L);
     if (kind == 2 && rows_per_task == 0) {          // evaluation once per pass + per track R fragment loads and one MMA per tile
@@ -103,7 +103,7 @@ inline int pattern_tile_cost(int L, int nc, int rows_per_task, int kind)
     }
     const int l = L < 2 ? 2 : L;
     if (kind == 0) return l <= 10 ? light[l] : 8422 + 300 * (l - 10);
-    if (kind == 1) return l <= 10 ? wide[l] : 4100;
+    if (kind == 1) return l <= 10 ? wide[l] : 4660;
     if (l <= 10) return narrow[l];
     // longer tracks (more than 10 cameras): one evaluation per pass plus the product rounds, scaled to meet the table at L = 10
     const int ntask = L * (L + 1) / 2 * ((nc + rows_per_task - 1) / rows_per_task);
