@@ -7,6 +7,8 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r
 timeout 600 python bench.py --workload rpc --steps 20 > gpurun_out/r02_bench_rpc.json 2> gpurun_out/r02_bench_rpc.err; echo "rpc exit $?"; tail -2 gpurun_out/r02_bench_rpc.err | cut -c1-300
 timeout 600 python bench.py --workload 5m --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_5m.json 2> gpurun_out/r02_bench_5m.err; echo "5m exit $?"
 timeout 600 python bench.py --workload cfg3full --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_cfg3full.json 2> gpurun_out/r02_bench_cfg3full.err; echo "cfg3full exit $?"
+timeout 600 python bench.py --workload rpcba --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_rpcba.json 2> gpurun_out/r02_bench_rpcba.err; echo "rpcba exit $?"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -2 gpurun_out/r02_pytest_gpu.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_under_ncu.json 2> /dev/null; echo "ncu list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_pt_|k_chol_fused' -s 8 -c 9 -o gpurun_out/r02_full_1m -f python tools/profile_iter.py 1m 3 > gpurun_out/ncu_full_1m.log 2>&1; echo "ncu full exit $?"
 (timeout 600 compute-sanitizer --tool memcheck python tools/profile_iter.py small 3; SBA_ENGINE=generic timeout 600 compute-sanitizer --tool memcheck python tools/profile_iter.py small 3; timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_triangulate.py -m gpu -x -q -k "edge or golden or oracle-perspective-10") > gpurun_out/r02_memcheck_raw.log 2>&1; grep -h "ERROR SUMMARY\|passed\|failed\|engine\|Error" gpurun_out/r02_memcheck_raw.log | cut -c1-200 > gpurun_out/r02_memcheck.log; cat gpurun_out/r02_memcheck.log
