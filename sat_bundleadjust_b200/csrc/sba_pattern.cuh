@@ -1,17 +1,21 @@
-// Pattern-major engine: the four fused passes of one trust-region iteration for problems whose reduced camera
-// system fits in shared memory (M * n_params <= PT_MAX_NS).  Layout and vocabulary: sba_pattern.h.
+// Pattern-major engine: the four fused passes of one trust-region iteration for problems with a small reduced camera system
+// (M * n_params <= PT_MAX_NS) whose tracks share their camera sets.  Layout and vocabulary: sba_pattern.h.
 //
 //   k_pt_assemble   trial point x + pa t1 + pb delta, residual, robust cost, analytic Jacobian and the blocks
 //                   V_i, g_i (per track, reduced inside the warp) and U_j, g_j (per camera, in registers over a work
-//                   unit) -- one evaluation per observation.  Doubles as the trial-cost evaluation of the step, so an
-//                   accepted step needs no further pass.                              (G1 + G2 of SURVEY.md 2.2)
+//                   unit, then in warp-private shared-memory accumulators) -- one evaluation per observation.  Doubles as
+//                   the trial-cost evaluation of the step, so an accepted step needs no further pass.   (G1 + G2 of SURVEY.md 2.2)
 //   k_pt_jvp1       x_scale update of the points, |g_h|^2 and |J_h g_h|^2 -> damping (scipy trf.py:485-490)
 //   k_pt_schur      damped point blocks inverted, Z_a = (Jc^T Jp) G^T staged in shared memory, all products
-//                   Z_a Z_b^T of a track accumulated in registers by fixed (camera pair, row chunk) lanes, flushed
-//                   once per unit into the CTA's shared-memory copy of S -- no Z in HBM, no pair lists    (G3)
+//                   Z_a Z_b^T of a track accumulated in registers by fixed (camera pair, row chunk) lanes; one record per
+//                   (unit, pass) in global memory, merged after a CTA barrier by one thread per (block, row) in unit order
+//                   into the CTA's partial of S -- no Z in HBM, no pair lists, no atomics                      (G3)
+//                   (k_pt_schur_mma: the same with the products on the FP64 tensor cores, opt-in, slower)
 //   k_pt_backsub    point steps from the camera step, and the Gram scalars of the 2-D subspace {g, gn}    (G6)
-// Every reduction has a fixed order (static unit -> warp assignment, ordered merges), so results are
-// reproducible bit for bit.  Included by sba_ba.cu only.
+//   k_pt_reduce_assemble / k_pt_reduce_schur   per-CTA partials -> [U | g_c | cost] / [S | rhs]; on several GPUs the all-reduce
+//                   over NVLink peer memory happens inside these kernels and inside the last CTA of k_pt_jvp1 / k_pt_backsub
+// Every reduction has a fixed order (static unit -> warp assignment, ordered merges, ranks summed in rank order), so results
+// are reproducible bit for bit.  Included by sba_ba.cu only.
 #pragma once
 #include "sba_comm.cuh"
 #include "sba_kernels.cuh"
@@ -23,7 +27,7 @@ constexpr int PT_CTAS = NUM_SMS;          // one persistent CTA per SM
 constexpr int PT_THREADS = 512;           // assemble (<= 128 registers)
 constexpr int PT_THREADS_LIGHT = 512;     // jvp1 / backsub
 constexpr int PT_THREADS_SCHUR = 384;     // schur (<= 168 registers)
-constexpr int PT_MAX_NS = 132;            // reduced camera system that still fits the shared-memory copy of S
+constexpr int PT_MAX_NS = 132;            // camera unknowns: bounds the warp-private camera accumulators of k_pt_assemble in shared memory
 constexpr int PT_RC = 3;                  // rows of a camera block per Schur task
 
 struct PatView {
