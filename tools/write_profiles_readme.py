@@ -53,7 +53,9 @@ def main():
             "| `r02_ncu_1m_selected_metrics.csv` | selected metrics of one `ncu --set full --import-source on` capture per kernel of the `1m` workload (`tools/summarize_profiles.py r02`) |",
             "| `r02_sass_pattern_kernels.txt` | `cuobjdump -sass` excerpts of the four pattern kernels (DFMA / LDS / SHFL mix, no local memory in the inner loops) |",
             "| `r02_fp64_peak.json`, `r02_dmma_issue_rate.txt` | measured FP64 peaks (`tools/fp64_peak.cu`: DFMA 33.9, DMMA 37.1 TFLOP/s) and DMMA issue rate vs occupancy (`tools/dmma_lat.cu`) |",
-            "| `r02_memcheck.log` | `compute-sanitizer --tool memcheck` over a solve of both engines and the triangulation kernels |", ""]
+            "| `r02_memcheck.log`, `r02_racecheck.log` | `compute-sanitizer` memcheck over a solve of both engines and the triangulation kernels (0 errors); racecheck + synccheck of the pattern engine and racecheck of the generic engine, dense and PCG (0 hazards) |",
+            "| `r02_bench_rpcba.json` | `bench.py --workload rpcba`: bundle adjustment with `cam_model='rpc'` (4 RPC cameras, 8e5 observations) |",
+            "| `r02_chol_time.log` | dense Cholesky solve alone, n = 30 ... 1800, with the stage clocks of the one-CTA kernel |", ""]
     b1 = load("r02_bench_n1.json")
     if b1:
         e, r, c = b1["e2e"], b1["roofline"], b1["cpu_baseline"]
