@@ -112,16 +112,25 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
     # The ranks must run the same engine and the same reduced-system solver (their exchange sequences differ), but each decides
     # from its own shard (tile fill, track lengths, table sizes): create, compare, and where they disagree re-create everybody
     # with the choice every shard supports (generic engine / PCG).
-    prob = DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank])
-    choice = torch.tensor([prob.engine == "pattern", prob.solver == "dense"], dtype=torch.int32, device="cuda")
+    create_error = None
+    try:
+        prob = DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank])
+        mine = [int(prob.engine == "pattern"), int(prob.solver == "dense")]
+    except Exception as exc:                           # agreed on below: no rank may be left waiting in a collective
+        create_error, prob, mine = exc, None, [-1, -1]
+    choice = torch.tensor(mine, dtype=torch.int32, device="cuda")
     lo, hi = choice.clone(), choice.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    lo_l = lo.tolist()
+    if min(lo_l) < 0:
+        if prob is not None:
+            prob.close()
+        raise create_error if create_error is not None else SbaError("the problem could not be created on another rank")
     if not torch.equal(lo, hi):
-        lo = lo.tolist()
         prob.close()
         prob = DeviceProblem(p, stream=stream, rank=rank, world_size=world, track_range=ranges[rank],
-                             engine="pattern" if lo[0] else "generic", solver="dense" if lo[1] else "pcg")
+                             engine="pattern" if lo_l[0] else "generic", solver="dense" if lo_l[1] else "pcg")
     with prob:
         t_create = time.perf_counter()
         prob.set_allreduce(hook)                       # NCCL fall-back for exchanges that do not fit the peer buffer
