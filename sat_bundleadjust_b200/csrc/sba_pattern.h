@@ -173,6 +173,7 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
     std::vector<int> t_lmax(nthr, 0), t_frozen(nthr, 0), t_bad(nthr, 0);
     auto scan = [&](int th) {
         const int i0 = (int)((long long)N * th / nthr), i1 = (int)((long long)N * (th + 1) / nthr);
+        int lmax = 0, frozen = 0;                       // thread-local: the per-thread slots share cache lines
         for (int i = i0; i < i1; ++i) {
             const int a0 = track_ptr_old[i], a1 = track_ptr_old[i + 1];
             uint64_t m = 0;
@@ -184,9 +185,11 @@ inline void build_pattern_layout(const int* cam, const int* track_ptr_old, long 
             }
             key[i] = m;
             aux[i] = (unsigned char)((i < n_pts_fix ? 0 : 1) | (a1 == a0 ? 2 : 0));
-            if (i < n_pts_fix && a1 > a0) t_frozen[th]++;
-            t_lmax[th] = std::max(t_lmax[th], a1 - a0);
+            if (i < n_pts_fix && a1 > a0) ++frozen;
+            lmax = std::max(lmax, a1 - a0);
         }
+        t_lmax[th] = lmax;
+        t_frozen[th] = frozen;
     };
     if (nthr == 1) scan(0);
     else {
