@@ -70,7 +70,7 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
 
     from . import ba_core
     from ._lib import SbaError
-    from .solver import DeviceProblem, initial_vars, n_common_params
+    from .solver import DeviceProblem, from_device_layout, initial_vars, n_common_params
 
     k_common = n_common_params(p)                  # COMMON_K: the caller's vector is [K | cameras | points] (ba_params.py:167-171)
     t_start = time.perf_counter()
@@ -170,8 +170,7 @@ def run_ba_optimization_distributed(p, ls_params=None, group=None):
     n_all, k_all = ncv + 3 * p.n_pts, sum(k_loc)
     x, err0, err1 = h[:n_all], h[n_all: n_all + k_all], h[n_all + k_all:]
     if k_common:                                                   # device layout -> [K | cameras | points]
-        cams = x[:ncv].reshape(p.n_cam, p.n_params)
-        x = np.concatenate([cams[0, p.n_params - k_common:], cams[:, : p.n_params - k_common].ravel(), x[ncv:]])
+        x = from_device_layout(x, k_common, p.n_params, p.n_cam)
     t_end = time.perf_counter()
     info["wall_s"] = {"prepare": t_prep - t_start, "create": t_create - t_prep, "connect": t_connect - t_create,
                       "solve": t_solve - t_connect, "close": t_close - t_solve, "gather": t_end - t_close}

@@ -53,6 +53,25 @@ def initial_vars(p):
     return x0
 
 
+def to_device_layout(v, n_common, n_params, n_cam):
+    """[K | cam_0[:c'] ... cam_M-1[:c'] | points] (ba_params.py:167-171) -> n_params slots per camera, the shared K in camera 0's."""
+    k, c, m = n_common, n_params, n_cam
+    v = np.asarray(v, dtype=np.float64)
+    x = np.zeros(v.size + (m - 1) * k)
+    cams = x[: m * c].reshape(m, c)
+    cams[:, : c - k] = v[k: k + m * (c - k)].reshape(m, c - k)
+    cams[0, c - k:] = v[:k]
+    x[m * c:] = v[k + m * (c - k):]
+    return x
+
+
+def from_device_layout(x, n_common, n_params, n_cam):
+    """Inverse of to_device_layout."""
+    k, c, m = n_common, n_params, n_cam
+    cams = np.asarray(x)[: m * c].reshape(m, c)
+    return np.concatenate([cams[0, c - k:], cams[:, : c - k].ravel(), np.asarray(x)[m * c:]])
+
+
 class DeviceProblem:
     """RAII wrapper of sba_problem_create / sba_problem_destroy."""
 
@@ -114,19 +133,10 @@ class DeviceProblem:
         self.close()
 
     def _to_device_layout(self, v):
-        """[K | cam_0[:c'] ... cam_M-1[:c'] | points] (ba_params.py:167-171) -> n_params slots per camera, K in camera 0's"""
-        k, c, m = self.n_common, self.n_params, self.n_cam
-        x = np.zeros(self.n_vars_device)
-        cams = x[: m * c].reshape(m, c)
-        cams[:, : c - k] = v[k: k + m * (c - k)].reshape(m, c - k)
-        cams[0, c - k:] = v[:k]
-        x[m * c:] = v[k + m * (c - k):]
-        return x
+        return to_device_layout(v, self.n_common, self.n_params, self.n_cam)
 
     def _from_device_layout(self, x):
-        k, c, m = self.n_common, self.n_params, self.n_cam
-        cams = x[: m * c].reshape(m, c)
-        return np.concatenate([cams[0, c - k:], cams[:, : c - k].ravel(), x[m * c:]])
+        return from_device_layout(x, self.n_common, self.n_params, self.n_cam)
 
     def _vars(self, x):
         """float64 device-layout vector (copy if needed) with the frozen points pinned to their initial values"""

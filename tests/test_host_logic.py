@@ -497,3 +497,17 @@ def test_sparse_scene_matches_dense_packing():
     assert (q.n_params, q.n_obs, q.n_cam, q.n_pts) == (r.n_params, r.n_obs, r.n_cam, r.n_pts)
     same = r.pts_ind[1:] == r.pts_ind[:-1]
     assert np.all(np.diff(r.pts_ind) >= 0) and np.all(r.cam_ind[1:][same] > r.cam_ind[:-1][same])
+
+
+def test_common_k_vector_layouts():
+    """COMMON_K: the caller's [K | cameras | points] vector (ba_params.py:167-171) <-> the device's n_params slots per camera."""
+    from sat_bundleadjust_b200.solver import from_device_layout, to_device_layout
+    rng = np.random.default_rng(0)
+    for k, c, m, n_pts in ((5, 11, 4, 7), (3, 8, 3, 5), (0, 6, 4, 3)):
+        v = rng.standard_normal(k + m * (c - k) + 3 * n_pts)
+        x = to_device_layout(v, k, c, m)
+        assert x.size == m * c + 3 * n_pts
+        cams = x[: m * c].reshape(m, c)
+        assert np.array_equal(cams[0, c - k:], v[:k]) and np.all(cams[1:, c - k:] == 0.0)
+        assert np.array_equal(cams[:, : c - k].ravel(), v[k: k + m * (c - k)]) and np.array_equal(x[m * c:], v[k + m * (c - k):])
+        assert np.array_equal(from_device_layout(x, k, c, m), v)
