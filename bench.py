@@ -465,7 +465,7 @@ def run_b200_arm(args):
                        "n_params_per_cam": int(c), "loss": LS["loss"], "tracks_per_gpu": int(N_loc), "engine": engine,
                        "parallelism": "tracks sharded over %d GPU(s), cameras replicated" % world,
                        "exchange": ("none" if world == 1 else os.environ.get("SBA_COMM", "peer") +
-                                    (" (per iteration: [U|g_c|cost], 5 scalars, [S|rhs], 7 scalars)" if engine == "pattern"
+                                    (" (per iteration: [U|g_c|cost], 21 scalars, [S|rhs] in block-upper form, 7 scalars; one-shot all-reduces over NVLink peer memory inside the producing kernels, no launch of their own)" if engine == "pattern"
                                      else " (per iteration: [U|g_c], [S|rhs], 5 scalar groups)")),
                        "l2": "256 MiB scratch overwritten between timed iterations (outside the event pairs)"},
             "lm_iters_per_s": K / (iter_ms * 1e-3),
