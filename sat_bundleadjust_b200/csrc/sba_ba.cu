@@ -840,6 +840,22 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
     HostIndex hidx;
     const bool try_pattern = d->engine != 2 && !(p->use_pcg && d->engine == 0) && pattern_engine_applicable(p, d->engine == 1);
     if (d->engine == 1 && !try_pattern) { set_error("the pattern engine does not apply to this problem (size, n_params or shared calibration)"); return SBA_E_INVALID; }
+    // The two big uploads of the pattern engine (observations 16 B and weights 8 B per observation, from pageable host memory: the
+    // driver stages them synchronously, ~2.4 ms per million observations) do not depend on the layout: a helper thread issues them
+    // on the problem's stream while this thread builds the host index and the pattern layout.
+    std::thread uploader;
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{uploader};
+    cudaError_t up_err = cudaSuccess;
+    if (try_pattern) {
+        SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
+        SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
+        p->pt_obs_uploaded = true;
+        uploader = std::thread([&up_err, p, d, K, s]() {
+            up_err = cudaSetDevice(p->device);
+            if (up_err == cudaSuccess) up_err = cudaMemcpyAsync(p->r_out, d->pts2d, 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s);
+            if (up_err == cudaSuccess) up_err = cudaMemcpyAsync(p->err_out, d->pts2d_w, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s);
+        });
+    }
     int irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx, try_pattern);
     if (irc == 1) { set_error("cam_ind / pts_ind out of range"); return SBA_E_INVALID; }
     if (irc == 2) { set_error("pts_ind must be non-decreasing (observations sorted by track)"); return SBA_E_INVALID; }
@@ -861,11 +877,14 @@ static int problem_create_impl(sba_problem* p, const sba_problem_desc* d)
             lay.ok = false;
             lay.why = "visibility patterns too diverse (tile fill " + std::to_string(lay.fill) + ")";
         }
+        if (uploader.joinable()) uploader.join();
+        if (up_err != cudaSuccess) { set_error(std::string("upload of the observations: ") + cudaGetErrorString(up_err)); return SBA_E_CUDA; }
         if (lay.ok) {
             const int rc = pattern_create(p, d, hidx, lay);
             stamp("pattern uploads + state");
             return rc;
         }
+        p->pt_obs_uploaded = false;                    // the generic engine uploads into its own layout
         if (timing) fprintf(stderr, "[sba create] pattern engine not applicable: %s\n", lay.why.c_str());
         if (d->engine == 1) { set_error(("the pattern engine does not apply: " + lay.why).c_str()); return SBA_E_INVALID; }
         irc = build_host_index(d->cam_ind, d->pts_ind, K, M, N, CHUNK, 8, hidx);       // the generic engine needs the camera-major tables too

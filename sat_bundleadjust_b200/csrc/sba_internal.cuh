@@ -169,6 +169,7 @@ struct sba_problem {
     int pt_n_cta = 0;
     double *V2 = nullptr, *g2 = nullptr, *camsys2 = nullptr;        // second buffer set (trial point)
     long long* pt_cycles = nullptr;                                 // SBA_PT_CYCLES=1: per-warp clocks of the last launch of each kernel shape (3 x 148 x 32)
+    bool pt_obs_uploaded = false;                                   // observations / weights already uploaded to r_out / err_out by the helper thread of problem creation
     bool pt_schur_mma = false;                                      // K3 variant (SBA_PT_SCHUR=mma): FP64 tensor-core Gram tiles instead of the DFMA task kernel -- measured slower, kept as a switch
     double *dsq = nullptr, *idsq = nullptr;                         // (n) squared column scales of the points and their reciprocals
     double *dsqc = nullptr, *dsqc2 = nullptr, *idsqc = nullptr, *idsqc2 = nullptr;   // (ns) the same for the cameras, double-buffered

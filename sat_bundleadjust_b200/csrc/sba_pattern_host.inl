@@ -415,16 +415,20 @@ static int pattern_create(sba_problem* p, const sba_problem_desc* d, const HostI
     }
     // warp tiles of the generic per-track kernels are not used by this engine
     p->n_tiles = 0;
-    SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
-    SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
+    if (!p->pt_obs_uploaded) {
+        SBA_TRY(dev_alloc(p, &p->r_out, 2 * (size_t)K));
+        SBA_TRY(dev_alloc(p, &p->err_out, (size_t)K));
+    }
     SBA_TRY(dev_alloc(p, &p->osc, 2 * (size_t)K)); SBA_TRY(dev_alloc(p, &p->osc2, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->r_int, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->e_int, (size_t)K));
     // observations and weights: uploaded in the caller's order, gathered into the internal order on the device
     SBA_TRY(dev_alloc(p, &p->pts2d, 2 * (size_t)K));
     SBA_TRY(dev_alloc(p, &p->w, (size_t)K));
-    SBA_CUDA(cudaMemcpyAsync(p->r_out, d->pts2d, 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
-    SBA_CUDA(cudaMemcpyAsync(p->err_out, d->pts2d_w, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (!p->pt_obs_uploaded) {      // else: already on their way (issued by problem_create_impl's helper thread on this stream)
+        SBA_CUDA(cudaMemcpyAsync(p->r_out, d->pts2d, 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+        SBA_CUDA(cudaMemcpyAsync(p->err_out, d->pts2d_w, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
     k_pt_obs_in<<<grid_for(2 * K, 256, NUM_SMS * 8), 256, 0, s>>>(p->r_out, p->obs_new2old, K, 2, p->pts2d);
     SBA_CUDA(cudaGetLastError());
     k_pt_obs_in<<<grid_for(K, 256, NUM_SMS * 8), 256, 0, s>>>(p->err_out, p->obs_new2old, K, 1, p->w);
